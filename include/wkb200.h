@@ -1,0 +1,215 @@
+/*
+ * wkb200.h - C ABI of libwkb200.so: the Blackwell (sm_100a) implementation of WhisperKit's hot path
+ *            PCM -> log-mel -> audio encoder -> KV-cached text decoder -> logits filters -> sampler.
+ *
+ * Every entry point is what a Swift (or Python ctypes) host binds to replace one member of the
+ * reference's protocol surface (paths relative to the WhisperKit repo):
+ *
+ *   wk_mel                  FeatureExtracting.logMelSpectrogram   Sources/WhisperKit/Core/FeatureExtractor.swift:13-17,40-56
+ *   wk_encode               AudioEncoding.encodeFeatures          Sources/WhisperKit/Core/AudioEncoder.swift:10-18,50-63
+ *   wk_session_create/reset TextDecoding.prepareDecoderInputs     Sources/WhisperKit/Core/TextDecoder.swift:109-161
+ *   wk_build_prompt         TextDecoding.prefillDecoderInputs     Sources/WhisperKit/Core/TextDecoder.swift:163-216
+ *   wk_decode_step          TextDecoding.predictLogits            Sources/WhisperKit/Core/TextDecoder.swift:361-418
+ *   wk_filter_sample        LogitsFiltering.filterLogits (x4) +   Sources/WhisperKit/Core/Text/LogitsFilter.swift:8-276
+ *                           TokenSampling.update                  Sources/WhisperKit/Core/Text/TokenSampler.swift:8-11,215-240
+ *   wk_decode_text          TextDecoding.decodeText (+ sampler    Sources/WhisperKit/Core/TextDecoder.swift:541-855
+ *                           finalize, DecodingFallback)           Sources/WhisperKit/Core/Models.swift:357-381
+ *   wk_transcribe_windows   the per-window body of                Sources/WhisperKit/Core/TranscribeTask.swift:116-278
+ *                           TranscribeTask.run, batched like      Sources/WhisperKit/Core/WhisperKit.swift:716-812
+ *                           WhisperKit.transcribeWithOptions
+ *   wk_model_info           melCount/windowSamples/embedSize/     FeatureExtractor.swift:24-38, AudioEncoder.swift:24-38,
+ *                           logitsSize/kvCache* properties        TextDecoder.swift:313-331
+ *
+ * Conventions: plain C types only; every function returns a wk_status (0 = ok, negative = error, mapped
+ * 1:1 onto WhisperError cases, Sources/WhisperKit/Utilities/WhisperError.swift:6-19); the message of the
+ * last error on the calling thread is wk_last_error().  Host pointers may be pageable or pinned; pointers
+ * documented as "host or device" are resolved with cudaPointerGetAttributes.  Handles are not thread-safe
+ * individually; a wk_model may be shared by several wk_sessions (one per concurrent worker, mirroring
+ * the per-task DecodingInputs of TranscribeTask.swift:83).  There is NO CPU fallback: every compute entry
+ * point fails with WK_ERR_MODELS_UNAVAILABLE if no sm_100 device is present.
+ */
+#ifndef WKB200_H
+#define WKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t wk_status;
+enum {
+    WK_OK = 0,
+    WK_ERR_INVALID_ARGUMENT = -1,       /* (no Swift twin: argument validation)             */
+    WK_ERR_MODELS_UNAVAILABLE = -2,     /* WhisperError.modelsUnavailable                    */
+    WK_ERR_AUDIO_PROCESSING_FAILED = -3,/* WhisperError.audioProcessingFailed                */
+    WK_ERR_PREPARE_DECODER_INPUTS = -4, /* WhisperError.prepareDecoderInputsFailed           */
+    WK_ERR_DECODING_LOGITS_FAILED = -5, /* WhisperError.decodingLogitsFailed                 */
+    WK_ERR_DECODING_FAILED = -6,        /* WhisperError.decodingFailed                       */
+    WK_ERR_TRANSCRIPTION_FAILED = -7,   /* WhisperError.transcriptionFailed                  */
+    WK_ERR_CUDA = -8                    /* CUDA runtime/driver failure (message has detail)  */
+};
+
+typedef struct wk_model wk_model;
+typedef struct wk_session wk_session;
+typedef struct wk_tensor wk_tensor;
+
+enum { WK_DTYPE_F32 = 0, WK_DTYPE_F16 = 1, WK_DTYPE_BF16 = 2, WK_DTYPE_I32 = 3 };
+
+/* Model dimensions.  The reference reads these off the CoreML model descriptions at run time
+ * (TextDecoder.swift:313-331, AudioEncoder.swift:24-38, FeatureExtractor.swift:24-38). */
+typedef struct wk_model_config {
+    int32_t n_mels;      /* 80 or 128 */
+    int32_t d_model;     /* embedSize */
+    int32_t n_heads;     /* head dim must be 64 */
+    int32_t enc_layers;
+    int32_t dec_layers;
+    int32_t vocab;       /* logitsSize */
+    int32_t n_audio_ctx; /* 1500 */
+    int32_t n_text_ctx;  /* 448 (positional table); kv_max_len is 224 = Constants.maxTokenContext */
+    int32_t dtype;       /* WK_DTYPE_BF16 (default) or WK_DTYPE_F16: storage/MMA-input type; accumulation is f32 */
+    int32_t max_batch;   /* windows processed per encoder/decoder pass (workspace sizing) */
+} wk_model_config;
+
+typedef struct wk_model_info {
+    int32_t n_mels, n_audio_ctx, d_model, n_heads, enc_layers, dec_layers, vocab;
+    int32_t kv_embed_dim;   /* kvCacheEmbedDim = dec_layers * d_model */
+    int32_t kv_max_len;     /* kvCacheMaxSequenceLength = 224 */
+    int32_t window_samples; /* 480000 */
+    int32_t has_alignment_heads;
+    int32_t is_multilingual; /* logitsSize != 51864 (ModelUtilities.swift:124-126) */
+    int32_t dtype, max_batch;
+} wk_model_info;
+
+/* SpecialTokens (Models.swift:1111-1149) - supplied by the host tokenizer. */
+typedef struct wk_special_tokens {
+    int32_t end_token, english_token, no_speech_token, no_timestamps_token, special_token_begin,
+        start_of_previous_token, start_of_transcript_token, time_token_begin, transcribe_token, translate_token,
+        whitespace_token;
+} wk_special_tokens;
+
+/* DecodingOptions mirror (Configurations.swift:155-247), fields the hot path reads.
+ * "has_*" = Swift optional is non-nil. */
+typedef struct wk_decode_opts {
+    int32_t task_translate;       /* task == .translate */
+    int32_t language_token;       /* id of "<|xx|>" (tokenizer lookup done by the host); <0 -> english_token */
+    float temperature;            /* 0 = greedy argmax; >0 = top-k multinomial (TokenSampler.swift:57-73) */
+    int32_t sample_length;        /* default 224 */
+    int32_t top_k;                /* default 5 */
+    int32_t use_prefill_prompt;   /* default 1 */
+    int32_t without_timestamps;   /* default 0 */
+    int32_t suppress_blank;       /* default 0 */
+    const int32_t* suppress_tokens; int32_t n_suppress_tokens;
+    const int32_t* prompt_tokens;   int32_t n_prompt_tokens;   /* n < 0 -> nil */
+    const int32_t* prefix_tokens;   int32_t n_prefix_tokens;   /* n < 0 -> nil */
+    int32_t has_compression_ratio_threshold; float compression_ratio_threshold; /* 2.4 */
+    int32_t has_logprob_threshold;           float logprob_threshold;           /* -1.0 */
+    int32_t has_first_token_logprob_threshold; float first_token_logprob_threshold; /* -1.5 */
+    int32_t has_no_speech_threshold;         float no_speech_threshold;         /* 0.6 */
+    uint64_t seed;                /* Philox seed for temperature > 0 (the reference uses Float.random) */
+} wk_decode_opts;
+
+/* Per-window DecodingResult (Models.swift:383-439) in flat arrays; tokens = SOT..EOT slice. */
+typedef struct wk_decode_result {
+    int32_t n_tokens;                 /* filteredTokens.count */
+    int32_t tokens[226];
+    float token_logprobs[226];
+    float avg_logprob;
+    float compression_ratio;
+    float temperature;
+    int32_t needs_fallback;           /* DecodingFallback.needsFallback (0 if fallback == nil) */
+    int32_t fallback_reason;          /* 0 nil, 1 firstTokenLogProbThreshold, 2 silence, 3 compressionRatio, 4 logProb */
+    int32_t first_token_logprob_too_low;
+    int32_t n_current_tokens;         /* currentTokens.count when the loop ended (before finalize) */
+    int32_t steps;                    /* decoder forward passes run for this window */
+} wk_decode_result;
+
+const char* wk_last_error(void);
+const char* wk_version(void);
+/* 1 if a compute-capability 10.x device is visible. */
+int32_t wk_device_available(void);
+
+/* ---- model ---- */
+void wk_default_config(const char* variant /* "tiny.en","large-v3","large-v3-turbo","distil-large-v3" */, wk_model_config* out);
+wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model** out);
+/* HuggingFace parameter names ("model.encoder.layers.0.self_attn.q_proj.weight", ...); data host or device. */
+wk_status wk_model_set_tensor(wk_model* m, const char* name, const void* data, int32_t dtype, const int64_t* shape, int32_t ndim);
+wk_status wk_model_finalize(wk_model* m);
+/* Seeded synthetic weights generated on the device (benchmarks: no checkpoints are available offline). */
+wk_status wk_model_init_random(wk_model* m, uint64_t seed, float std);
+wk_status wk_model_info_get(const wk_model* m, wk_model_info* out);
+void wk_model_free(wk_model* m);
+
+/* ---- tensors (opaque device buffers passed mel -> encoder -> decoder without touching the host) ---- */
+wk_status wk_tensor_shape(const wk_tensor* t, int64_t* shape4, int32_t* ndim, int32_t* dtype);
+/* Copies to the host in the REFERENCE layout as f32: mel -> [B, nMels, 3000]; encoder output -> [B, d, 1500]. */
+wk_status wk_tensor_to_host(const wk_tensor* t, float* dst, int64_t dst_elems);
+void wk_tensor_free(wk_tensor* t);
+
+/* ---- FeatureExtracting ---- */
+/* pcm: n_windows rows of `stride` floats (host or device); samples_per_window[i] <= 480000 valid samples
+ * (NULL = all 480000); the rest of the window is zero-padded (padOrTrimAudio, AudioProcessor.swift:151-174). */
+wk_status wk_mel(wk_model* m, const float* pcm, int64_t n_windows, int64_t stride, const int32_t* samples_per_window, wk_tensor** mel_out);
+
+/* ---- AudioEncoding ---- */
+wk_status wk_encode(wk_model* m, const wk_tensor* mel, wk_tensor** enc_out);
+
+/* ---- TextDecoding ---- */
+wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out);
+void wk_session_free(wk_session* s);
+/* Bind encoder output for `batch` windows: computes the per-layer cross-attention K/V cache. */
+wk_status wk_session_set_encoder_output(wk_session* s, const wk_tensor* enc);
+/* Zero caches/masks (prepareDecoderInputs / DecodingInputs.reset). */
+wk_status wk_session_reset(wk_session* s);
+/* prefillDecoderInputs: builds initialPrompt into out (capacity cap); returns length in *n. */
+wk_status wk_build_prompt(const wk_model* m, const wk_special_tokens* st, const wk_decode_opts* opts, int32_t use_options, int32_t* out, int32_t cap, int32_t* n);
+/* predictLogits for every bound window: input_ids[B], cache_length[B] (host) -> logits [B, vocab] f32 (host, may be NULL). */
+wk_status wk_decode_step(wk_session* s, const int32_t* input_ids, const int32_t* cache_length, float* logits_out);
+/* Filters + sampler alone (parity entry): logits [B, vocab] f32 host; tokens [B, ld_tokens], n_tokens[B] = currentTokens;
+ * sample_begin_ts = TimestampRulesFilter.sampleBegin (<0: filter absent), sample_begin_blank = SuppressBlankFilter.sampleBegin
+ * (<0: absent); language_tokens != NULL adds LanguageLogitsFilter(sampleBegin = language_sample_begin).
+ * Writes token_out[B], logprob_out[B] and (optional) the masked logits back into filtered_out [B, vocab]. */
+wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_decode_opts* opts, int32_t is_multilingual,
+                           const float* logits, int32_t batch, int32_t vocab, const int32_t* tokens, int32_t ld_tokens,
+                           const int32_t* n_tokens, int32_t sample_begin_ts, int32_t sample_begin_blank,
+                           const int32_t* language_tokens, int32_t n_language_tokens, int32_t language_sample_begin,
+                           int32_t* token_out, float* logprob_out, float* filtered_out);
+/* decodeText for every bound window with one shared prompt (device-resident loop: no per-token host round trip).
+ * results: array of `batch` wk_decode_result. */
+wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* opts,
+                         const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
+/* Device logits of the last step, copied to host (debug / parity). */
+wk_status wk_session_last_logits(wk_session* s, float* logits_out);
+
+/* ---- whole hot path: host PCM in, token IDs out (TranscribeTask.run body, batched) ---- */
+wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_host /* host (pageable/pinned) or device */, int64_t n_windows, int64_t stride,
+                                const int32_t* samples_per_window, const wk_special_tokens* st, const wk_decode_opts* opts,
+                                const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
+
+/* ---- instrumentation ---- */
+/* Number of kernels launched by this library on the calling process since the last reset. */
+int64_t wk_kernel_launch_count(int32_t reset);
+/* Last-run stage timings in ms, TranscriptionTimings buckets (Models.swift:730-776):
+ * [0] logmels [1] encoding [2] crossKV [3] decodingLoop [4] h2d [5] d2h */
+wk_status wk_last_timings(wk_model* m, float* ms6);
+/* Stream all work is enqueued on (cudaStream_t as void*), for CUDA-event timing by the host harness. */
+void* wk_model_stream(wk_model* m);
+
+/* ---- kernel-level test/bench hooks (used by tests/ and bench.py; device pointers) ---- */
+/* C[M,N] = A[M,K] * W[N,K]^T (+bias) with the tcgen05 GEMM; out_dtype WK_DTYPE_BF16/F16/F32. */
+wk_status wk_test_gemm(wk_model* m, const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
+                       int32_t in_dtype, int32_t out_dtype, int32_t gelu, int32_t simt_reference);
+/* Same product through the decoder's swap-AB split-K path: out f32 [rows_x, N]. */
+wk_status wk_test_gemm_splitk(wk_model* m, const void* w, const void* x, float* out, int32_t N, int32_t rows_x, int32_t K, int32_t in_dtype, int32_t splits);
+/* Encoder attention on packed qkv [B*T, 3*d] -> out [B*T, d]. */
+wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, int32_t T, int32_t n_heads, int32_t dtype);
+
+/* Average device time (ms) of one launch of a named hot kernel on the live buffers, plus its algorithmic work
+ * (bytes for HBM-bound kernels, FLOPs for tensor-bound ones): 0 decoder cross-attention, 1 encoder FC1 GEMM,
+ * 2 log-mel, 3 encoder attention, 4 decoder QKV swap-AB GEMM, 5 encoder QKV GEMM.  Used by bench.py's roofline. */
+wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t batch, int32_t iters, float* ms_out, double* work_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WKB200_H */

@@ -1,0 +1,187 @@
+"""Kernel-level parity tests on the B200 (through the C ABI test hooks of libwkb200.so).
+References: torch fp32 on the same 16-bit-rounded inputs (floating-point kernels), the CPU oracle (mel),
+the reference's own known-answer vectors (filters)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import whisperkit_b200 as wk  # noqa: E402
+from whisperkit_b200 import _lib  # noqa: E402
+from oracle import decode_ref as D  # noqa: E402
+from oracle import mel_ref  # noqa: E402
+from tests import kat_vectors as K  # noqa: E402
+
+TD = {"bf16": (torch.bfloat16, _lib.WK_DTYPE_BF16), "f16": (torch.float16, _lib.WK_DTYPE_F16)}
+
+
+@pytest.fixture(scope="module")
+def toy():
+    m = wk.Model("toy", max_batch=4)
+    m.init_random(seed=3)
+    yield m
+    m.close()
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+def p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K,gelu,out32", [
+    (128, 256, 64, 0, 1), (256, 256, 128, 0, 0), (1000, 384, 128, 1, 0), (3000, 1280, 1280, 1, 0),
+    (4500, 3840, 1280, 0, 0), (777, 1280, 5120, 0, 1), (130, 128, 64, 0, 1),
+])
+def test_gemm_tcgen05_vs_torch(toy, dt, M, N, K, gelu, out32):
+    tdt, wdt = TD[dt]
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(tdt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(tdt)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out32 else tdt)
+    _sync()
+    wk._lib.check(toy.lib.wk_test_gemm(toy.handle, p(a), p(w), p(bias), p(out), M, N, K, wdt,
+                                       _lib.WK_DTYPE_F32 if out32 else wdt, gelu, 0))
+    torch.cuda.current_stream().synchronize()
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    tol = 2e-5 * scale * max(1, K / 256) if out32 else (8e-3 if dt == "bf16" else 1e-3) * scale
+    assert err <= tol, f"max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("N,rows,Kd,splits", [(1280, 64, 1280, 0), (1280, 16, 1280, 20), (3840, 64, 1280, 5),
+                                              (1280, 48, 5120, 16), (51866, 32, 256, 1), (384, 16, 384, 0)])
+def test_gemm_swap_ab_splitk(toy, N, rows, Kd, splits):
+    g = torch.Generator(device="cuda").manual_seed(N + rows)
+    w = (torch.randn(N, Kd, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    x = (torch.randn(rows, Kd, device="cuda", generator=g)).to(torch.bfloat16)
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    _sync()
+    wk._lib.check(toy.lib.wk_test_gemm_splitk(toy.handle, p(w), p(x), p(out), N, rows, Kd, _lib.WK_DTYPE_BF16, splits))
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    err = (out - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err <= 3e-5 * ref.abs().max().item() * max(1, Kd / 256), err
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (1, 200, 1), (3, 77, 2)])
+def test_encoder_attention_vs_torch(toy, dt, B, T, H):
+    tdt, wdt = TD[dt]
+    dm = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B * T + H)
+    qkv = (torch.randn(B * T, 3 * dm, device="cuda", generator=g)).to(tdt)
+    out = torch.zeros(B * T, dm, device="cuda", dtype=tdt)
+    _sync()
+    wk._lib.check(toy.lib.wk_test_attention(toy.handle, p(qkv), p(out), B, T, H, wdt))
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(dm, dim=1)]
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v
+    ref = ref.transpose(1, 2).reshape(B * T, dm)
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-2 if dt == "bf16" else 3e-3  # P is rounded to 16 bits before P.V; outputs are 16-bit
+    assert err <= tol * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("variant,n_mels", [("toy", 80), ("toy128", 128)])
+def test_log_mel_vs_oracle(variant, n_mels):
+    m = wk.Model(variant, max_batch=4)
+    fe = wk.FeatureExtractor(m)
+    assert fe.melCount == n_mels and fe.windowSamples == 480000
+    pcm = np.stack([mel_ref.synthetic_pcm(0), mel_ref.synthetic_pcm(1), np.zeros(480000, np.float32),
+                    mel_ref.synthetic_pcm(2)])
+    nv = [480000, 480000, 480000, 176000]
+    pcm[3, 176000:] = 0
+    # host input with explicit valid lengths (padOrTrim folded into the kernel)
+    got = fe.logMelSpectrogram(pcm, samples_per_window=nv).numpy()
+    assert got.shape == (4, n_mels, 3000)
+    for i in range(4):
+        ref = mel_ref.log_mel(pcm[i], n_mels)
+        err = np.abs(got[i] - ref).max()
+        # north_star tolerance: log-mel within 1e-3 (relative to the tensor scale, which is O(1)); f16 output
+        assert err <= 1e-3 * max(1.0, np.abs(ref).max()), (i, err)
+    # device-resident input, no lengths
+    dev = torch.from_numpy(pcm[:2]).cuda()
+    got2 = fe.logMelSpectrogram(dev).numpy()
+    np.testing.assert_array_equal(got2, got[:2])
+    m.close()
+
+
+def _f16(v):
+    return np.array(v, dtype=np.float16).astype(np.float32)
+
+
+def test_filters_reference_kats_on_device(toy):
+    """UnitTests.swift:1982-2115 through the fused CUDA filter+sampler kernel."""
+    for name, sup, logits, tokens, exp in K.SUPPRESS_TOKENS:
+        st = wk.SpecialTokens(specialTokenBegin=100)
+        _, _, f = wk.filter_and_sample(toy, _f16(logits), [tokens], st, wk.DecodingOptions(suppressTokens=sup))
+        np.testing.assert_array_equal(f[0], _f16(exp), err_msg=name)
+    for name, eot, ws, sb, logits, tokens, exp in K.SUPPRESS_BLANK:
+        st = wk.SpecialTokens.from_any(D.SpecialTokens.test_default(endToken=eot, whitespaceToken=ws))
+        _, _, f = wk.filter_and_sample(toy, _f16(logits), [tokens], st, blankSampleBegin=sb)
+        np.testing.assert_array_equal(f[0], _f16(exp), err_msg=name)
+    for name, langs, dim, sb, logits, tokens, exp in K.LANGUAGE:
+        st = wk.SpecialTokens.from_any(D.SpecialTokens.test_default())
+        _, _, f = wk.filter_and_sample(toy, _f16(logits), [tokens], st, languageTokens=langs, languageSampleBegin=sb)
+        np.testing.assert_array_equal(f[0], _f16(exp), err_msg=name)
+    for name, multi, sb, logits, tokens, exp in K.TIMESTAMP_RULES:
+        st = wk.SpecialTokens.from_any(D.SpecialTokens.test_default(**K.TS_SPECIAL))
+        tok, lp, f = wk.filter_and_sample(toy, _f16(logits), [tokens], st, isModelMultilingual=multi, timestampSampleBegin=sb)
+        np.testing.assert_array_equal(f[0], _f16(exp), err_msg=name)
+        # sampler on the filtered row == oracle GreedyTokenSampler
+        s = D.GreedyTokenSampler(0.0, st.endToken, D.DecodingOptions())
+        r = s.update([], _f16(exp), [])
+        assert tok[0] == r.tokens[-1], name
+        assert abs(lp[0] - r.logProbs[-1]) < 1e-5, name
+
+
+def test_filter_sampler_random_rows_vs_oracle(toy):
+    """Bit-exact token choice vs the oracle on random full-vocabulary rows with random token histories."""
+    rng = np.random.default_rng(7)
+    V = 51866
+    st_o = D.SpecialTokens.large_v3()
+    st = wk.SpecialTokens.from_any(st_o)
+    B = 24
+    logits = rng.standard_normal((B, V)).astype(np.float32) * 2
+    toks = []
+    for b in range(B):
+        prompt = [st_o.startOfTranscriptToken, st_o.englishToken, st_o.transcribeToken, st_o.timeTokenBegin]
+        n = int(rng.integers(0, 12))
+        hist = []
+        for _ in range(n):
+            if rng.random() < 0.4:
+                hist.append(int(st_o.timeTokenBegin + rng.integers(0, 1500)))
+            else:
+                hist.append(int(rng.integers(0, 50000)))
+        if b % 3 == 0:
+            logits[b, st_o.timeTokenBegin:] += 6.0  # make the timestamp mass win
+        toks.append(prompt + hist)
+    opts = D.DecodingOptions(suppressTokens=[5, 17, 300], suppressBlank=True)
+    tok, lp, filt = wk.filter_and_sample(toy, logits, toks, st, wk.DecodingOptions(suppressTokens=[5, 17, 300]),
+                                         timestampSampleBegin=4, blankSampleBegin=4)
+    for b in range(B):
+        fs = [D.SuppressBlankFilter(st_o, 4), D.SuppressTokensFilter([5, 17, 300]),
+              D.TimestampRulesFilter(st_o, 4, None, True)]
+        row = logits[b].copy()
+        for f in fs:
+            row = f.filterLogits(row, toks[b])
+        np.testing.assert_array_equal(np.isneginf(filt[b]), np.isneginf(row), err_msg=f"row {b}")
+        r = D.GreedyTokenSampler(0.0, st_o.endToken, opts).update([], row, [])
+        assert tok[b] == r.tokens[-1], b
+        assert abs(lp[b] - r.logProbs[-1]) < 2e-4, (b, lp[b], r.logProbs[-1])

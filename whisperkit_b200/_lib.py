@@ -1,0 +1,140 @@
+"""ctypes binding of libwkb200.so (the C ABI in include/wkb200.h).
+
+This is the binding a reference-side host would write (Swift: `@_silgen_name` / module map; here: ctypes).
+Loading fails loudly when the shared library has not been built - there is no Python or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libwkb200.so")
+
+WK_DTYPE_F32, WK_DTYPE_F16, WK_DTYPE_BF16, WK_DTYPE_I32 = 0, 1, 2, 3
+
+STATUS_NAMES = {
+    0: "ok", -1: "invalidArgument", -2: "modelsUnavailable", -3: "audioProcessingFailed",
+    -4: "prepareDecoderInputsFailed", -5: "decodingLogitsFailed", -6: "decodingFailed",
+    -7: "transcriptionFailed", -8: "cudaError",
+}
+
+
+class WhisperError(RuntimeError):
+    """Mirrors WhisperError (Sources/WhisperKit/Utilities/WhisperError.swift:6-19)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+        self.case = STATUS_NAMES.get(status, str(status))
+
+
+class wk_model_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mels", "d_model", "n_heads", "enc_layers", "dec_layers", "vocab",
+                                         "n_audio_ctx", "n_text_ctx", "dtype", "max_batch")]
+
+
+class wk_model_info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mels", "n_audio_ctx", "d_model", "n_heads", "enc_layers", "dec_layers",
+                                         "vocab", "kv_embed_dim", "kv_max_len", "window_samples",
+                                         "has_alignment_heads", "is_multilingual", "dtype", "max_batch")]
+
+
+class wk_special_tokens(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("end_token", "english_token", "no_speech_token", "no_timestamps_token",
+                                         "special_token_begin", "start_of_previous_token",
+                                         "start_of_transcript_token", "time_token_begin", "transcribe_token",
+                                         "translate_token", "whitespace_token")]
+
+
+class wk_decode_opts(C.Structure):
+    _fields_ = [
+        ("task_translate", C.c_int32), ("language_token", C.c_int32), ("temperature", C.c_float),
+        ("sample_length", C.c_int32), ("top_k", C.c_int32), ("use_prefill_prompt", C.c_int32),
+        ("without_timestamps", C.c_int32), ("suppress_blank", C.c_int32),
+        ("suppress_tokens", C.POINTER(C.c_int32)), ("n_suppress_tokens", C.c_int32),
+        ("prompt_tokens", C.POINTER(C.c_int32)), ("n_prompt_tokens", C.c_int32),
+        ("prefix_tokens", C.POINTER(C.c_int32)), ("n_prefix_tokens", C.c_int32),
+        ("has_compression_ratio_threshold", C.c_int32), ("compression_ratio_threshold", C.c_float),
+        ("has_logprob_threshold", C.c_int32), ("logprob_threshold", C.c_float),
+        ("has_first_token_logprob_threshold", C.c_int32), ("first_token_logprob_threshold", C.c_float),
+        ("has_no_speech_threshold", C.c_int32), ("no_speech_threshold", C.c_float),
+        ("seed", C.c_uint64),
+    ]
+
+
+class wk_decode_result(C.Structure):
+    _fields_ = [
+        ("n_tokens", C.c_int32), ("tokens", C.c_int32 * 226), ("token_logprobs", C.c_float * 226),
+        ("avg_logprob", C.c_float), ("compression_ratio", C.c_float), ("temperature", C.c_float),
+        ("needs_fallback", C.c_int32), ("fallback_reason", C.c_int32), ("first_token_logprob_too_low", C.c_int32),
+        ("n_current_tokens", C.c_int32), ("steps", C.c_int32),
+    ]
+
+
+# every symbol include/wkb200.h declares: (name, restype, argtypes)
+P = C.c_void_p
+I32, I64, F32 = C.c_int32, C.c_int64, C.c_float
+PI32, PI64, PF32 = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_float)
+SYMBOLS = [
+    ("wk_last_error", C.c_char_p, []),
+    ("wk_version", C.c_char_p, []),
+    ("wk_device_available", I32, []),
+    ("wk_default_config", None, [C.c_char_p, C.POINTER(wk_model_config)]),
+    ("wk_model_create", I32, [C.POINTER(wk_model_config), I32, C.POINTER(P)]),
+    ("wk_model_set_tensor", I32, [P, C.c_char_p, P, I32, PI64, I32]),
+    ("wk_model_finalize", I32, [P]),
+    ("wk_model_init_random", I32, [P, C.c_uint64, F32]),
+    ("wk_model_info_get", I32, [P, C.POINTER(wk_model_info)]),
+    ("wk_model_free", None, [P]),
+    ("wk_tensor_shape", I32, [P, PI64, PI32, PI32]),
+    ("wk_tensor_to_host", I32, [P, P, I64]),
+    ("wk_tensor_free", None, [P]),
+    ("wk_mel", I32, [P, P, I64, I64, PI32, C.POINTER(P)]),
+    ("wk_encode", I32, [P, P, C.POINTER(P)]),
+    ("wk_session_create", I32, [P, I32, C.POINTER(P)]),
+    ("wk_session_free", None, [P]),
+    ("wk_session_set_encoder_output", I32, [P, P]),
+    ("wk_session_reset", I32, [P]),
+    ("wk_build_prompt", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), I32, PI32, I32, PI32]),
+    ("wk_decode_step", I32, [P, PI32, PI32, P]),
+    ("wk_filter_sample", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), I32, P, I32, I32, P, I32, P,
+                               I32, I32, P, I32, I32, P, P, P]),
+    ("wk_decode_text", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), PI32, I32,
+                             C.POINTER(wk_decode_result)]),
+    ("wk_session_last_logits", I32, [P, P]),
+    ("wk_transcribe_windows", I32, [P, P, P, I64, I64, PI32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts),
+                                    PI32, I32, C.POINTER(wk_decode_result)]),
+    ("wk_kernel_launch_count", I64, [I32]),
+    ("wk_last_timings", I32, [P, PF32]),
+    ("wk_model_stream", P, [P]),
+    ("wk_test_gemm", I32, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32]),
+    ("wk_test_gemm_splitk", I32, [P, P, P, P, I32, I32, I32, I32, I32]),
+    ("wk_test_attention", I32, [P, P, P, I32, I32, I32, I32]),
+    ("wk_bench_kernel", I32, [P, P, I32, I32, I32, PF32, C.POINTER(C.c_double)]),
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libwkb200.so and attach prototypes.  Raises if the library is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not built: run `python -m whisperkit_b200.build` (needs nvcc). "
+            "whisperkit_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header ever diverge
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise WhisperError(status, load().wk_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,724 @@
+// Decoder-side kernels: everything one autoregressive step needs besides the (swap-AB, split-K) tcgen05 GEMMs.
+//
+// Reference behaviour restated on the device (so the host sees only final token IDs):
+//   decodeText loop state machine            Sources/WhisperKit/Core/TextDecoder.swift:566-686
+//   updateKVCache (host splice, eliminated)  Sources/WhisperKit/Core/TextDecoder.swift:218-270
+//   LogitsFiltering x4                       Sources/WhisperKit/Core/Text/LogitsFilter.swift:12-276
+//   GreedyTokenSampler.update                Sources/WhisperKit/Core/Text/TokenSampler.swift:42-83,215-240
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wk {
+
+static constexpr int kMaxCtx = 224;  // Constants.maxTokenContext (Models.swift:1334)
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? scratch[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+    v = warp_max(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? scratch[lane] : -INFINITY;
+    r = warp_max(r);
+    return r;
+}
+
+// =====================================================================================================
+// decode state
+// =====================================================================================================
+__global__ void decode_state_init_kernel(DecodeState st, const int32_t* __restrict__ prompt, int n_prompt, int B) {
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) {
+        st.tokens[b * kMaxCtx + i] = i < n_prompt ? prompt[i] : 0;
+        st.logprobs[b * kMaxCtx + i] = 0.f;
+    }
+    if (threadIdx.x == 0) {
+        st.n_tokens[b] = n_prompt;
+        st.next_token[b] = n_prompt > 0 ? prompt[n_prompt - 1] : 0;
+        st.done[b] = 0;
+        st.first_low[b] = 0;
+        st.steps[b] = 0;
+        st.input_ids[b] = 0;
+        if (b == 0) { *st.step = 0; *st.n_done = 0; }
+    }
+}
+
+wk_status decode_state_init(DecodeState st, const int32_t* prompt_dev, int n_prompt, int B, cudaStream_t stream) {
+    decode_state_init_kernel<<<B, 64, 0, stream>>>(st, prompt_dev, n_prompt, B);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decode_state_init launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+// =====================================================================================================
+// token + position embedding, prompt forcing (TextDecoder.swift:581-594), first LayerNorm
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+decoder_embed_ln_kernel(const T* __restrict__ emb, const float* __restrict__ pos_emb, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, DecodeState st, int prompt_len, int ts_begin, float* __restrict__ x,
+                        T* __restrict__ xn, int d, int explicit_inputs, const int32_t* __restrict__ explicit_pos) {
+    __shared__ float scratch[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int tok, pos;
+    if (explicit_inputs) {
+        tok = st.input_ids[b];
+        pos = explicit_pos[b];
+    } else {
+        const int step = *st.step;
+        pos = step;
+        tok = st.next_token[b];
+        bool overwrite = false;
+        if (!st.done[b] && step < prompt_len) {
+            const int cur = st.tokens[b * kMaxCtx + step];
+            const bool is_ts = cur >= ts_begin, pred_ts = tok >= ts_begin;
+            if (!(step == prompt_len - 1 && is_ts && pred_ts)) tok = cur;
+            else overwrite = true;  // model-predicted first timestamp replaces the forced <|0.00|>
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (overwrite) st.tokens[b * kMaxCtx + step] = tok;
+            st.input_ids[b] = tok;
+        }
+    }
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * 256;
+        v[k] = 0.f;
+        if (i < d) {
+            v[k] = T16<T>::to_f(emb[(long long)tok * d + i]) + pos_emb[(long long)pos * d + i];
+            x[(long long)b * d + i] = v[k];
+            s += v[k];
+        }
+    }
+    const float mean = block_sum(s, scratch) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * 256;
+        if (i < d) { const float a = v[k] - mean; q += a * a; }
+    }
+    const float rstd = rsqrtf(block_sum(q, scratch) / d + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * 256;
+        if (i < d) xn[(long long)b * d + i] = T16<T>::from_f((v[k] - mean) * rstd * gamma[i] + beta[i]);
+    }
+}
+
+wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gamma, const float* beta, DecodeState st,
+                           int prompt_len, int ts_begin, float* x, void* xn, int B, int d, int dtype, int explicit_inputs,
+                           const int32_t* explicit_pos, cudaStream_t stream) {
+    if (d > 2048) { set_error("decoder_embed_ln: d_model %d > 2048", d); return WK_ERR_INVALID_ARGUMENT; }
+    if (dtype == WK_DTYPE_F16)
+        decoder_embed_ln_kernel<__half><<<B, 256, 0, stream>>>((const __half*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__half*)xn, d, explicit_inputs, explicit_pos);
+    else
+        decoder_embed_ln_kernel<__nv_bfloat16><<<B, 256, 0, stream>>>((const __nv_bfloat16*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_inputs, explicit_pos);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decoder_embed_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+// =====================================================================================================
+// split-K reduce + bias + residual + LayerNorm      (partials [S][Bp][d] f32, written by the swap-AB GEMM)
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+decoder_reduce_resid_ln_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bias,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x,
+                               T* __restrict__ xn, int d) {
+    __shared__ float scratch[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * 256;
+        v[k] = 0.f;
+        if (i < d) {
+            float a = x[(long long)b * d + i] + (bias ? bias[i] : 0.f);
+            for (int sp = 0; sp < splits; ++sp) a += partial[((long long)sp * Bp + b) * d + i];
+            v[k] = a;
+            x[(long long)b * d + i] = a;
+            s += a;
+        }
+    }
+    const float mean = block_sum(s, scratch) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * 256;
+        if (i < d) { const float a = v[k] - mean; q += a * a; }
+    }
+    const float rstd = rsqrtf(block_sum(q, scratch) / d + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * 256;
+        if (i < d) xn[(long long)b * d + i] = T16<T>::from_f((v[k] - mean) * rstd * gamma[i] + beta[i]);
+    }
+}
+
+wk_status decoder_reduce_resid_ln(const float* partial, int splits, int Bp, const float* bias, const float* gamma,
+                                  const float* beta, float* x, void* xn, int B, int d, int dtype, cudaStream_t stream) {
+    if (dtype == WK_DTYPE_F16)
+        decoder_reduce_resid_ln_kernel<__half><<<B, 256, 0, stream>>>(partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
+    else
+        decoder_reduce_resid_ln_kernel<__nv_bfloat16><<<B, 256, 0, stream>>>(partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decoder_reduce_resid_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+decoder_reduce_bias_gelu_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bias,
+                                T* __restrict__ out, int B, int n) {
+    const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (idx >= (long long)B * n) return;
+    const int b = (int)(idx / n), i = (int)(idx - (long long)b * n);
+    float4 a = *reinterpret_cast<const float4*>(bias + i);
+    for (int sp = 0; sp < splits; ++sp) {
+        const float4 p = *reinterpret_cast<const float4*>(partial + ((long long)sp * Bp + b) * n + i);
+        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    uint2 pk;
+    pk.x = T16<T>::pack2(gelu_erf(a.x), gelu_erf(a.y));
+    pk.y = T16<T>::pack2(gelu_erf(a.z), gelu_erf(a.w));
+    *reinterpret_cast<uint2*>(out + (long long)b * n + i) = pk;
+}
+
+wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, const float* bias, void* out, int B, int n,
+                                   int dtype, cudaStream_t stream) {
+    const long long threads = (long long)B * n / 4;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (dtype == WK_DTYPE_F16)
+        decoder_reduce_bias_gelu_kernel<__half><<<grid, 256, 0, stream>>>(partial, splits, Bp, bias, (__half*)out, B, n);
+    else
+        decoder_reduce_bias_gelu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decoder_reduce_bias_gelu launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+// =====================================================================================================
+// self attention for one new token: warp per (b, h); reduces q/k/v partials, appends K/V in place in the
+// device cache (replaces the host-side updateKVCache splice), attends over positions 0..pos
+// cache layout [B][H][max_len][64]
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128)
+decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
+                              const float* __restrict__ bv, T* __restrict__ kcache, T* __restrict__ vcache,
+                              const int32_t* __restrict__ step, const int32_t* __restrict__ explicit_pos,
+                              T* __restrict__ out, int B, int H, int max_len) {
+    __shared__ float sq[4][64];
+    __shared__ float skc[4][64];
+    __shared__ float svc[4][64];
+    __shared__ float sp[4][kMaxCtx];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x * 4 + warp;
+    if (bh >= B * H) return;
+    const int b = bh / H, h = bh % H;
+    const int dm = H * 64;
+    const int pos = explicit_pos ? explicit_pos[b] : *step;
+    const int e = 2 * lane;
+    float2 q = make_float2(bq[h * 64 + e], bq[h * 64 + e + 1]);
+    float2 k = make_float2(0.f, 0.f);
+    float2 v = make_float2(bv[h * 64 + e], bv[h * 64 + e + 1]);
+    for (int s = 0; s < splits; ++s) {
+        const float* pr = partial + ((long long)s * Bp + b) * (3LL * dm) + h * 64 + e;
+        const float2 pq = *reinterpret_cast<const float2*>(pr);
+        const float2 pk = *reinterpret_cast<const float2*>(pr + dm);
+        const float2 pv = *reinterpret_cast<const float2*>(pr + 2 * dm);
+        q.x += pq.x; q.y += pq.y; k.x += pk.x; k.y += pk.y; v.x += pv.x; v.y += pv.y;
+    }
+    // append to the cache (16-bit rounding is part of the precision policy)
+    T* krow = kcache + ((long long)bh * max_len + pos) * 64;
+    T* vrow = vcache + ((long long)bh * max_len + pos) * 64;
+    const uint32_t k16 = T16<T>::pack2(k.x, k.y), v16 = T16<T>::pack2(v.x, v.y);
+    *reinterpret_cast<uint32_t*>(krow + e) = k16;
+    *reinterpret_cast<uint32_t*>(vrow + e) = v16;
+    const float2 kr = T16<T>::unpack2(k16), vr = T16<T>::unpack2(v16);
+    sq[warp][e] = q.x; sq[warp][e + 1] = q.y;
+    skc[warp][e] = kr.x; skc[warp][e + 1] = kr.y;
+    svc[warp][e] = vr.x; svc[warp][e + 1] = vr.y;
+    __syncwarp();
+    // scores: lane handles keys lane, lane+32, ...
+    float smax = -INFINITY;
+    float sc[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const int t = lane + 32 * i;
+        sc[i] = -INFINITY;
+        if (t <= pos) {
+            float acc = 0.f;
+            if (t == pos) {
+#pragma unroll 16
+                for (int j = 0; j < 64; ++j) acc += sq[warp][j] * skc[warp][j];
+            } else {
+                const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)bh * max_len + t) * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 u = kp[c];
+                    const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+                    const float* qq = &sq[warp][c * 8];
+                    acc += qq[0] * a0.x + qq[1] * a0.y + qq[2] * a1.x + qq[3] * a1.y + qq[4] * a2.x + qq[5] * a2.y + qq[6] * a3.x + qq[7] * a3.y;
+                }
+            }
+            sc[i] = acc * 0.125f;
+            smax = fmaxf(smax, sc[i]);
+        }
+    }
+    smax = warp_max(smax);
+    float ssum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const int t = lane + 32 * i;
+        if (t <= pos) {
+            const float p = __expf(sc[i] - smax);
+            sp[warp][t] = p;
+            ssum += p;
+        }
+    }
+    ssum = warp_sum(ssum);
+    __syncwarp();
+    // output: lane handles dims e, e+1
+    float2 acc = make_float2(0.f, 0.f);
+    const T* vb = vcache + (long long)bh * max_len * 64 + e;
+    for (int t = 0; t < pos; ++t) {
+        const float2 vv = T16<T>::unpack2(*reinterpret_cast<const uint32_t*>(vb + (long long)t * 64));
+        const float p = sp[warp][t];
+        acc.x += p * vv.x; acc.y += p * vv.y;
+    }
+    {
+        const float p = sp[warp][pos];
+        acc.x += p * svc[warp][e]; acc.y += p * svc[warp][e + 1];
+    }
+    const float inv = 1.f / ssum;
+    *reinterpret_cast<uint32_t*>(out + (long long)b * dm + h * 64 + e) = T16<T>::pack2(acc.x * inv, acc.y * inv);
+}
+
+wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
+                                 void* vcache, const int32_t* step, const int32_t* explicit_pos, void* out, int B, int H,
+                                 int max_len, int dtype, cudaStream_t stream) {
+    if (max_len > kMaxCtx) { set_error("decoder_self_attention: max_len %d > %d", max_len, kMaxCtx); return WK_ERR_INVALID_ARGUMENT; }
+    const unsigned grid = (unsigned)((B * H + 3) / 4);
+    if (dtype == WK_DTYPE_F16)
+        decoder_self_attention_kernel<__half><<<grid, 128, 0, stream>>>(partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, step, explicit_pos, (__half*)out, B, H, max_len);
+    else
+        decoder_self_attention_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, step, explicit_pos, (__nv_bfloat16*)out, B, H, max_len);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decoder_self_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+// =====================================================================================================
+// cross attention for one query per (b, h) over T encoder positions.  HBM-streaming kernel: each CTA pulls its
+// contiguous K block then V block (T x 64 x 2 B each) through a 4-deep ring of 16 KB bulk-copy stages
+// (cp.async.bulk + mbarrier), a dedicated producer warp keeps the ring full while 4 consumer warps compute.
+// K/V layout [B][H][T][64] (written head-major by the cross-KV GEMM epilogue).
+// =====================================================================================================
+static constexpr int kCrossRows = 125;              // rows per stage: 125 * 128 B = 16000 B (multiple of 16)
+static constexpr int kCrossStageBytes = kCrossRows * 128;
+static constexpr int kCrossStages = 4;
+static constexpr int kCrossThreads = 160;           // 4 consumer warps + 1 producer warp
+
+template <typename T>
+__global__ void __launch_bounds__(kCrossThreads)
+decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
+                               const T* __restrict__ kcross, const T* __restrict__ vcross, T* __restrict__ out, int B, int H,
+                               int Tlen) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ring = smem;                                                   // kCrossStages * 16000
+    float* scores = reinterpret_cast<float*>(smem + kCrossStages * kCrossStageBytes);  // [Tlen]
+    float* sq = scores + ((Tlen + 3) & ~3);                                 // [64]
+    float* red = sq + 64;                                                   // [4][64] + scratch
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 4 * 64 + 32);
+    uint64_t* empty_bar = full_bar + kCrossStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bh = blockIdx.x, b = bh / H, h = bh % H;
+    const int dm = H * 64;
+    const int chunks = Tlen / kCrossRows;  // per K and per V
+    if (tid == 0) {
+        for (int i = 0; i < kCrossStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
+        fence_barrier_init();
+    }
+    if (tid < 64) {
+        float q = bq[h * 64 + tid];
+        for (int s = 0; s < splits; ++s) q += partial[((long long)s * Bp + b) * dm + h * 64 + tid];
+        sq[tid] = q * 0.125f;
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const uint8_t* kb = reinterpret_cast<const uint8_t*>(kcross + (long long)bh * Tlen * 64);
+            const uint8_t* vb = reinterpret_cast<const uint8_t*>(vcross + (long long)bh * Tlen * 64);
+            for (int c = 0; c < 2 * chunks; ++c) {
+                const int stage = c % kCrossStages;
+                const uint32_t ph = (c / kCrossStages) & 1;
+                mbar_wait(&empty_bar[stage], ph ^ 1);
+                mbar_expect_tx(&full_bar[stage], kCrossStageBytes);
+                const uint8_t* src = c < chunks ? kb + (long long)c * kCrossStageBytes : vb + (long long)(c - chunks) * kCrossStageBytes;
+                bulk_load_1d(ring + stage * kCrossStageBytes, src, kCrossStageBytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+    // ---------------- consumers (128 threads) ----------------
+    const int sub = lane & 7;        // 16-byte piece of the 128-byte row: dims sub*8 .. sub*8+7
+    const int rsel = lane >> 3;      // row within a group of 4
+    float qv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qv[j] = sq[sub * 8 + j];
+
+    // K phase: scores[t] = q . K[t]
+    for (int c = 0; c < chunks; ++c) {
+        const int stage = c % kCrossStages;
+        const uint32_t ph = (c / kCrossStages) & 1;
+        mbar_wait(&full_bar[stage], ph);
+        const uint8_t* tile = ring + stage * kCrossStageBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = warp * 4 + rsel + 16 * i;
+            float acc = 0.f;
+            if (r < kCrossRows) {
+                const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + sub * 16);
+                const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+                acc = qv[0] * a0.x + qv[1] * a0.y + qv[2] * a1.x + qv[3] * a1.y + qv[4] * a2.x + qv[5] * a2.y + qv[6] * a3.x + qv[7] * a3.y;
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (sub == 0 && r < kCrossRows) scores[c * kCrossRows + r] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // softmax over Tlen scores (consumers only)
+    float mx = -INFINITY;
+    for (int t = tid; t < Tlen; t += 128) mx = fmaxf(mx, scores[t]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float sm = 0.f;
+    for (int t = tid; t < Tlen; t += 128) {
+        const float p = __expf(scores[t] - mx);
+        scores[t] = p;
+        sm += p;
+    }
+    sm = warp_sum(sm);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone has read red[] (max) before it is reused
+    if (lane == 0) red[warp] = sm;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+
+    // V phase: out[d] = sum_t p[t] V[t][d]
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int c = chunks; c < 2 * chunks; ++c) {
+        const int stage = c % kCrossStages;
+        const uint32_t ph = (c / kCrossStages) & 1;
+        mbar_wait(&full_bar[stage], ph);
+        const uint8_t* tile = ring + stage * kCrossStageBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = warp * 4 + rsel + 16 * i;
+            if (r < kCrossRows) {
+                const float p = scores[(c - chunks) * kCrossRows + r];
+                const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + sub * 16);
+                const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+                acc[0] += p * a0.x; acc[1] += p * a0.y; acc[2] += p * a1.x; acc[3] += p * a1.y;
+                acc[4] += p * a2.x; acc[5] += p * a2.y; acc[6] += p * a3.x; acc[7] += p * a3.y;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // red[] (sum) consumed by everyone
+    if (rsel == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp * 64 + sub * 8 + j] = acc[j];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid < 64) {
+        const float o = (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]) * inv;
+        out[(long long)b * dm + h * 64 + tid] = T16<T>::from_f(o);
+    }
+}
+
+static size_t cross_smem_bytes(int T) {
+    return (size_t)kCrossStages * kCrossStageBytes + (size_t)((T + 3) & ~3) * 4 + 64 * 4 + (4 * 64 + 32) * 4 + 2 * kCrossStages * 8 + 64;
+}
+
+wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
+                                  const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream) {
+    if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
+    const size_t smem = cross_smem_bytes(T);
+    static bool attr_set[2] = {false, false};
+    const int ti = dtype == WK_DTYPE_F16 ? 1 : 0;
+    if (!attr_set[ti]) {
+        cudaError_t e = dtype == WK_DTYPE_F16
+            ? cudaFuncSetAttribute(decoder_cross_attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
+            : cudaFuncSetAttribute(decoder_cross_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(cross): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+        attr_set[ti] = true;
+    }
+    if (dtype == WK_DTYPE_F16)
+        decoder_cross_attention_kernel<__half><<<B * H, kCrossThreads, smem, stream>>>(partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T);
+    else
+        decoder_cross_attention_kernel<__nv_bfloat16><<<B * H, kCrossThreads, smem, stream>>>(partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decoder_cross_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+// =====================================================================================================
+// K7: fused logits filters + greedy sampler + decode-loop state update.  One CTA per sequence; the logits row
+// (V f32, 207 KB for V = 51866) is staged once in shared memory, masks are applied while it streams in, and the
+// max / log-sum-exp / argmax reductions of TimestampRulesFilter and GreedyTokenSampler run out of smem.
+// =====================================================================================================
+static constexpr int kSamplerThreads = 1024;
+
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax argmax_better(ArgMax a, ArgMax b) {
+    // larger value wins; ties -> lower index (first maximal index, like argmax)
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+__global__ void __launch_bounds__(kSamplerThreads)
+sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerParams p, DecodeState st,
+               const int32_t* __restrict__ tokens_in, int ld_tokens, const int32_t* __restrict__ n_tokens_in,
+               int32_t* __restrict__ token_out, float* __restrict__ logprob_out, float* __restrict__ filtered_out) {
+    extern __shared__ __align__(16) float srow[];  // [V]
+    __shared__ float scratch[32];
+    __shared__ int sflag[8];     // 0: ts filter active, 1: lo0, 2: hi0 (interval A), 3: lo1, 4: hi1 (interval B), 5: blank active
+    __shared__ ArgMax sarg[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int V = p.vocab;
+    const bool loop_mode = p.prompt_len >= 0;
+    const int32_t* toks = loop_mode ? st.tokens + b * kMaxCtx : tokens_in + (long long)b * ld_tokens;
+    const int n_tok = loop_mode ? st.n_tokens[b] : n_tokens_in[b];
+    const wk_special_tokens& S = p.st;
+
+    if (tid == 0) {
+        // ---- TimestampRulesFilter rule state (LogitsFilter.swift:72-109)
+        int active = 0, loA = 0, hiA = 0, loB = 0, hiB = 0;
+        if (p.sample_begin_ts >= 0) {
+            int sb = -1;
+            if (p.is_multilingual) {
+                const int lim = n_tok < 3 ? n_tok : 3;
+                for (int i = 0; i < lim; ++i)
+                    if (toks[i] == S.transcribe_token || toks[i] == S.translate_token) { sb = max(i + 1, p.sample_begin_ts); break; }
+            } else {
+                sb = p.sample_begin_ts;
+            }
+            if (sb >= 0 && sb <= n_tok) {
+                active = 1;
+                if (n_tok > sb) {
+                    const int ns = n_tok - sb;
+                    const bool last_ts = ns >= 1 && toks[n_tok - 1] >= S.time_token_begin;
+                    const bool pen_ts = ns < 2 || toks[n_tok - 2] >= S.time_token_begin;
+                    if (last_ts) {
+                        if (pen_ts) { loA = S.time_token_begin; hiA = V; }   // has to be non-timestamp
+                        else { loA = 0; hiA = S.end_token; }                 // cannot be normal text
+                    }
+                    int last_time = -1;
+                    for (int i = n_tok - 1; i >= sb; --i)
+                        if (toks[i] >= S.time_token_begin) { last_time = toks[i]; break; }
+                    if (last_time >= 0) {
+                        const int ts_last = (last_ts && !pen_ts) ? last_time : last_time + 1;
+                        loB = S.time_token_begin; hiB = ts_last;
+                    }
+                }
+            }
+        }
+        sflag[0] = active; sflag[1] = loA; sflag[2] = hiA; sflag[3] = loB; sflag[4] = hiB;
+        sflag[5] = (p.sample_begin_blank >= 0 && n_tok == p.sample_begin_blank) ? 1 : 0;   // SuppressBlankFilter
+        sflag[6] = (p.language_tokens != nullptr && n_tok >= p.language_sample_begin) ? 1 : 0;  // LanguageLogitsFilter
+    }
+    __syncthreads();
+    const int ts_active = sflag[0], loA = sflag[1], hiA = sflag[2], loB = sflag[3], hiB = sflag[4];
+    const int blank_active = sflag[5], lang_active = sflag[6];
+    const float* row = logits + (long long)b * ld_logits;
+
+    // ---- stream the row into smem with the interval / single-token masks applied
+    for (int i = tid; i < V; i += kSamplerThreads) {
+        float x = lang_active ? -INFINITY : row[i];
+        if (blank_active && (i == S.whitespace_token || i == S.end_token)) x = -INFINITY;
+        if (ts_active) {
+            if (i == S.no_timestamps_token) x = -INFINITY;
+            if ((i >= loA && i < hiA) || (i >= loB && i < hiB)) x = -INFINITY;
+        }
+        srow[i] = x;
+    }
+    __syncthreads();
+    if (lang_active) {
+        for (int j = tid; j < p.n_language_tokens; j += kSamplerThreads) {
+            const int t = p.language_tokens[j];
+            if (t >= 0 && t < V) srow[t] = row[t];
+        }
+        __syncthreads();
+        // re-apply the filters that run after a (custom-positioned) language filter
+        for (int j = tid; j < p.n_language_tokens; j += kSamplerThreads) {
+            const int i = p.language_tokens[j];
+            if (i < 0 || i >= V) continue;
+            if (blank_active && (i == S.whitespace_token || i == S.end_token)) srow[i] = -INFINITY;
+            if (ts_active && (i == S.no_timestamps_token || (i >= loA && i < hiA) || (i >= loB && i < hiB))) srow[i] = -INFINITY;
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < p.n_suppress; j += kSamplerThreads) {   // SuppressTokensFilter
+        const int t = p.suppress[j];
+        if (t >= 0 && t < V) srow[t] = -INFINITY;
+    }
+    __syncthreads();
+
+    // ---- reductions: max over text / timestamp partitions
+    const int tsb = (ts_active && S.time_token_begin > 0 && S.time_token_begin < V) ? S.time_token_begin : V;
+    float mtext = -INFINITY, mts = -INFINITY;
+    for (int i = tid; i < V; i += kSamplerThreads) {
+        const float x = srow[i];
+        if (i < tsb) mtext = fmaxf(mtext, x); else mts = fmaxf(mts, x);
+    }
+    mtext = block_max(mtext, scratch);
+    mts = block_max(mts, scratch);
+    const float mall = fmaxf(mtext, mts);
+    float sall = 0.f, sts = 0.f;
+    for (int i = tid; i < V; i += kSamplerThreads) {
+        const float x = srow[i];
+        if (x == -INFINITY) continue;
+        sall += __expf(x - mall);
+        if (i >= tsb) sts += __expf(x - mts);
+    }
+    sall = block_sum(sall, scratch);
+    sts = block_sum(sts, scratch);
+    float lse = mall + logf(sall);
+    // "sum of probability over timestamps is above any other token" (LogitsFilter.swift:124-127,144-242)
+    bool ts_wins = false;
+    if (tsb < V && mts > -INFINITY) {
+        const float lse_ts = mts + logf(sts);
+        const float ts_logprob = lse_ts - lse;
+        const float max_text_logprob = mtext - lse;
+        ts_wins = ts_logprob > max_text_logprob;
+        if (ts_wins) lse = lse_ts;
+    }
+    const int lo = ts_wins ? tsb : 0;
+    if (ts_wins && filtered_out) {
+        for (int i = tid; i < tsb; i += kSamplerThreads) srow[i] = -INFINITY;
+        __syncthreads();
+    }
+    // ---- argmax (first maximal index) over [lo, V)
+    ArgMax best = {-INFINITY, 0x7fffffff};
+    for (int i = lo + tid; i < V; i += kSamplerThreads) {
+        const float x = srow[i];
+        if (x > best.v) { best.v = x; best.i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax other;
+        other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+        best = argmax_better(best, other);
+    }
+    if ((tid & 31) == 0) sarg[tid >> 5] = best;
+    __syncthreads();
+    if (tid < 32) {
+        best = sarg[tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgMax other;
+            other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+            other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+            best = argmax_better(best, other);
+        }
+    }
+    if (filtered_out) {
+        for (int i = tid; i < V; i += kSamplerThreads) filtered_out[(long long)b * V + i] = srow[i];
+    }
+    if (tid == 0) {
+        const int tok = best.i;
+        const float lp = best.v - lse;
+        if (token_out) token_out[b] = tok;
+        if (logprob_out) logprob_out[b] = lp;
+        if (loop_mode && !st.done[b]) {
+            // decodeText bookkeeping (TextDecoder.swift:654-686)
+            const int step = *st.step;
+            const bool first_low = (step == 0) && p.has_first_thr && (lp < p.first_thr);
+            const bool completed = (tok == S.end_token) || (n_tok >= p.max_ctx - 1) || first_low;
+            st.next_token[b] = tok;
+            st.steps[b] = step + 1;
+            if (completed) {
+                st.done[b] = 1;
+                st.first_low[b] = first_low ? 1 : 0;
+                atomicAdd(st.n_done, 1);
+            } else if (!(step < p.prompt_len - 1)) {   // !isPrefill
+                st.tokens[b * kMaxCtx + n_tok] = tok;
+                st.logprobs[b * kMaxCtx + n_tok] = lp;
+                st.n_tokens[b] = n_tok + 1;
+            }
+        }
+    }
+}
+
+__global__ void advance_step_kernel(DecodeState st) { *st.step += 1; }
+
+wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
+                                int ld_tokens, const int32_t* n_tokens, int32_t* token_out, float* logprob_out,
+                                float* filtered_out, int B, cudaStream_t stream) {
+    if (p.temperature != 0.f) {
+        set_error("sampler: temperature > 0 (top-k multinomial fallback sampling) is not implemented in this round");
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    const size_t smem = (size_t)p.vocab * sizeof(float);
+    if (smem > 220 * 1024) { set_error("sampler: vocab %d too large for the shared-memory row", p.vocab); return WK_ERR_INVALID_ARGUMENT; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(sampler): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+        attr_set = true;
+    }
+    sampler_kernel<<<B, kSamplerThreads, smem, stream>>>(logits, (long long)ld_logits, p, st, tokens, ld_tokens, n_tokens, token_out,
+                                                        logprob_out, filtered_out);
+    count_launch();
+    if (p.prompt_len >= 0) {
+        advance_step_kernel<<<1, 1, 0, stream>>>(st);
+        count_launch();
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("sampler launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+}  // namespace wk

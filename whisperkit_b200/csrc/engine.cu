@@ -1,0 +1,1214 @@
+// libwkb200 engine: model / session objects, weight ingestion, the encoder and decoder schedules, and the C ABI of
+// include/wkb200.h.  Host-side control flow mirrors the reference's per-window body
+// (Sources/WhisperKit/Core/TranscribeTask.swift:116-278) and decode loop
+// (Sources/WhisperKit/Core/TextDecoder.swift:541-855); all arithmetic runs in the sm_100a kernels of this directory.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wk {
+
+// ------------------------------------------------------------------------------------------------ errors / counters
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static constexpr int kKvMaxLen = 224;  // Constants.maxTokenContext (Models.swift:1334)
+static constexpr int kWindowSamples = 480000;
+
+#define WK_CHECK(expr)                    \
+    do {                                  \
+        wk_status _s = (expr);            \
+        if (_s != WK_OK) return _s;       \
+    } while (0)
+
+template <typename T>
+static wk_status dmalloc(T** p, size_t n, bool zero = true) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        return WK_ERR_CUDA;
+    }
+    if (zero) {
+        e = cudaMemset(*p, 0, n * sizeof(T));
+        if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    }
+    return WK_OK;
+}
+
+struct LayerNormW { float* g = nullptr; float* b = nullptr; };
+struct EncLayer {
+    LayerNormW ln1, ln2;
+    void* wqkv = nullptr; float* bqkv = nullptr;  // [3d, d]
+    void* wo = nullptr; float* bo = nullptr;
+    void* w1 = nullptr; float* b1 = nullptr;      // [4d, d]
+    void* w2 = nullptr; float* b2 = nullptr;      // [d, 4d]
+};
+struct DecLayer {
+    LayerNormW ln1, lnx, ln3;
+    void* wqkv = nullptr; float* bq = nullptr; float* bv = nullptr;
+    void* wo = nullptr; float* bo = nullptr;
+    void* wcq = nullptr; float* bcq = nullptr;
+    void* wco = nullptr; float* bco = nullptr;
+    void* w1 = nullptr; float* b1 = nullptr;
+    void* w2 = nullptr; float* b2 = nullptr;
+};
+
+}  // namespace wk
+
+using namespace wk;
+
+struct wk_tensor {
+    void* data;
+    int kind;      // 0 = mel [B,3002,128] f16 ; 1 = encoder output [B*1500, d] model dtype
+    int dtype;
+    int64_t batch;
+    wk_model* owner;
+};
+
+struct wk_model {
+    wk_model_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool finalized = false;
+    int esz = 2;
+    // weights
+    void* conv1_w = nullptr; float* conv1_b = nullptr;   // f16 [d][3][128]
+    void* conv2_w = nullptr; float* conv2_b = nullptr;   // f16 [d][3][d]
+    float* enc_pos = nullptr;                            // [1500][d]
+    std::vector<EncLayer> enc;
+    LayerNormW enc_ln;
+    void* emb = nullptr;                                 // [V][d]
+    float* dec_pos = nullptr;                            // [448][d]
+    std::vector<DecLayer> dec;
+    LayerNormW dec_ln;
+    void* wckv = nullptr; float* bckv = nullptr;         // [2L*d][d], [2L*d]
+    // front end
+    MelTables* mel_tables = nullptr;
+    // workspaces (max_batch windows)
+    float* pcm_dev = nullptr; int32_t* nvalid_dev = nullptr; int32_t* gmax = nullptr;
+    void* mel = nullptr;       // f16 [Bm][3002][128]
+    void* h1 = nullptr;        // f16 [Bm][3002][d]
+    float* x = nullptr;        // f32 [Bm*1500][d]
+    void* xn = nullptr; void* qkv = nullptr; void* attn = nullptr; void* ffn = nullptr; void* enc_out = nullptr;
+    float timings[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8];
+    wk_tensor mel_tensor, enc_tensor;
+};
+
+struct wk_session {
+    wk_model* m;
+    int max_batch, batch = 0, bp = 16;
+    void* cross_kv = nullptr;   // [2L][Bs][H][T][64]
+    void* self_k = nullptr;     // [L][Bs][H][224][64]
+    void* self_v = nullptr;
+    float* partial = nullptr; size_t partial_elems = 0;
+    float* x = nullptr; void* xn = nullptr; void* attn = nullptr; void* ffn = nullptr;
+    float* logits = nullptr;
+    DecodeState st;
+    int32_t* prompt_dev = nullptr; int32_t* pos_dev = nullptr; int32_t* suppress_dev = nullptr; int32_t* lang_dev = nullptr;
+    int32_t* tok_scratch = nullptr; int32_t* ntok_scratch = nullptr; int32_t* tokout_dev = nullptr; float* lpout_dev = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+};
+
+namespace wk {
+
+static int choose_splits(int tiles, int total_kb, int num_sms) {
+    int best = 1;
+    for (int s = 1; s <= total_kb; ++s) {
+        if (total_kb % s) continue;
+        best = s;
+        if (tiles * s >= (num_sms * 9) / 10) break;
+    }
+    return best;
+}
+
+static size_t esize(int dtype) { return dtype == WK_DTYPE_F32 || dtype == WK_DTYPE_I32 ? 4 : 2; }
+
+static wk_status alloc_ln(LayerNormW& ln, int d) {
+    WK_CHECK(dmalloc(&ln.g, d));
+    WK_CHECK(dmalloc(&ln.b, d));
+    return WK_OK;
+}
+
+static wk_status alloc16(void** p, size_t n) {
+    uint16_t* q = nullptr;
+    WK_CHECK(dmalloc(&q, n));
+    *p = q;
+    return WK_OK;
+}
+
+static wk_status model_alloc(wk_model* m) {
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, L = c.enc_layers, Ld = c.dec_layers, Bm = c.max_batch;
+    const size_t T = c.n_audio_ctx;
+    WK_CHECK(alloc16(&m->conv1_w, (size_t)d * 3 * 128));
+    WK_CHECK(dmalloc(&m->conv1_b, d));
+    WK_CHECK(alloc16(&m->conv2_w, (size_t)d * 3 * d));
+    WK_CHECK(dmalloc(&m->conv2_b, d));
+    WK_CHECK(dmalloc(&m->enc_pos, T * d));
+    m->enc.resize(L);
+    for (auto& l : m->enc) {
+        WK_CHECK(alloc_ln(l.ln1, d)); WK_CHECK(alloc_ln(l.ln2, d));
+        WK_CHECK(alloc16(&l.wqkv, (size_t)3 * d * d)); WK_CHECK(dmalloc(&l.bqkv, 3 * d));
+        WK_CHECK(alloc16(&l.wo, (size_t)d * d)); WK_CHECK(dmalloc(&l.bo, d));
+        WK_CHECK(alloc16(&l.w1, (size_t)4 * d * d)); WK_CHECK(dmalloc(&l.b1, 4 * d));
+        WK_CHECK(alloc16(&l.w2, (size_t)4 * d * d)); WK_CHECK(dmalloc(&l.b2, d));
+    }
+    WK_CHECK(alloc_ln(m->enc_ln, d));
+    // embedding rows padded to a multiple of 128 so the last TMA tile never leaves the allocation
+    WK_CHECK(alloc16(&m->emb, (size_t)round_up(c.vocab, 128) * d));
+    WK_CHECK(dmalloc(&m->dec_pos, (size_t)c.n_text_ctx * d));
+    m->dec.resize(Ld);
+    for (auto& l : m->dec) {
+        WK_CHECK(alloc_ln(l.ln1, d)); WK_CHECK(alloc_ln(l.lnx, d)); WK_CHECK(alloc_ln(l.ln3, d));
+        WK_CHECK(alloc16(&l.wqkv, (size_t)3 * d * d)); WK_CHECK(dmalloc(&l.bq, d)); WK_CHECK(dmalloc(&l.bv, d));
+        WK_CHECK(alloc16(&l.wo, (size_t)d * d)); WK_CHECK(dmalloc(&l.bo, d));
+        WK_CHECK(alloc16(&l.wcq, (size_t)d * d)); WK_CHECK(dmalloc(&l.bcq, d));
+        WK_CHECK(alloc16(&l.wco, (size_t)d * d)); WK_CHECK(dmalloc(&l.bco, d));
+        WK_CHECK(alloc16(&l.w1, (size_t)4 * d * d)); WK_CHECK(dmalloc(&l.b1, 4 * d));
+        WK_CHECK(alloc16(&l.w2, (size_t)4 * d * d)); WK_CHECK(dmalloc(&l.b2, d));
+    }
+    WK_CHECK(alloc_ln(m->dec_ln, d));
+    WK_CHECK(alloc16(&m->wckv, (size_t)2 * Ld * d * d));
+    WK_CHECK(dmalloc(&m->bckv, (size_t)2 * Ld * d));
+    // workspaces
+    WK_CHECK(dmalloc(&m->pcm_dev, (size_t)Bm * kWindowSamples, false));
+    WK_CHECK(dmalloc(&m->nvalid_dev, Bm));
+    WK_CHECK(dmalloc(&m->gmax, Bm));
+    WK_CHECK(alloc16(&m->mel, (size_t)Bm * kMelRows * kMelCols));
+    WK_CHECK(alloc16(&m->h1, (size_t)Bm * kMelRows * d));
+    const size_t M = (size_t)Bm * T;
+    WK_CHECK(dmalloc(&m->x, M * d, false));
+    WK_CHECK(alloc16(&m->xn, M * d));
+    WK_CHECK(alloc16(&m->qkv, M * 3 * d));
+    WK_CHECK(alloc16(&m->attn, M * d));
+    WK_CHECK(alloc16(&m->ffn, M * 4 * d));
+    WK_CHECK(alloc16(&m->enc_out, M * d));
+    return WK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- weight ingestion
+__global__ void conv_w_rearrange_kernel(const float* __restrict__ src, __half* __restrict__ dst, int co, int ci, int ci_pad) {
+    // src [co][ci][3] f32 -> dst [co][3][ci_pad] f16
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)co * 3 * ci_pad;
+    if (idx >= n) return;
+    const int c = (int)(idx % ci_pad);
+    const int tap = (int)((idx / ci_pad) % 3);
+    const int o = (int)(idx / (3LL * ci_pad));
+    dst[idx] = c < ci ? __float2half_rn(src[((long long)o * ci + c) * 3 + tap]) : __float2half_rn(0.f);
+}
+
+struct Dest { void* p; int dtype; size_t numel; int special; };  // special: 1 conv1, 2 conv2
+
+static bool resolve_name(wk_model* m, const std::string& name, Dest* out) {
+    const int d = m->cfg.d_model, dt = m->cfg.dtype;
+    auto W = [&](void* p, size_t rows_off, size_t n) { *out = {(char*)p + rows_off * (size_t)d * 2, dt, n, 0}; return true; };
+    auto F = [&](float* p, size_t n) { *out = {p, WK_DTYPE_F32, n, 0}; return true; };
+    int i = -1;
+    char rest[128];
+    if (name == "model.encoder.conv1.weight") { *out = {m->conv1_w, WK_DTYPE_F16, (size_t)d * m->cfg.n_mels * 3, 1}; return true; }
+    if (name == "model.encoder.conv1.bias") return F(m->conv1_b, d);
+    if (name == "model.encoder.conv2.weight") { *out = {m->conv2_w, WK_DTYPE_F16, (size_t)d * d * 3, 2}; return true; }
+    if (name == "model.encoder.conv2.bias") return F(m->conv2_b, d);
+    if (name == "model.encoder.embed_positions.weight") return F(m->enc_pos, (size_t)m->cfg.n_audio_ctx * d);
+    if (name == "model.encoder.layer_norm.weight") return F(m->enc_ln.g, d);
+    if (name == "model.encoder.layer_norm.bias") return F(m->enc_ln.b, d);
+    if (name == "model.decoder.embed_tokens.weight" || name == "proj_out.weight") { *out = {m->emb, dt, (size_t)m->cfg.vocab * d, 0}; return true; }
+    if (name == "model.decoder.embed_positions.weight") return F(m->dec_pos, (size_t)m->cfg.n_text_ctx * d);
+    if (name == "model.decoder.layer_norm.weight") return F(m->dec_ln.g, d);
+    if (name == "model.decoder.layer_norm.bias") return F(m->dec_ln.b, d);
+    if (sscanf(name.c_str(), "model.encoder.layers.%d.%127s", &i, rest) == 2 && i >= 0 && i < (int)m->enc.size()) {
+        EncLayer& l = m->enc[i];
+        const std::string r = rest;
+        const size_t dd = (size_t)d * d;
+        if (r == "self_attn.q_proj.weight") return W(l.wqkv, 0, dd);
+        if (r == "self_attn.k_proj.weight") return W(l.wqkv, d, dd);
+        if (r == "self_attn.v_proj.weight") return W(l.wqkv, 2 * (size_t)d, dd);
+        if (r == "self_attn.q_proj.bias") return F(l.bqkv, d);
+        if (r == "self_attn.k_proj.bias") return F(l.bqkv + d, d);
+        if (r == "self_attn.v_proj.bias") return F(l.bqkv + 2 * d, d);
+        if (r == "self_attn.out_proj.weight") return W(l.wo, 0, dd);
+        if (r == "self_attn.out_proj.bias") return F(l.bo, d);
+        if (r == "self_attn_layer_norm.weight") return F(l.ln1.g, d);
+        if (r == "self_attn_layer_norm.bias") return F(l.ln1.b, d);
+        if (r == "final_layer_norm.weight") return F(l.ln2.g, d);
+        if (r == "final_layer_norm.bias") return F(l.ln2.b, d);
+        if (r == "fc1.weight") return W(l.w1, 0, 4 * dd);
+        if (r == "fc1.bias") return F(l.b1, 4 * (size_t)d);
+        if (r == "fc2.weight") return W(l.w2, 0, 4 * dd);
+        if (r == "fc2.bias") return F(l.b2, d);
+        return false;
+    }
+    if (sscanf(name.c_str(), "model.decoder.layers.%d.%127s", &i, rest) == 2 && i >= 0 && i < (int)m->dec.size()) {
+        DecLayer& l = m->dec[i];
+        const std::string r = rest;
+        const size_t dd = (size_t)d * d;
+        if (r == "self_attn.q_proj.weight") return W(l.wqkv, 0, dd);
+        if (r == "self_attn.k_proj.weight") return W(l.wqkv, d, dd);
+        if (r == "self_attn.v_proj.weight") return W(l.wqkv, 2 * (size_t)d, dd);
+        if (r == "self_attn.q_proj.bias") return F(l.bq, d);
+        if (r == "self_attn.v_proj.bias") return F(l.bv, d);
+        if (r == "self_attn.out_proj.weight") return W(l.wo, 0, dd);
+        if (r == "self_attn.out_proj.bias") return F(l.bo, d);
+        if (r == "self_attn_layer_norm.weight") return F(l.ln1.g, d);
+        if (r == "self_attn_layer_norm.bias") return F(l.ln1.b, d);
+        if (r == "encoder_attn.q_proj.weight") return W(l.wcq, 0, dd);
+        if (r == "encoder_attn.q_proj.bias") return F(l.bcq, d);
+        if (r == "encoder_attn.k_proj.weight") return W(m->wckv, (size_t)(2 * i) * d, dd);
+        if (r == "encoder_attn.v_proj.weight") return W(m->wckv, (size_t)(2 * i + 1) * d, dd);
+        if (r == "encoder_attn.v_proj.bias") return F(m->bckv + (size_t)(2 * i + 1) * d, d);
+        if (r == "encoder_attn.out_proj.weight") return W(l.wco, 0, dd);
+        if (r == "encoder_attn.out_proj.bias") return F(l.bco, d);
+        if (r == "encoder_attn_layer_norm.weight") return F(l.lnx.g, d);
+        if (r == "encoder_attn_layer_norm.bias") return F(l.lnx.b, d);
+        if (r == "final_layer_norm.weight") return F(l.ln3.g, d);
+        if (r == "final_layer_norm.bias") return F(l.ln3.b, d);
+        if (r == "fc1.weight") return W(l.w1, 0, 4 * dd);
+        if (r == "fc1.bias") return F(l.b1, 4 * (size_t)d);
+        if (r == "fc2.weight") return W(l.w2, 0, 4 * dd);
+        if (r == "fc2.bias") return F(l.b2, d);
+        return false;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------- encoder schedule
+static GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int dtype, int mode, void* out, int64_t ld_out,
+                           const float* bias, int gelu) {
+    GemmDesc g;
+    memset(&g, 0, sizeof(g));
+    g.a = a; g.a_rows = M; g.a_cols = K; g.a_ld = K; g.a_batches = 1;
+    g.b = w; g.b_rows = N; g.b_ld = K; g.in_dtype = dtype;
+    g.m_rows_per_batch = (int)M; g.n = N; g.k = K; g.taps = 1;
+    g.bn = N >= 256 ? 256 : round_up(N, 16);
+    g.splits = 1; g.mode = mode; g.gelu = gelu; g.out = out; g.ld_out = ld_out; g.out_rows_per_batch = M; g.bias = bias;
+    return g;
+}
+
+static wk_status encode_chunk(wk_model* m, int B) {
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, T = c.n_audio_ctx, dt = c.dtype;
+    cudaStream_t s = m->stream;
+    const int64_t M = (int64_t)B * T;
+    // conv1 (k=3, pad 1) + GELU as implicit GEMM over the time-major mel: taps = 3 row shifts of the same tensor map
+    {
+        GemmDesc g;
+        memset(&g, 0, sizeof(g));
+        g.a = m->mel; g.a_rows = kMelRows; g.a_cols = kMelCols; g.a_ld = kMelCols; g.a_batch_stride = (int64_t)kMelRows * kMelCols;
+        g.a_batches = B; g.a_3d = 1;
+        g.b = m->conv1_w; g.b_rows = d; g.b_ld = 3 * kMelCols; g.in_dtype = WK_DTYPE_F16;
+        g.m_rows_per_batch = 2 * T; g.n = d; g.k = kMelCols; g.taps = 3;
+        for (int t = 0; t < 3; ++t) { g.tap_row_shift[t] = t; g.tap_col_off[t] = 0; }
+        g.bn = d >= 256 ? 256 : round_up(d, 16);
+        g.splits = 1; g.mode = GEMM_OUT_T16; g.gelu = 1;
+        g.out = (char*)m->h1 + (size_t)d * 2;  // row 0 of every window is the zero pad
+        g.ld_out = d; g.out_rows_per_batch = kMelRows; g.bias = m->conv1_b;
+        WK_CHECK(gemm_tcgen05(g, m->num_sms, s));
+    }
+    // conv2 (k=3, stride 2, pad 1) + GELU + positional embedding -> residual stream x (f32)
+    {
+        GemmDesc g;
+        memset(&g, 0, sizeof(g));
+        g.a = m->h1; g.a_rows = kMelRows / 2; g.a_cols = 2 * d; g.a_ld = 2 * d; g.a_batch_stride = (int64_t)kMelRows * d;
+        g.a_batches = B; g.a_3d = 1;
+        g.b = m->conv2_w; g.b_rows = d; g.b_ld = 3 * d; g.in_dtype = WK_DTYPE_F16;
+        g.m_rows_per_batch = T; g.n = d; g.k = d; g.taps = 3;
+        g.tap_row_shift[0] = 0; g.tap_col_off[0] = 0;
+        g.tap_row_shift[1] = 0; g.tap_col_off[1] = d;
+        g.tap_row_shift[2] = 1; g.tap_col_off[2] = 0;
+        g.bn = d >= 256 ? 256 : round_up(d, 16);
+        g.splits = 1; g.mode = GEMM_OUT_F32_GELU_POS; g.gelu = 1;
+        g.out = m->x; g.ld_out = d; g.out_rows_per_batch = T; g.bias = m->conv2_b; g.pos = m->enc_pos; g.ld_pos = d;
+        WK_CHECK(gemm_tcgen05(g, m->num_sms, s));
+    }
+    for (int li = 0; li < c.enc_layers; ++li) {
+        EncLayer& l = m->enc[li];
+        WK_CHECK(layernorm_f32_to_16(m->x, l.ln1.g, l.ln1.b, m->xn, M, d, dt, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(m->xn, M, d, l.wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, l.bqkv, 0), m->num_sms, s));
+        WK_CHECK(encoder_attention(m->qkv, m->attn, B, T, c.n_heads, dt, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(m->attn, M, d, l.wo, d, dt, GEMM_OUT_F32_ADD, m->x, d, l.bo, 0), m->num_sms, s));
+        WK_CHECK(layernorm_f32_to_16(m->x, l.ln2.g, l.ln2.b, m->xn, M, d, dt, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(m->xn, M, d, l.w1, 4 * d, dt, GEMM_OUT_T16, m->ffn, 4 * d, l.b1, 1), m->num_sms, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(m->ffn, M, 4 * d, l.w2, d, dt, GEMM_OUT_F32_ADD, m->x, d, l.b2, 0), m->num_sms, s));
+    }
+    WK_CHECK(layernorm_f32_to_16(m->x, m->enc_ln.g, m->enc_ln.b, m->enc_out, M, d, dt, s));
+    return WK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- decoder schedule
+static wk_status dec_gemm(wk_session* s, const void* w, int N, int K, const void* act, int* splits_out) {
+    wk_model* m = s->m;
+    GemmDesc g;
+    memset(&g, 0, sizeof(g));
+    // swap-AB: A = weights [N, K] (128 output features per tile), B = activations [Bp, K]
+    g.a = w; g.a_rows = N; g.a_cols = K; g.a_ld = K; g.a_batches = 1;
+    g.b = act; g.b_rows = s->bp; g.b_ld = K; g.in_dtype = m->cfg.dtype;
+    g.m_rows_per_batch = N; g.n = s->bp; g.k = K; g.taps = 1; g.bn = s->bp;
+    const int tiles = (N + 127) / 128;
+    g.splits = choose_splits(tiles, K / 64, m->num_sms);
+    g.mode = GEMM_OUT_PARTIAL_T; g.out = s->partial; g.ld_out = N; g.out_rows_per_batch = N; g.partial_cols = s->bp;
+    if ((size_t)g.splits * s->bp * N > s->partial_elems) { set_error("partial workspace too small"); return WK_ERR_DECODING_FAILED; }
+    *splits_out = g.splits;
+    return gemm_tcgen05(g, m->num_sms, m->stream);
+}
+
+// one decoder forward for every bound sequence.  explicit_pos == nullptr: loop mode (token/position from DecodeState)
+static wk_status decoder_forward(wk_session* s, int prompt_len, int ts_begin, const int32_t* explicit_pos) {
+    wk_model* m = s->m;
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, H = c.n_heads, dt = c.dtype, B = s->batch, Bp = s->bp, T = c.n_audio_ctx;
+    cudaStream_t st = m->stream;
+    const size_t self_layer = (size_t)s->max_batch * H * kKvMaxLen * 64 * 2;   // bytes per layer
+    const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;          // bytes per (layer, k|v)
+    int sp = 1;
+    WK_CHECK(decoder_embed_ln(m->emb, m->dec_pos, m->dec[0].ln1.g, m->dec[0].ln1.b, s->st, prompt_len, ts_begin, s->x, s->xn, B, d, dt,
+                              explicit_pos ? 1 : 0, explicit_pos, st));
+    for (int li = 0; li < c.dec_layers; ++li) {
+        DecLayer& l = m->dec[li];
+        WK_CHECK(dec_gemm(s, l.wqkv, 3 * d, d, s->xn, &sp));
+        WK_CHECK(decoder_self_attention(s->partial, sp, Bp, l.bq, l.bv, (char*)s->self_k + li * self_layer, (char*)s->self_v + li * self_layer,
+                                        s->st.step, explicit_pos, s->attn, B, H, kKvMaxLen, dt, st));
+        WK_CHECK(dec_gemm(s, l.wo, d, d, s->attn, &sp));
+        WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.bo, l.lnx.g, l.lnx.b, s->x, s->xn, B, d, dt, st));
+        WK_CHECK(dec_gemm(s, l.wcq, d, d, s->xn, &sp));
+        WK_CHECK(decoder_cross_attention(s->partial, sp, Bp, l.bcq, (char*)s->cross_kv + (size_t)(2 * li) * cross_block,
+                                         (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st));
+        WK_CHECK(dec_gemm(s, l.wco, d, d, s->attn, &sp));
+        WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.bco, l.ln3.g, l.ln3.b, s->x, s->xn, B, d, dt, st));
+        WK_CHECK(dec_gemm(s, l.w1, 4 * d, d, s->xn, &sp));
+        WK_CHECK(decoder_reduce_bias_gelu(s->partial, sp, Bp, l.b1, s->ffn, B, 4 * d, dt, st));
+        WK_CHECK(dec_gemm(s, l.w2, d, 4 * d, s->ffn, &sp));
+        const LayerNormW& nxt = (li + 1 < c.dec_layers) ? m->dec[li + 1].ln1 : m->dec_ln;
+        WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.b2, nxt.g, nxt.b, s->x, s->xn, B, d, dt, st));
+    }
+    // logits = xn . E^T  (tied embedding), written [B][V] f32 by the transposed-store epilogue (splits = 1)
+    {
+        GemmDesc g;
+        memset(&g, 0, sizeof(g));
+        g.a = m->emb; g.a_rows = c.vocab; g.a_cols = d; g.a_ld = d; g.a_batches = 1;
+        g.b = s->xn; g.b_rows = Bp; g.b_ld = d; g.in_dtype = dt;
+        g.m_rows_per_batch = c.vocab; g.n = Bp; g.k = d; g.taps = 1; g.bn = Bp; g.splits = 1;
+        g.mode = GEMM_OUT_PARTIAL_T; g.out = s->logits; g.ld_out = c.vocab; g.out_rows_per_batch = c.vocab; g.partial_cols = B;
+        WK_CHECK(gemm_tcgen05(g, m->num_sms, st));
+    }
+    return WK_OK;
+}
+
+static SamplerParams make_sampler_params(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, int is_multilingual,
+                                         int sample_begin_ts, int sample_begin_blank, int prompt_len) {
+    SamplerParams p;
+    memset(&p, 0, sizeof(p));
+    p.st = *st;
+    p.vocab = s->m->cfg.vocab;
+    p.is_multilingual = is_multilingual;
+    p.sample_begin_ts = sample_begin_ts;
+    p.sample_begin_blank = sample_begin_blank;
+    p.suppress = s->suppress_dev; p.n_suppress = 0;
+    p.language_tokens = nullptr; p.n_language_tokens = 0; p.language_sample_begin = 0;
+    p.temperature = o->temperature; p.top_k = o->top_k; p.seed = o->seed;
+    p.has_first_thr = o->has_first_token_logprob_threshold; p.first_thr = o->first_token_logprob_threshold;
+    p.prompt_len = prompt_len;
+    p.max_ctx = kKvMaxLen;
+    return p;
+}
+
+// uploads the (< specialTokenBegin) suppress list (TextDecoder.swift:876-879); returns count
+static wk_status upload_suppress(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, int* n_out) {
+    std::vector<int32_t> sup;
+    for (int i = 0; i < o->n_suppress_tokens; ++i)
+        if (o->suppress_tokens[i] < st->special_token_begin && o->suppress_tokens[i] >= 0) sup.push_back(o->suppress_tokens[i]);
+    if (sup.size() > 4096) { set_error("too many suppress tokens"); return WK_ERR_INVALID_ARGUMENT; }
+    if (!sup.empty()) WK_CUDA_CHECK(cudaMemcpyAsync(s->suppress_dev, sup.data(), sup.size() * 4, cudaMemcpyHostToDevice, s->m->stream));
+    *n_out = (int)sup.size();
+    return WK_OK;
+}
+
+// TextUtilities.compressionRatio(of: [Int]) (TextUtilities.swift:14-28): raw DEFLATE of the Int32 LE bytes
+static float compression_ratio(const std::vector<int32_t>& toks) {
+    if (toks.empty()) return INFINITY;
+    const uLong n = (uLong)toks.size() * 4;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, 5, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return INFINITY;
+    std::vector<unsigned char> out(deflateBound(&zs, n) + 64);
+    zs.next_in = (Bytef*)toks.data(); zs.avail_in = n;
+    zs.next_out = out.data(); zs.avail_out = (uInt)out.size();
+    const int r = deflate(&zs, Z_FINISH);
+    const uLong clen = zs.total_out;
+    deflateEnd(&zs);
+    if (r != Z_STREAM_END || clen == 0) return INFINITY;
+    return (float)n / (float)clen;
+}
+
+}  // namespace wk
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* wk_last_error(void) { return wk::g_err; }
+const char* wk_version(void) { return "wkb200 0.1 (sm_100a)"; }
+
+int32_t wk_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return 0;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) return 0;
+    return p.major == 10 ? 1 : 0;
+}
+
+void wk_default_config(const char* variant, wk_model_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->n_audio_ctx = 1500; c->n_text_ctx = 448; c->dtype = WK_DTYPE_BF16; c->max_batch = 16;
+    const std::string v = variant ? variant : "large-v3";
+    if (v == "tiny.en" || v == "tiny") { c->n_mels = 80; c->d_model = 384; c->n_heads = 6; c->enc_layers = 4; c->dec_layers = 4; c->vocab = v == "tiny" ? 51865 : 51864; }
+    else if (v == "large-v3-turbo") { c->n_mels = 128; c->d_model = 1280; c->n_heads = 20; c->enc_layers = 32; c->dec_layers = 4; c->vocab = 51866; }
+    else if (v == "distil-large-v3") { c->n_mels = 128; c->d_model = 1280; c->n_heads = 20; c->enc_layers = 32; c->dec_layers = 2; c->vocab = 51866; }
+    else if (v == "toy") { c->n_mels = 80; c->d_model = 128; c->n_heads = 2; c->enc_layers = 2; c->dec_layers = 2; c->vocab = 1024; }
+    else if (v == "toy128") { c->n_mels = 128; c->d_model = 256; c->n_heads = 4; c->enc_layers = 2; c->dec_layers = 2; c->vocab = 2048; }
+    else { c->n_mels = 128; c->d_model = 1280; c->n_heads = 20; c->enc_layers = 32; c->dec_layers = 32; c->vocab = 51866; }
+}
+
+wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model** out) {
+    if (!cfg || !out) { set_error("wk_model_create: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    if (!wk_device_available()) {
+        set_error("no sm_100 CUDA device visible: libwkb200 has no CPU fallback");
+        return WK_ERR_MODELS_UNAVAILABLE;
+    }
+    if (cfg->d_model != cfg->n_heads * 64 || cfg->d_model % 128 != 0 || (cfg->n_mels != 80 && cfg->n_mels != 128) ||
+        cfg->n_audio_ctx != 1500 || cfg->max_batch < 1 || cfg->vocab < 16 ||
+        (cfg->dtype != WK_DTYPE_BF16 && cfg->dtype != WK_DTYPE_F16)) {
+        set_error("wk_model_create: unsupported configuration (d_model %d heads %d mels %d ctx %d dtype %d)", cfg->d_model,
+                  cfg->n_heads, cfg->n_mels, cfg->n_audio_ctx, cfg->dtype);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    WK_CUDA_CHECK(cudaSetDevice(device));
+    wk_model* m = new wk_model();
+    m->cfg = *cfg;
+    m->device = device;
+    cudaDeviceProp prop;
+    WK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    m->num_sms = prop.multiProcessorCount;
+    WK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto& e : m->ev) WK_CUDA_CHECK(cudaEventCreate(&e));
+    wk_status s = model_alloc(m);
+    if (s != WK_OK) return s;
+    WK_CHECK(mel_tables_create(cfg->n_mels, &m->mel_tables));
+    m->mel_tensor = {m->mel, 0, WK_DTYPE_F16, 0, m};
+    m->enc_tensor = {m->enc_out, 1, cfg->dtype, 0, m};
+    *out = m;
+    return WK_OK;
+}
+
+wk_status wk_model_set_tensor(wk_model* m, const char* name, const void* data, int32_t dtype, const int64_t* shape, int32_t ndim) {
+    if (!m || !name || !data) { set_error("wk_model_set_tensor: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    Dest dst;
+    if (!resolve_name(m, name, &dst)) {
+        if (strstr(name, "k_proj.bias")) return WK_OK;  // Whisper has no key bias; tolerate zero tensors
+        set_error("wk_model_set_tensor: unknown parameter '%s'", name);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= (size_t)shape[i];
+    if (numel != dst.numel) {
+        set_error("wk_model_set_tensor: '%s' has %zu elements, expected %zu", name, numel, dst.numel);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    void* tmp = nullptr;
+    WK_CUDA_CHECK(cudaMalloc(&tmp, numel * esize(dtype)));
+    WK_CUDA_CHECK(cudaMemcpy(tmp, data, numel * esize(dtype), cudaMemcpyDefault));
+    wk_status st = WK_OK;
+    if (dst.special) {
+        float* f = nullptr;
+        WK_CUDA_CHECK(cudaMalloc(&f, numel * 4));
+        st = convert_to_16(tmp, dtype, f, WK_DTYPE_F32, (int64_t)numel, m->stream);
+        const int co = m->cfg.d_model, ci = dst.special == 1 ? m->cfg.n_mels : m->cfg.d_model, cip = dst.special == 1 ? kMelCols : m->cfg.d_model;
+        const long long n = (long long)co * 3 * cip;
+        conv_w_rearrange_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(f, (__half*)dst.p, co, ci, cip);
+        cudaStreamSynchronize(m->stream);
+        cudaFree(f);
+    } else {
+        st = convert_to_16(tmp, dtype, dst.p, dst.dtype, (int64_t)numel, m->stream);
+        cudaStreamSynchronize(m->stream);
+    }
+    cudaFree(tmp);
+    return st;
+}
+
+wk_status wk_model_finalize(wk_model* m) {
+    if (!m) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    m->finalized = true;
+    return WK_OK;
+}
+
+wk_status wk_model_init_random(wk_model* m, uint64_t seed, float std) {
+    if (!m) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, dt = c.dtype;
+    cudaStream_t s = m->stream;
+    uint64_t k = seed * 1000003ull;
+    auto W = [&](void* p, size_t n, int dtype) { return fill_random_16(p, (int64_t)n, ++k, std, 0.f, dtype, s); };
+    auto F = [&](float* p, size_t n, float mean) { return fill_random_f32(p, (int64_t)n, ++k, std, mean, s); };
+    auto LN = [&](LayerNormW& l) { wk_status r = F(l.g, d, 1.f); return r != WK_OK ? r : F(l.b, d, 0.f); };
+    WK_CHECK(W(m->conv1_w, (size_t)d * 3 * 128, WK_DTYPE_F16));
+    if (c.n_mels < kMelCols) {  // zero the padded input channels (keeps the padded GEMM exact)
+        std::vector<float> w((size_t)d * c.n_mels * 3);
+        srand((unsigned)seed);
+        for (auto& v : w) v = std * ((rand() / (float)RAND_MAX) * 2.f - 1.f) * 1.7f;
+        int64_t shp[3] = {d, c.n_mels, 3};
+        WK_CHECK(wk_model_set_tensor(m, "model.encoder.conv1.weight", w.data(), WK_DTYPE_F32, shp, 3));
+    }
+    WK_CHECK(F(m->conv1_b, d, 0.f));
+    WK_CHECK(W(m->conv2_w, (size_t)d * 3 * d, WK_DTYPE_F16));
+    WK_CHECK(F(m->conv2_b, d, 0.f));
+    {
+        std::vector<float> pe((size_t)c.n_audio_ctx * d);
+        const int half = d / 2;
+        const double inc = log(10000.0) / (half - 1);
+        for (int t = 0; t < c.n_audio_ctx; ++t)
+            for (int i = 0; i < half; ++i) {
+                const double a = t * exp(-inc * i);
+                pe[(size_t)t * d + i] = (float)sin(a);
+                pe[(size_t)t * d + half + i] = (float)cos(a);
+            }
+        WK_CUDA_CHECK(cudaMemcpyAsync(m->enc_pos, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice, s));
+        WK_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    for (auto& l : m->enc) {
+        WK_CHECK(LN(l.ln1)); WK_CHECK(LN(l.ln2));
+        WK_CHECK(W(l.wqkv, (size_t)3 * d * d, dt)); WK_CHECK(F(l.bqkv, 3 * d, 0.f));
+        WK_CUDA_CHECK(cudaMemsetAsync(l.bqkv + d, 0, d * 4, s));  // no key bias
+        WK_CHECK(W(l.wo, (size_t)d * d, dt)); WK_CHECK(F(l.bo, d, 0.f));
+        WK_CHECK(W(l.w1, (size_t)4 * d * d, dt)); WK_CHECK(F(l.b1, 4 * d, 0.f));
+        WK_CHECK(W(l.w2, (size_t)4 * d * d, dt)); WK_CHECK(F(l.b2, d, 0.f));
+    }
+    WK_CHECK(LN(m->enc_ln));
+    WK_CHECK(W(m->emb, (size_t)c.vocab * d, dt));
+    WK_CHECK(F(m->dec_pos, (size_t)c.n_text_ctx * d, 0.f));
+    for (size_t i = 0; i < m->dec.size(); ++i) {
+        DecLayer& l = m->dec[i];
+        WK_CHECK(LN(l.ln1)); WK_CHECK(LN(l.lnx)); WK_CHECK(LN(l.ln3));
+        WK_CHECK(W(l.wqkv, (size_t)3 * d * d, dt)); WK_CHECK(F(l.bq, d, 0.f)); WK_CHECK(F(l.bv, d, 0.f));
+        WK_CHECK(W(l.wo, (size_t)d * d, dt)); WK_CHECK(F(l.bo, d, 0.f));
+        WK_CHECK(W(l.wcq, (size_t)d * d, dt)); WK_CHECK(F(l.bcq, d, 0.f));
+        WK_CHECK(W(l.wco, (size_t)d * d, dt)); WK_CHECK(F(l.bco, d, 0.f));
+        WK_CHECK(W(l.w1, (size_t)4 * d * d, dt)); WK_CHECK(F(l.b1, 4 * d, 0.f));
+        WK_CHECK(W(l.w2, (size_t)4 * d * d, dt)); WK_CHECK(F(l.b2, d, 0.f));
+    }
+    WK_CHECK(LN(m->dec_ln));
+    WK_CHECK(W(m->wckv, (size_t)2 * m->dec.size() * d * d, dt));
+    WK_CHECK(F(m->bckv, (size_t)2 * m->dec.size() * d, 0.f));
+    for (size_t i = 0; i < m->dec.size(); ++i) WK_CUDA_CHECK(cudaMemsetAsync(m->bckv + 2 * i * d, 0, d * 4, s));  // no key bias
+    WK_CUDA_CHECK(cudaStreamSynchronize(s));
+    m->finalized = true;
+    return WK_OK;
+}
+
+wk_status wk_model_info_get(const wk_model* m, wk_model_info* o) {
+    if (!m || !o) return WK_ERR_INVALID_ARGUMENT;
+    const wk_model_config& c = m->cfg;
+    o->n_mels = c.n_mels; o->n_audio_ctx = c.n_audio_ctx; o->d_model = c.d_model; o->n_heads = c.n_heads;
+    o->enc_layers = c.enc_layers; o->dec_layers = c.dec_layers; o->vocab = c.vocab;
+    o->kv_embed_dim = c.dec_layers * c.d_model; o->kv_max_len = kKvMaxLen; o->window_samples = kWindowSamples;
+    o->has_alignment_heads = 0;
+    o->is_multilingual = c.vocab != 51864;
+    o->dtype = c.dtype; o->max_batch = c.max_batch;
+    return WK_OK;
+}
+
+void wk_model_free(wk_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(m->conv1_w); fr(m->conv1_b); fr(m->conv2_w); fr(m->conv2_b); fr(m->enc_pos);
+    for (auto& l : m->enc) { fr(l.ln1.g); fr(l.ln1.b); fr(l.ln2.g); fr(l.ln2.b); fr(l.wqkv); fr(l.bqkv); fr(l.wo); fr(l.bo); fr(l.w1); fr(l.b1); fr(l.w2); fr(l.b2); }
+    fr(m->enc_ln.g); fr(m->enc_ln.b); fr(m->emb); fr(m->dec_pos);
+    for (auto& l : m->dec) {
+        fr(l.ln1.g); fr(l.ln1.b); fr(l.lnx.g); fr(l.lnx.b); fr(l.ln3.g); fr(l.ln3.b); fr(l.wqkv); fr(l.bq); fr(l.bv); fr(l.wo); fr(l.bo);
+        fr(l.wcq); fr(l.bcq); fr(l.wco); fr(l.bco); fr(l.w1); fr(l.b1); fr(l.w2); fr(l.b2);
+    }
+    fr(m->dec_ln.g); fr(m->dec_ln.b); fr(m->wckv); fr(m->bckv);
+    fr(m->pcm_dev); fr(m->nvalid_dev); fr(m->gmax); fr(m->mel); fr(m->h1); fr(m->x); fr(m->xn); fr(m->qkv); fr(m->attn); fr(m->ffn); fr(m->enc_out);
+    mel_tables_free(m->mel_tables);
+    for (auto& e : m->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+void* wk_model_stream(wk_model* m) { return m ? (void*)m->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------- tensors
+wk_status wk_tensor_shape(const wk_tensor* t, int64_t* shape4, int32_t* ndim, int32_t* dtype) {
+    if (!t) return WK_ERR_INVALID_ARGUMENT;
+    const wk_model_config& c = t->owner->cfg;
+    if (t->kind == 0) { shape4[0] = t->batch; shape4[1] = c.n_mels; shape4[2] = 1; shape4[3] = 3000; }
+    else { shape4[0] = t->batch; shape4[1] = c.d_model; shape4[2] = 1; shape4[3] = c.n_audio_ctx; }
+    if (ndim) *ndim = 4;
+    if (dtype) *dtype = t->dtype;
+    return WK_OK;
+}
+
+wk_status wk_tensor_to_host(const wk_tensor* t, float* dst, int64_t dst_elems) {
+    if (!t || !dst) return WK_ERR_INVALID_ARGUMENT;
+    wk_model* m = t->owner;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const wk_model_config& c = m->cfg;
+    const int64_t rows = t->kind == 0 ? 3000 : c.n_audio_ctx, cols = t->kind == 0 ? c.n_mels : c.d_model;
+    const int64_t n = t->batch * rows * cols;
+    if (dst_elems < n) { set_error("wk_tensor_to_host: destination too small (%lld < %lld)", (long long)dst_elems, (long long)n); return WK_ERR_INVALID_ARGUMENT; }
+    float* tmp = nullptr;
+    WK_CUDA_CHECK(cudaMalloc(&tmp, n * 4));
+    wk_status s = t->kind == 0
+        ? transpose_to_host_layout(t->data, tmp, t->batch, rows, cols, kMelRows, 1, kMelCols, WK_DTYPE_F16, m->stream)
+        : transpose_to_host_layout(t->data, tmp, t->batch, rows, cols, rows, 0, cols, t->dtype, m->stream);
+    if (s == WK_OK) {
+        cudaError_t e = cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) { set_error("wk_tensor_to_host: %s", cudaGetErrorString(e)); s = WK_ERR_CUDA; }
+    }
+    cudaFree(tmp);
+    return s;
+}
+
+void wk_tensor_free(wk_tensor*) { /* tensors are views into model-owned workspaces */ }
+
+// ---------------------------------------------------------------------------------------------- mel / encode
+static wk_status mel_device(wk_model* m, const float* pcm_dev, int64_t n, int64_t stride, const int32_t* nvalid_dev) {
+    return mel_forward(m->mel_tables, pcm_dev, n, stride, nvalid_dev, m->mel, m->gmax, m->stream);
+}
+
+wk_status wk_mel(wk_model* m, const float* pcm, int64_t n_windows, int64_t stride, const int32_t* samples_per_window, wk_tensor** mel_out) {
+    if (!m || !pcm || !mel_out) { set_error("wk_mel: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    if (n_windows < 1 || n_windows > m->cfg.max_batch) { set_error("wk_mel: n_windows %lld outside [1, max_batch=%d]", (long long)n_windows, m->cfg.max_batch); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+    if (stride < kWindowSamples) {
+        // short rows: treat as padOrTrim of each row
+        if (!samples_per_window) { set_error("wk_mel: stride %lld < 480000 requires samples_per_window", (long long)stride); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+    }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    cudaPointerAttributes at;
+    const bool on_device = cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const float* src = pcm;
+    int64_t src_stride = stride;
+    if (!on_device || stride < kWindowSamples) {
+        if (stride >= kWindowSamples) {
+            WK_CUDA_CHECK(cudaMemcpy2DAsync(m->pcm_dev, kWindowSamples * 4, pcm, stride * 4, kWindowSamples * 4, n_windows, cudaMemcpyDefault, m->stream));
+        } else {
+            WK_CUDA_CHECK(cudaMemsetAsync(m->pcm_dev, 0, (size_t)n_windows * kWindowSamples * 4, m->stream));
+            WK_CUDA_CHECK(cudaMemcpy2DAsync(m->pcm_dev, kWindowSamples * 4, pcm, stride * 4, stride * 4, n_windows, cudaMemcpyDefault, m->stream));
+        }
+        src = m->pcm_dev;
+        src_stride = kWindowSamples;
+    }
+    const int32_t* nv = nullptr;
+    if (samples_per_window) {
+        for (int64_t i = 0; i < n_windows; ++i)
+            if (samples_per_window[i] < 0 || samples_per_window[i] > kWindowSamples) { set_error("wk_mel: samples_per_window[%lld] out of range", (long long)i); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+        WK_CUDA_CHECK(cudaMemcpyAsync(m->nvalid_dev, samples_per_window, n_windows * 4, cudaMemcpyHostToDevice, m->stream));
+        nv = m->nvalid_dev;
+    }
+    WK_CHECK(mel_device(m, src, n_windows, src_stride, nv));
+    m->mel_tensor.batch = n_windows;
+    *mel_out = &m->mel_tensor;
+    return WK_OK;
+}
+
+wk_status wk_encode(wk_model* m, const wk_tensor* mel, wk_tensor** enc_out) {
+    if (!m || !mel || !enc_out) { set_error("wk_encode: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    if (!m->finalized) { set_error("wk_encode: model weights not finalized"); return WK_ERR_MODELS_UNAVAILABLE; }
+    if (mel->kind != 0 || mel->owner != m) { set_error("wk_encode: input is not this model's mel tensor"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    WK_CHECK(encode_chunk(m, (int)mel->batch));
+    m->enc_tensor.batch = mel->batch;
+    *enc_out = &m->enc_tensor;
+    return WK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- session
+wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
+    if (!m || !out || max_batch < 1 || max_batch > 256) { set_error("wk_session_create: bad arguments (max_batch %d)", max_batch); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, H = c.n_heads, L = c.dec_layers, T = c.n_audio_ctx;
+    wk_session* s = new wk_session();
+    s->m = m;
+    s->max_batch = max_batch;
+    const int bpm = round_up(max_batch, 16);
+    WK_CHECK(alloc16(&s->cross_kv, (size_t)2 * L * max_batch * H * T * 64));
+    WK_CHECK(alloc16(&s->self_k, (size_t)L * max_batch * H * kKvMaxLen * 64));
+    WK_CHECK(alloc16(&s->self_v, (size_t)L * max_batch * H * kKvMaxLen * 64));
+    // split-K partial workspace: max over the decoder GEMM shapes of splits * N
+    size_t pe = 0;
+    const int shapes[4][2] = {{3 * d, d}, {d, d}, {4 * d, d}, {d, 4 * d}};
+    for (auto& sh : shapes) {
+        const int sp = choose_splits((sh[0] + 127) / 128, sh[1] / 64, m->num_sms);
+        pe = std::max(pe, (size_t)sp * sh[0]);
+    }
+    s->partial_elems = pe * bpm;
+    WK_CHECK(dmalloc(&s->partial, s->partial_elems));
+    WK_CHECK(dmalloc(&s->x, (size_t)bpm * d));
+    WK_CHECK(alloc16(&s->xn, (size_t)bpm * d));
+    WK_CHECK(alloc16(&s->attn, (size_t)bpm * d));
+    WK_CHECK(alloc16(&s->ffn, (size_t)bpm * 4 * d));
+    WK_CHECK(dmalloc(&s->logits, (size_t)max_batch * c.vocab));
+    WK_CHECK(dmalloc(&s->st.tokens, (size_t)max_batch * kKvMaxLen));
+    WK_CHECK(dmalloc(&s->st.n_tokens, max_batch));
+    WK_CHECK(dmalloc(&s->st.logprobs, (size_t)max_batch * kKvMaxLen));
+    WK_CHECK(dmalloc(&s->st.next_token, max_batch));
+    WK_CHECK(dmalloc(&s->st.done, max_batch));
+    WK_CHECK(dmalloc(&s->st.first_low, max_batch));
+    WK_CHECK(dmalloc(&s->st.steps, max_batch));
+    WK_CHECK(dmalloc(&s->st.step, 1));
+    WK_CHECK(dmalloc(&s->st.n_done, 1));
+    WK_CHECK(dmalloc(&s->st.input_ids, max_batch));
+    WK_CHECK(dmalloc(&s->prompt_dev, kKvMaxLen));
+    WK_CHECK(dmalloc(&s->pos_dev, max_batch));
+    WK_CHECK(dmalloc(&s->suppress_dev, 4096));
+    WK_CHECK(dmalloc(&s->lang_dev, 4096));
+    WK_CHECK(dmalloc(&s->tok_scratch, (size_t)max_batch * kKvMaxLen));
+    WK_CHECK(dmalloc(&s->ntok_scratch, max_batch));
+    WK_CHECK(dmalloc(&s->tokout_dev, max_batch));
+    WK_CHECK(dmalloc(&s->lpout_dev, max_batch));
+    *out = s;
+    return WK_OK;
+}
+
+void wk_session_free(wk_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->m->device);
+    cudaDeviceSynchronize();
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
+                    s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.step, s->st.n_done, s->st.input_ids,
+                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev, s->tok_scratch, s->ntok_scratch, s->tokout_dev, s->lpout_dev};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete s;
+}
+
+wk_status wk_session_reset(wk_session* s) {
+    if (!s) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
+    const wk_model_config& c = s->m->cfg;
+    const size_t n = (size_t)c.dec_layers * s->max_batch * c.n_heads * kKvMaxLen * 64 * 2;
+    WK_CUDA_CHECK(cudaMemsetAsync(s->self_k, 0, n, s->m->stream));
+    WK_CUDA_CHECK(cudaMemsetAsync(s->self_v, 0, n, s->m->stream));
+    return WK_OK;
+}
+
+wk_status wk_session_set_encoder_output(wk_session* s, const wk_tensor* enc) {
+    if (!s || !enc) { set_error("wk_session_set_encoder_output: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    wk_model* m = s->m;
+    if (enc->kind != 1 || enc->owner != m) { set_error("encoder output does not belong to this model"); return WK_ERR_INVALID_ARGUMENT; }
+    if (enc->batch < 1 || enc->batch > s->max_batch) { set_error("encoder batch %lld exceeds session max_batch %d", (long long)enc->batch, s->max_batch); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, T = c.n_audio_ctx;
+    s->batch = (int)enc->batch;
+    s->bp = round_up(s->batch, 16);
+    const int64_t M = enc->batch * T;
+    GemmDesc g = plain_gemm(enc->data, M, d, m->wckv, 2 * c.dec_layers * d, c.dtype, GEMM_OUT_T16_HEADS, s->cross_kv, 0, m->bckv, 0);
+    g.heads_T = T; g.heads_B = s->max_batch; g.heads_H = c.n_heads; g.heads_dmodel = d;
+    WK_CHECK(gemm_tcgen05(g, m->num_sms, m->stream));
+    return WK_OK;
+}
+
+wk_status wk_build_prompt(const wk_model* m, const wk_special_tokens* st, const wk_decode_opts* o, int32_t use_options, int32_t* out, int32_t cap, int32_t* n) {
+    // prefillDecoderInputs (TextDecoder.swift:163-216)
+    if (!m || !st || !out || !n) return WK_ERR_INVALID_ARGUMENT;
+    std::vector<int32_t> p;
+    p.push_back(st->start_of_transcript_token);
+    if (use_options && o) {
+        const bool multilingual = m->cfg.vocab != 51864;
+        if (multilingual) {
+            p.push_back(o->language_token >= 0 ? o->language_token : st->english_token);
+            p.push_back(o->task_translate ? st->translate_token : st->transcribe_token);
+        }
+        p.push_back(o->without_timestamps ? st->no_timestamps_token : st->time_token_begin);
+        if (o->n_prompt_tokens >= 0 && (o->prompt_tokens || o->n_prompt_tokens == 0)) {
+            const int maxlen = kKvMaxLen / 2 - 1;
+            std::vector<int32_t> q;
+            const int start = o->n_prompt_tokens > maxlen ? o->n_prompt_tokens - maxlen : 0;
+            q.push_back(st->start_of_previous_token);
+            for (int i = start; i < o->n_prompt_tokens; ++i)
+                if (o->prompt_tokens[i] < st->special_token_begin) q.push_back(o->prompt_tokens[i]);
+            q.insert(q.end(), p.begin(), p.end());
+            p.swap(q);
+        }
+        if (o->n_prefix_tokens >= 0 && (o->prefix_tokens || o->n_prefix_tokens == 0)) {
+            const int maxlen = kKvMaxLen / 2;
+            const int start = o->n_prefix_tokens > maxlen ? o->n_prefix_tokens - maxlen : 0;
+            for (int i = start; i < o->n_prefix_tokens; ++i)
+                if (o->prefix_tokens[i] < st->special_token_begin) p.push_back(o->prefix_tokens[i]);
+        }
+    }
+    if ((int)p.size() > cap) { set_error("wk_build_prompt: capacity %d < %zu", cap, p.size()); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    memcpy(out, p.data(), p.size() * 4);
+    *n = (int)p.size();
+    return WK_OK;
+}
+
+wk_status wk_decode_step(wk_session* s, const int32_t* input_ids, const int32_t* cache_length, float* logits_out) {
+    if (!s || !input_ids || !cache_length) { set_error("wk_decode_step: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    wk_model* m = s->m;
+    if (s->batch < 1) { set_error("wk_decode_step: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    for (int i = 0; i < s->batch; ++i) {
+        if (cache_length[i] < 0 || cache_length[i] >= kKvMaxLen) { set_error("wk_decode_step: cache_length[%d]=%d out of range", i, cache_length[i]); return WK_ERR_DECODING_LOGITS_FAILED; }
+        if (input_ids[i] < 0 || input_ids[i] >= m->cfg.vocab) { set_error("wk_decode_step: input_ids[%d]=%d out of range", i, input_ids[i]); return WK_ERR_DECODING_LOGITS_FAILED; }
+    }
+    WK_CUDA_CHECK(cudaMemcpyAsync(s->st.input_ids, input_ids, s->batch * 4, cudaMemcpyHostToDevice, m->stream));
+    WK_CUDA_CHECK(cudaMemcpyAsync(s->pos_dev, cache_length, s->batch * 4, cudaMemcpyHostToDevice, m->stream));
+    WK_CHECK(decoder_forward(s, 0, 0, s->pos_dev));
+    if (logits_out) WK_CUDA_CHECK(cudaMemcpyAsync(logits_out, s->logits, (size_t)s->batch * m->cfg.vocab * 4, cudaMemcpyDeviceToHost, m->stream));
+    cudaError_t e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) { set_error("wk_decode_step: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_LOGITS_FAILED; }
+    return WK_OK;
+}
+
+wk_status wk_session_last_logits(wk_session* s, float* logits_out) {
+    if (!s || !logits_out) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
+    WK_CUDA_CHECK(cudaMemcpyAsync(logits_out, s->logits, (size_t)s->batch * s->m->cfg.vocab * 4, cudaMemcpyDeviceToHost, s->m->stream));
+    WK_CUDA_CHECK(cudaStreamSynchronize(s->m->stream));
+    return WK_OK;
+}
+
+wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_decode_opts* opts, int32_t is_multilingual,
+                           const float* logits, int32_t batch, int32_t vocab, const int32_t* tokens, int32_t ld_tokens,
+                           const int32_t* n_tokens, int32_t sample_begin_ts, int32_t sample_begin_blank,
+                           const int32_t* language_tokens, int32_t n_language_tokens, int32_t language_sample_begin,
+                           int32_t* token_out, float* logprob_out, float* filtered_out) {
+    if (!m || !st || !opts || !logits || !n_tokens || batch < 1 || vocab < 2) { set_error("wk_filter_sample: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    float *dlog = nullptr, *dfil = nullptr, *dlp = nullptr;
+    int32_t *dtok = nullptr, *dn = nullptr, *dout = nullptr, *dsup = nullptr, *dlang = nullptr;
+    const int ldt = ld_tokens > 0 ? ld_tokens : 1;
+    WK_CUDA_CHECK(cudaMalloc(&dlog, (size_t)batch * vocab * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dfil, (size_t)batch * vocab * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dlp, batch * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dtok, (size_t)batch * ldt * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dn, batch * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dout, batch * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dsup, 4096 * 4));
+    WK_CUDA_CHECK(cudaMalloc(&dlang, 4096 * 4));
+    WK_CUDA_CHECK(cudaMemcpyAsync(dlog, logits, (size_t)batch * vocab * 4, cudaMemcpyDefault, s));
+    if (tokens && ld_tokens > 0) WK_CUDA_CHECK(cudaMemcpyAsync(dtok, tokens, (size_t)batch * ldt * 4, cudaMemcpyDefault, s));
+    WK_CUDA_CHECK(cudaMemcpyAsync(dn, n_tokens, batch * 4, cudaMemcpyDefault, s));
+    SamplerParams p;
+    memset(&p, 0, sizeof(p));
+    p.st = *st; p.vocab = vocab; p.is_multilingual = is_multilingual;
+    p.sample_begin_ts = sample_begin_ts; p.sample_begin_blank = sample_begin_blank;
+    std::vector<int32_t> sup;
+    for (int i = 0; i < opts->n_suppress_tokens; ++i)
+        if (opts->suppress_tokens[i] >= 0 && opts->suppress_tokens[i] < vocab) sup.push_back(opts->suppress_tokens[i]);
+    if (sup.size() > 4096 || n_language_tokens > 4096) { set_error("wk_filter_sample: list too long"); return WK_ERR_INVALID_ARGUMENT; }
+    if (!sup.empty()) WK_CUDA_CHECK(cudaMemcpyAsync(dsup, sup.data(), sup.size() * 4, cudaMemcpyHostToDevice, s));
+    p.suppress = dsup; p.n_suppress = (int)sup.size();
+    if (language_tokens && n_language_tokens > 0) {
+        WK_CUDA_CHECK(cudaMemcpyAsync(dlang, language_tokens, n_language_tokens * 4, cudaMemcpyHostToDevice, s));
+        p.language_tokens = dlang; p.n_language_tokens = n_language_tokens; p.language_sample_begin = language_sample_begin;
+    }
+    p.temperature = opts->temperature; p.top_k = opts->top_k; p.seed = opts->seed;
+    p.prompt_len = -1; p.max_ctx = kKvMaxLen;
+    DecodeState none;
+    memset(&none, 0, sizeof(none));
+    wk_status r = sampler_filter_sample(dlog, vocab, p, none, dtok, ldt, dn, dout, dlp, dfil, batch, s);
+    if (r == WK_OK) {
+        cudaError_t e = cudaSuccess;
+        if (token_out) e = cudaMemcpyAsync(token_out, dout, batch * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && logprob_out) e = cudaMemcpyAsync(logprob_out, dlp, batch * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && filtered_out) e = cudaMemcpyAsync(filtered_out, dfil, (size_t)batch * vocab * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("wk_filter_sample: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
+    }
+    cudaFree(dlog); cudaFree(dfil); cudaFree(dlp); cudaFree(dtok); cudaFree(dn); cudaFree(dout); cudaFree(dsup); cudaFree(dlang);
+    return r;
+}
+
+wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, const int32_t* prompt, int32_t n_prompt,
+                         wk_decode_result* results) {
+    if (!s || !st || !o || !prompt || !results) { set_error("wk_decode_text: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    wk_model* m = s->m;
+    if (s->batch < 1) { set_error("wk_decode_text: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    if (n_prompt < 1 || n_prompt >= kKvMaxLen) { set_error("wk_decode_text: prompt length %d out of range", n_prompt); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    for (int i = 0; i < n_prompt; ++i)
+        if (prompt[i] < 0 || prompt[i] >= m->cfg.vocab) { set_error("wk_decode_text: prompt token %d out of range", prompt[i]); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    cudaStream_t stream = m->stream;
+    const int B = s->batch;
+    const bool multilingual = m->cfg.vocab != 51864;
+    WK_CUDA_CHECK(cudaMemcpyAsync(s->prompt_dev, prompt, n_prompt * 4, cudaMemcpyHostToDevice, stream));
+    WK_CHECK(decode_state_init(s->st, s->prompt_dev, n_prompt, B, stream));
+    // createLogitsFilters (TextDecoder.swift:857-899): SuppressBlank(sampleBegin = prefilledIndex = 0),
+    // SuppressTokens(< specialTokenBegin), TimestampRules(sampleBegin = initialPrompt.count)
+    SamplerParams sp = make_sampler_params(s, st, o, multilingual ? 1 : 0, o->without_timestamps ? -1 : n_prompt,
+                                           o->suppress_blank ? 0 : -1, n_prompt);
+    WK_CHECK(upload_suppress(s, st, o, &sp.n_suppress));
+    const int loop_count = std::min(o->sample_length, kKvMaxLen - 1);  // TextDecoder.swift:566
+    const bool use_graph = getenv("WKB200_NO_GRAPH") == nullptr;
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    auto one_step = [&]() -> wk_status {
+        WK_CHECK(decoder_forward(s, n_prompt, st->time_token_begin, nullptr));
+        return sampler_filter_sample(s->logits, m->cfg.vocab, sp, s->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, B, stream);
+    };
+    int32_t n_done = 0;
+    long long launches_per_step = 0;
+    for (int step = 0; step < loop_count; ++step) {
+        if (step == 0 || !use_graph) {
+            WK_CHECK(one_step());
+        } else {
+            if (!s->graph_exec) {
+                cudaGraph_t graph = nullptr;
+                const long long before = g_launches.load();
+                WK_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                wk_status r = one_step();
+                cudaError_t e = cudaStreamEndCapture(stream, &graph);
+                launches_per_step = g_launches.load() - before;
+                g_launches.fetch_sub(launches_per_step);  // captured, not executed
+                if (r != WK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+                if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+                e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+            }
+            WK_CUDA_CHECK(cudaGraphLaunch(s->graph_exec, stream));
+            count_launch((int)launches_per_step);
+        }
+        if ((step & 15) == 15) {  // early exit when every window has completed
+            WK_CUDA_CHECK(cudaMemcpyAsync(&n_done, s->st.n_done, 4, cudaMemcpyDeviceToHost, stream));
+            WK_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (n_done >= B) break;
+        }
+    }
+    // ---- read back and finalise on the host (finalize + slicing + averages: TextDecoder.swift:776-853)
+    std::vector<int32_t> tokens((size_t)B * kKvMaxLen), n_tok(B), done(B), first_low(B), steps(B);
+    std::vector<float> lps((size_t)B * kKvMaxLen);
+    WK_CUDA_CHECK(cudaMemcpyAsync(tokens.data(), s->st.tokens, tokens.size() * 4, cudaMemcpyDeviceToHost, stream));
+    WK_CUDA_CHECK(cudaMemcpyAsync(lps.data(), s->st.logprobs, lps.size() * 4, cudaMemcpyDeviceToHost, stream));
+    WK_CUDA_CHECK(cudaMemcpyAsync(n_tok.data(), s->st.n_tokens, B * 4, cudaMemcpyDeviceToHost, stream));
+    WK_CUDA_CHECK(cudaMemcpyAsync(done.data(), s->st.done, B * 4, cudaMemcpyDeviceToHost, stream));
+    WK_CUDA_CHECK(cudaMemcpyAsync(first_low.data(), s->st.first_low, B * 4, cudaMemcpyDeviceToHost, stream));
+    WK_CUDA_CHECK(cudaMemcpyAsync(steps.data(), s->st.steps, B * 4, cudaMemcpyDeviceToHost, stream));
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("wk_decode_text: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
+    for (int b = 0; b < B; ++b) {
+        wk_decode_result& r = results[b];
+        memset(&r, 0, sizeof(r));
+        std::vector<int32_t> seg(tokens.begin() + (size_t)b * kKvMaxLen, tokens.begin() + (size_t)b * kKvMaxLen + n_tok[b]);
+        std::vector<float> slp(lps.begin() + (size_t)b * kKvMaxLen, lps.begin() + (size_t)b * kKvMaxLen + n_tok[b]);
+        r.n_current_tokens = n_tok[b];
+        r.steps = steps[b];
+        r.first_token_logprob_too_low = first_low[b];
+        if (seg.empty() || seg.back() != st->end_token) { seg.push_back(st->end_token); slp.push_back(0.f); }  // sampler.finalize
+        size_t start = 0, end = seg.size();
+        for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->start_of_transcript_token) { start = i; break; }
+        for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->end_token) { end = i; break; }
+        if (end >= seg.size()) end = seg.size() - 1;
+        if (end < start) start = 0;
+        float sum = 0.f;
+        std::vector<int32_t> words;
+        r.n_tokens = 0;
+        for (size_t i = start; i <= end && r.n_tokens < 226; ++i) {
+            r.tokens[r.n_tokens] = seg[i];
+            r.token_logprobs[r.n_tokens] = slp[i];
+            sum += slp[i];
+            if (seg[i] < st->special_token_begin) words.push_back(seg[i]);
+            ++r.n_tokens;
+        }
+        r.avg_logprob = sum / (float)r.n_tokens;
+        r.compression_ratio = compression_ratio(words);
+        r.temperature = roundf(o->temperature * 1000.f) / 1000.f;
+        // DecodingFallback (Models.swift:357-381); noSpeechProb is always 0 in the reference (TextDecoder.swift:802)
+        r.needs_fallback = 0; r.fallback_reason = 0;
+        if (first_low[b]) { r.needs_fallback = 1; r.fallback_reason = 1; }
+        else if (o->has_no_speech_threshold && 0.f > o->no_speech_threshold) { r.needs_fallback = 0; r.fallback_reason = 2; }
+        else if (o->has_compression_ratio_threshold && r.compression_ratio > o->compression_ratio_threshold) { r.needs_fallback = 1; r.fallback_reason = 3; }
+        else if (o->has_logprob_threshold && r.avg_logprob < o->logprob_threshold) { r.needs_fallback = 1; r.fallback_reason = 4; }
+    }
+    return WK_OK;
+}
+
+wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_host, int64_t n_windows, int64_t stride,
+                                const int32_t* samples_per_window, const wk_special_tokens* st, const wk_decode_opts* opts,
+                                const int32_t* prompt, int32_t n_prompt, wk_decode_result* results) {
+    if (!m || !s || !pcm_host || !st || !opts || !prompt || !results) { set_error("wk_transcribe_windows: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    if (s->m != m) { set_error("wk_transcribe_windows: session belongs to another model"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const int chunk = std::min(m->cfg.max_batch, s->max_batch);
+    float acc[6] = {0, 0, 0, 0, 0, 0};
+    cudaPointerAttributes pat;
+    const bool pcm_on_device = cudaPointerGetAttributes(&pat, pcm_host) == cudaSuccess && pat.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    for (int64_t w0 = 0; w0 < n_windows; w0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, n_windows - w0);
+        wk_tensor *mel = nullptr, *enc = nullptr;
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
+        // H2D inside wk_mel (host pointer) ; time it separately by staging first
+        if (stride < kWindowSamples && !samples_per_window) { set_error("wk_transcribe_windows: stride < 480000 requires samples_per_window"); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+        const float* src = pcm_host + w0 * stride;
+        int64_t src_stride = stride;
+        if (!(pcm_on_device && stride >= kWindowSamples)) {   // host PCM (or short rows): stage into the device workspace
+            WK_CUDA_CHECK(cudaMemcpy2DAsync(m->pcm_dev, kWindowSamples * 4, src, stride * 4,
+                                            std::min<int64_t>(stride, kWindowSamples) * 4, nb, cudaMemcpyDefault, m->stream));
+            src = m->pcm_dev;
+            src_stride = kWindowSamples;
+        }
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
+        WK_CHECK(wk_mel(m, src, nb, src_stride, samples_per_window ? samples_per_window + w0 : nullptr, &mel));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[2], m->stream));
+        WK_CHECK(wk_encode(m, mel, &enc));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[3], m->stream));
+        WK_CHECK(wk_session_set_encoder_output(s, enc));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[4], m->stream));
+        WK_CHECK(wk_decode_text(s, st, opts, prompt, n_prompt, results + w0));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[5], m->stream));
+        WK_CUDA_CHECK(cudaEventSynchronize(m->ev[5]));
+        float t;
+        cudaEventElapsedTime(&t, m->ev[0], m->ev[1]); acc[4] += t;
+        cudaEventElapsedTime(&t, m->ev[1], m->ev[2]); acc[0] += t;
+        cudaEventElapsedTime(&t, m->ev[2], m->ev[3]); acc[1] += t;
+        cudaEventElapsedTime(&t, m->ev[3], m->ev[4]); acc[2] += t;
+        cudaEventElapsedTime(&t, m->ev[4], m->ev[5]); acc[3] += t;
+    }
+    memcpy(m->timings, acc, sizeof(acc));
+    return WK_OK;
+}
+
+int64_t wk_kernel_launch_count(int32_t reset) {
+    const long long v = wk::g_launches.load();
+    if (reset) wk::g_launches.store(0);
+    return v;
+}
+
+wk_status wk_last_timings(wk_model* m, float* ms6) {
+    if (!m || !ms6) return WK_ERR_INVALID_ARGUMENT;
+    memcpy(ms6, m->timings, sizeof(m->timings));
+    return WK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- kernel-level hooks
+wk_status wk_test_gemm(wk_model* m, const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
+                       int32_t in_dtype, int32_t out_dtype, int32_t gelu, int32_t simt_reference) {
+    if (!m) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    if (simt_reference) return gemm_simt_reference(a, w, bias, out, M, N, K, in_dtype, out_dtype, gelu, m->stream);
+    const int mode = out_dtype == WK_DTYPE_F32 ? GEMM_OUT_F32 : GEMM_OUT_T16;
+    return gemm_tcgen05(plain_gemm(a, M, K, w, N, in_dtype, mode, out, N, bias, gelu), m->num_sms, m->stream);
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int Bp, int N, int rows, float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * N) return;
+    const int b = (int)(idx / N), i = (int)(idx % N);
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += partial[((long long)s * Bp + b) * N + i];
+    out[idx] = a;
+}
+
+wk_status wk_test_gemm_splitk(wk_model* m, const void* w, const void* x, float* out, int32_t N, int32_t rows_x, int32_t K, int32_t in_dtype, int32_t splits) {
+    if (!m) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    if (rows_x % 16 != 0 || rows_x > 256) { set_error("wk_test_gemm_splitk: rows_x must be a multiple of 16 <= 256"); return WK_ERR_INVALID_ARGUMENT; }
+    const int tiles = (N + 127) / 128;
+    const int sp = splits > 0 ? splits : choose_splits(tiles, K / 64, m->num_sms);
+    float* partial = nullptr;
+    WK_CUDA_CHECK(cudaMalloc(&partial, (size_t)sp * rows_x * N * 4));
+    GemmDesc g;
+    memset(&g, 0, sizeof(g));
+    g.a = w; g.a_rows = N; g.a_cols = K; g.a_ld = K; g.a_batches = 1;
+    g.b = x; g.b_rows = rows_x; g.b_ld = K; g.in_dtype = in_dtype;
+    g.m_rows_per_batch = N; g.n = rows_x; g.k = K; g.taps = 1; g.bn = rows_x; g.splits = sp;
+    g.mode = GEMM_OUT_PARTIAL_T; g.out = partial; g.ld_out = N; g.out_rows_per_batch = N; g.partial_cols = rows_x;
+    wk_status r = gemm_tcgen05(g, m->num_sms, m->stream);
+    if (r == WK_OK) {
+        const long long n = (long long)rows_x * N;
+        reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(partial, sp, rows_x, N, rows_x, out);
+        cudaError_t e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) { set_error("wk_test_gemm_splitk: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
+    }
+    cudaFree(partial);
+    return r;
+}
+
+// Average device time (ms, CUDA events on the library stream) of one launch of a named hot kernel on the session's
+// current buffers: which = 0 decoder cross-attention (one layer, bound batch), 1 encoder FC1 GEMM (M = B*1500),
+// 2 log-mel (pass 1 + pass 2, B windows), 3 encoder attention, 4 decoder QKV swap-AB GEMM, 5 encoder QKV GEMM,
+// 6 sampler.  Also returns the algorithmic bytes (HBM-bound kernels) or FLOPs (tensor-bound) of one launch.
+wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t batch, int32_t iters, float* ms_out, double* work_out) {
+    if (!m || !ms_out || !work_out || iters < 1) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, T = c.n_audio_ctx, H = c.n_heads, dt = c.dtype;
+    const int B = batch;
+    if (B < 1 || B > c.max_batch || (s && B > s->max_batch)) { set_error("wk_bench_kernel: bad batch"); return WK_ERR_INVALID_ARGUMENT; }
+    const int64_t M = (int64_t)B * T;
+    cudaStream_t st = m->stream;
+    auto run = [&]() -> wk_status {
+        switch (which) {
+            case 0: {
+                if (!s) return WK_ERR_INVALID_ARGUMENT;
+                const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;
+                return decoder_cross_attention(s->partial, 1, round_up(B, 16), m->dec[0].bcq, s->cross_kv, (char*)s->cross_kv + cross_block, s->attn, B, H, T, dt, st);
+            }
+            case 1: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].w1, 4 * d, dt, GEMM_OUT_T16, m->ffn, 4 * d, m->enc[0].b1, 1), m->num_sms, st);
+            case 2: return mel_forward(m->mel_tables, m->pcm_dev, B, kWindowSamples, nullptr, m->mel, m->gmax, st);
+            case 3: return encoder_attention(m->qkv, m->attn, B, T, H, dt, st);
+            case 4: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].wqkv, 3 * d, d, s->xn, &sp); }
+            case 5: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, m->enc[0].bqkv, 0), m->num_sms, st);
+            default: set_error("wk_bench_kernel: unknown kernel %d", which); return WK_ERR_INVALID_ARGUMENT;
+        }
+    };
+    switch (which) {
+        case 0: *work_out = (double)B * H * T * 64 * 2 * 2; break;                         // K + V bytes
+        case 1: *work_out = 2.0 * (double)M * d * 4 * d; break;                            // FLOPs
+        case 2: *work_out = (double)B * (kWindowSamples * 4.0 + c.n_mels * 3000 * 2.0); break;  // bytes
+        case 3: *work_out = 4.0 * (double)B * H * T * T * 64; break;                       // FLOPs
+        case 4: *work_out = 3.0 * d * d * 2; break;                                        // weight bytes
+        case 5: *work_out = 2.0 * (double)M * d * 3 * d; break;
+        default: *work_out = 0; break;
+    }
+    for (int i = 0; i < 2; ++i) WK_CHECK(run());
+    WK_CUDA_CHECK(cudaEventRecord(m->ev[6], st));
+    for (int i = 0; i < iters; ++i) WK_CHECK(run());
+    WK_CUDA_CHECK(cudaEventRecord(m->ev[7], st));
+    WK_CUDA_CHECK(cudaEventSynchronize(m->ev[7]));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
+    *ms_out = t / iters;
+    return WK_OK;
+}
+
+wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, int32_t T, int32_t n_heads, int32_t dtype) {
+    if (!m) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    return encoder_attention(qkv, out, B, T, n_heads, dtype, m->stream);
+}
+
+}  // extern "C"

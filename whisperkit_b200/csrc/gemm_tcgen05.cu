@@ -1,0 +1,470 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[rows, cols] = A[rows, K] * B[cols, K]^T      (both operands K-major, 16-bit, f32 accumulate in TMEM)
+//
+// One kernel serves every dense contraction of the Whisper hot path:
+//   * encoder / cross-KV projections: A = activations (M = B*1500 rows), B = weights [N, K]
+//   * conv stem as implicit GEMM: A is a 3-D tensor map, the 3 taps are extra K-blocks with a row shift
+//   * decoder (M = batch <= 256): swap-AB, A = weights (128 output features per tile), B = activations,
+//     split-K partials written transposed so the next fused reduce(+LN) kernel reads them coalesced.
+//
+// Structure (192 threads, 1 CTA / SM, persistent over work items):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) into a ring of smem stages, mbarrier tx
+//   warp 1      MMA issuer: one lane issues tcgen05.mma kind::f16 128xBNx16, tcgen05.commit frees stages
+//   warps 2..5  epilogue: tcgen05.ld 32x32b from a double-buffered TMEM accumulator -> fused epilogue -> HBM
+// The WhisperKit reference has no counterpart source for this file: the contraction lives inside
+// AudioEncoder.mlmodelc / TextDecoder.mlmodelc (Sources/WhisperKit/Core/AudioEncoder.swift:59-62,
+// Sources/WhisperKit/Core/TextDecoder.swift:394-417).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wk {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;   // 64 x 2 B = one 128-byte swizzle row
+static constexpr int kUmmaK = 16;
+static constexpr int kStageA = kBlockM * kBlockK * 2;  // 16 KiB
+static constexpr int kGemmThreads = 192;
+static constexpr int kTmemCols = 512;
+static constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
+static constexpr int kMaxStages = 10;
+
+struct GemmKParams {
+    int tiles_per_batch, n_batches, tiles_n, splits, work;
+    int kb_per_tap, kb_per_split, taps;
+    int tap_row_shift[3];
+    int tap_col_off[3];
+    int a_is_3d;
+    int m_rows_per_batch, n, bn;
+    uint32_t idesc;
+    int stage_b_bytes, stages;
+    int mode, gelu;
+    void* out;
+    long long ld_out, out_rows_per_batch, partial_cols;
+    const float* bias;
+    const float* pos;
+    long long ld_pos;
+    int heads_T, heads_B, heads_H, heads_dmodel;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // manual 1024-byte alignment (SWIZZLE_128B atoms are 1024 B)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = kStageA + p.stage_b_bytes;
+    uint8_t* smem_tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_tail);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int t = w / p.splits;
+                const int n_tile = t % p.tiles_n;
+                const int m_tile = t / p.tiles_n;
+                const int batch = m_tile / p.tiles_per_batch;
+                const int row0 = (m_tile % p.tiles_per_batch) * kBlockM;
+                const int kb0 = split * p.kb_per_split;
+                for (int kb = kb0; kb < kb0 + p.kb_per_split; ++kb) {
+                    const int tap = kb / p.kb_per_tap;
+                    const int kk = kb - tap * p.kb_per_tap;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + kStageA;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                    const int ac0 = p.tap_col_off[tap] + kk * kBlockK;
+                    const int ar = row0 + p.tap_row_shift[tap];
+                    if (p.a_is_3d) tma_load_3d(sa, &tmA, &full_bar[stage], ac0, ar, batch);
+                    else tma_load_2d(sa, &tmA, &full_bar[stage], ac0, ar);
+                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_tile * p.bn);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccStride;
+            for (int kb = 0; kb < p.kb_per_split; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageA);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance the start address by k*32 bytes inside the swizzle atom (>>4 -> +2k)
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                   (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (kb == p.kb_per_split - 1) tc_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int split = w % p.splits;
+            const int t = w / p.splits;
+            const int n_tile = t % p.tiles_n;
+            const int m_tile = t / p.tiles_n;
+            const int batch = m_tile / p.tiles_per_batch;
+            const int row_in_batch = (m_tile % p.tiles_per_batch) * kBlockM + quarter * 32 + lane;
+            const bool row_ok = row_in_batch < p.m_rows_per_batch;
+            const long long grow = (long long)batch * p.out_rows_per_batch + row_in_batch;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
+            const int col_base = n_tile * p.bn;
+
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t r[32];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent tails below
+                tmem_ld_32x32(taddr + c, r);
+                tmem_ld_wait();
+                const int col0 = col_base + c;
+                if (p.mode == GEMM_OUT_PARTIAL_T) {
+                    if (row_ok) {
+                        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = col0 + j;
+                            if (c + j < p.bn && col < p.partial_cols)
+                                o[((long long)split * p.partial_cols + col) * p.ld_out + grow] = __uint_as_float(r[j]);
+                        }
+                    }
+                    continue;
+                }
+                if (!row_ok || col0 >= p.n) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = __ldg(b4 + j);
+                        v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                    }
+                }
+                if (p.gelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if (p.mode == GEMM_OUT_T16 || p.mode == GEMM_OUT_T16_HEADS) {
+                    T* o;
+                    if (p.mode == GEMM_OUT_T16) {
+                        o = reinterpret_cast<T*>(p.out) + grow * p.ld_out + col0;
+                    } else {
+                        const int b = (int)(grow / p.heads_T);
+                        const int tt = (int)(grow - (long long)b * p.heads_T);
+                        const int which = col0 / p.heads_dmodel;
+                        const int rem = col0 - which * p.heads_dmodel;
+                        const int h = rem >> 6;
+                        const int dd = rem & 63;
+                        o = reinterpret_cast<T*>(p.out) +
+                            ((((long long)which * p.heads_B + b) * p.heads_H + h) * p.heads_T + tt) * 64 + dd;
+                    }
+                    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        pk.x = T16<T>::pack2(v[8 * j], v[8 * j + 1]);
+                        pk.y = T16<T>::pack2(v[8 * j + 2], v[8 * j + 3]);
+                        pk.z = T16<T>::pack2(v[8 * j + 4], v[8 * j + 5]);
+                        pk.w = T16<T>::pack2(v[8 * j + 6], v[8 * j + 7]);
+                        o4[j] = pk;
+                    }
+                } else {
+                    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ld_out + col0);
+                    if (p.mode == GEMM_OUT_F32_ADD) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 x = o4[j];
+                            x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
+                            o4[j] = x;
+                        }
+                    } else if (p.mode == GEMM_OUT_F32_GELU_POS) {
+                        const float4* p4 = reinterpret_cast<const float4*>(p.pos + (long long)row_in_batch * p.ld_pos + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 pp = __ldg(p4 + j);
+                            o4[j] = make_float4(v[4 * j] + pp.x, v[4 * j + 1] + pp.y, v[4 * j + 2] + pp.z, v[4 * j + 3] + pp.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+            // release the accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static wk_status make_tmap(CUtensorMap* tm, const void* base, int dtype, int ndim, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return WK_ERR_CUDA;
+    }
+    cuuint64_t gdim[3];
+    cuuint64_t gstr[2];
+    cuuint32_t bx[3];
+    cuuint32_t es[3] = {1, 1, 1};
+    for (int i = 0; i < ndim; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < ndim - 1; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(tm, dtype == WK_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     (cuuint32_t)ndim, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: %d (ndim %d dims %llu %llu stride %llu box %u %u)", (int)r, ndim,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0], box[0],
+                  box[1]);
+        return WK_ERR_CUDA;
+    }
+    return WK_OK;
+}
+
+wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
+    if (d.k % kBlockK != 0 || d.bn % 16 != 0 || d.bn < 16 || d.bn > 256 || d.taps < 1 || d.taps > 3) {
+        set_error("gemm_tcgen05: unsupported shape k=%d bn=%d taps=%d", d.k, d.bn, d.taps);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    if (d.mode != GEMM_OUT_PARTIAL_T && (d.n % 32 != 0 || d.splits != 1)) {
+        set_error("gemm_tcgen05: n=%d must be a multiple of 32 and splits 1 for mode %d", d.n, d.mode);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    GemmKParams p;
+    memset(&p, 0, sizeof(p));
+    p.kb_per_tap = d.k / kBlockK;
+    const int total_kb = p.kb_per_tap * d.taps;
+    p.splits = d.splits < 1 ? 1 : d.splits;
+    if (total_kb % p.splits != 0) {
+        set_error("gemm_tcgen05: splits %d does not divide %d k-blocks", p.splits, total_kb);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    p.kb_per_split = total_kb / p.splits;
+    p.taps = d.taps;
+    for (int i = 0; i < 3; ++i) { p.tap_row_shift[i] = d.tap_row_shift[i]; p.tap_col_off[i] = d.tap_col_off[i]; }
+    p.a_is_3d = d.a_3d ? 1 : 0;
+    p.n_batches = d.a_3d ? d.a_batches : 1;
+    p.m_rows_per_batch = d.m_rows_per_batch;
+    p.tiles_per_batch = (d.m_rows_per_batch + kBlockM - 1) / kBlockM;
+    p.n = d.n;
+    p.bn = d.bn;
+    p.tiles_n = (d.n + d.bn - 1) / d.bn;
+    p.work = p.tiles_per_batch * p.n_batches * p.tiles_n * p.splits;
+    p.idesc = 0;
+    {
+        const int fmt = d.in_dtype == WK_DTYPE_F16 ? 0 : 1;
+        uint32_t id = 0;
+        id |= 1u << 4;
+        id |= (uint32_t)fmt << 7;
+        id |= (uint32_t)fmt << 10;
+        id |= (uint32_t)(d.bn >> 3) << 17;
+        id |= (uint32_t)(kBlockM >> 4) << 24;
+        p.idesc = id;
+    }
+    p.stage_b_bytes = d.bn * kBlockK * 2;
+    // B stage must keep 1024-byte alignment of the following A stage
+    if (p.stage_b_bytes % 1024 != 0) p.stage_b_bytes = (p.stage_b_bytes + 1023) / 1024 * 1024;
+    const int stage_bytes = kStageA + p.stage_b_bytes;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
+    int stages = smem_budget / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > total_kb / p.splits + 2) stages = total_kb / p.splits + 2;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    p.mode = d.mode;
+    p.gelu = d.gelu;
+    p.out = d.out;
+    p.ld_out = d.ld_out;
+    p.out_rows_per_batch = d.out_rows_per_batch;
+    p.partial_cols = d.partial_cols;
+    p.bias = d.bias;
+    p.pos = d.pos;
+    p.ld_pos = d.ld_pos;
+    p.heads_T = d.heads_T; p.heads_B = d.heads_B; p.heads_H = d.heads_H; p.heads_dmodel = d.heads_dmodel;
+
+    CUtensorMap tmA, tmB;
+    wk_status st;
+    if (p.a_is_3d) {
+        uint64_t dims[3] = {(uint64_t)d.a_cols, (uint64_t)d.a_rows, (uint64_t)d.a_batches};
+        uint64_t str[2] = {(uint64_t)d.a_ld * 2, (uint64_t)d.a_batch_stride * 2};
+        uint32_t box[3] = {kBlockK, kBlockM, 1};
+        st = make_tmap(&tmA, d.a, d.in_dtype, 3, dims, str, box);
+    } else {
+        uint64_t dims[2] = {(uint64_t)d.a_cols, (uint64_t)d.a_rows};
+        uint64_t str[1] = {(uint64_t)d.a_ld * 2};
+        uint32_t box[2] = {kBlockK, kBlockM};
+        st = make_tmap(&tmA, d.a, d.in_dtype, 2, dims, str, box);
+    }
+    if (st != WK_OK) return st;
+    {
+        uint64_t dims[2] = {(uint64_t)d.k * d.taps, (uint64_t)d.b_rows};
+        uint64_t str[1] = {(uint64_t)d.b_ld * 2};
+        uint32_t box[2] = {kBlockK, (uint32_t)d.bn};
+        st = make_tmap(&tmB, d.b, d.in_dtype, 2, dims, str, box);
+        if (st != WK_OK) return st;
+    }
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+    int grid = p.work < num_sms ? p.work : num_sms;
+    if (grid < 1) return WK_OK;
+    cudaError_t e;
+    if (d.in_dtype == WK_DTYPE_F16) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(gemm_tcgen05_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+            attr_set = true;
+        }
+        gemm_tcgen05_kernel<__half><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(gemm_tcgen05_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+            attr_set = true;
+        }
+        gemm_tcgen05_kernel<__nv_bfloat16><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+    }
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("gemm_tcgen05 launch: %s", cudaGetErrorString(e));
+        return WK_ERR_CUDA;
+    }
+    return WK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core reference used only by tests to validate the tcgen05 path on the device.
+template <typename T, typename O>
+__global__ void gemm_simt_kernel(const T* __restrict__ a, const T* __restrict__ w, const float* __restrict__ bias,
+                                 O* __restrict__ out, int M, int N, int K, int gelu) {
+    __shared__ float sa[16][17];
+    __shared__ float sw[16][17];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        const int ar = blockIdx.y * 16 + ty, wr = blockIdx.x * 16 + ty;
+        sa[ty][tx] = (ar < M && k0 + tx < K) ? T16<T>::to_f(a[(long long)ar * K + k0 + tx]) : 0.f;
+        sw[ty][tx] = (wr < N && k0 + tx < K) ? T16<T>::to_f(w[(long long)wr * K + k0 + tx]) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sw[tx][k];
+        __syncthreads();
+    }
+    if (row < M && col < N) {
+        if (bias) acc += bias[col];
+        if (gelu) acc = gelu_erf(acc);
+        if constexpr (sizeof(O) == 4) out[(long long)row * N + col] = acc;
+        else out[(long long)row * N + col] = T16<O>::from_f(acc);
+    }
+}
+
+wk_status gemm_simt_reference(const void* a, const void* w, const float* bias, void* out, int M, int N, int K, int in_dtype,
+                              int out_dtype, int gelu, cudaStream_t stream) {
+    dim3 block(16, 16), grid((N + 15) / 16, (M + 15) / 16);
+    if (in_dtype == WK_DTYPE_BF16) {
+        if (out_dtype == WK_DTYPE_F32)
+            gemm_simt_kernel<__nv_bfloat16, float><<<grid, block, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias, (float*)out, M, N, K, gelu);
+        else
+            gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, M, N, K, gelu);
+    } else {
+        if (out_dtype == WK_DTYPE_F32)
+            gemm_simt_kernel<__half, float><<<grid, block, 0, stream>>>((const __half*)a, (const __half*)w, bias, (float*)out, M, N, K, gelu);
+        else
+            gemm_simt_kernel<__half, __half><<<grid, block, 0, stream>>>((const __half*)a, (const __half*)w, bias, (__half*)out, M, N, K, gelu);
+    }
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("gemm_simt launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
+}  // namespace wk

@@ -1,0 +1,140 @@
+// Internal launcher declarations shared by the .cu files of libwkb200.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/wkb200.h"
+
+namespace wk {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+// ---------------------------------------------------------------- GEMM (gemm_tcgen05.cu)
+enum GemmMode {
+    GEMM_OUT_T16 = 0,        // out16[row, col] = act(acc + bias[col])
+    GEMM_OUT_F32_ADD = 1,    // out32[row, col] += acc + bias[col]           (residual update in place)
+    GEMM_OUT_F32_GELU_POS = 2,  // out32[row, col] = gelu(acc + bias[col]) + pos[row_in_batch, col]
+    GEMM_OUT_PARTIAL_T = 3,  // out32[split][col][row] = acc                  (swap-AB split-K partials)
+    GEMM_OUT_T16_HEADS = 4,  // out16[which][b][h][t][64] head-major scatter  (cross-attention K/V cache)
+    GEMM_OUT_F32 = 5,        // out32[row, col] = acc + bias[col]
+};
+
+struct GemmDesc {
+    // A operand: [a_rows, K] 16-bit, K contiguous.  If a_batches > 1 it is a 3-D tensor
+    // [a_batches][a_rows_per_batch][a_cols] addressed per batch (conv-as-GEMM with taps).
+    const void* a;
+    int64_t a_rows;          // rows (per batch if a_batches > 1)
+    int64_t a_cols;          // row length in elements (>= K for tap addressing)
+    int64_t a_ld;            // row stride in elements
+    int64_t a_batch_stride;  // elements between batches (3-D only)
+    int a_batches;           // 1 = plain 2-D
+    int a_3d;                // address A through a 3-D tensor map [a_batches][a_rows][a_cols]
+    // B operand: [b_rows, K_total] 16-bit, K contiguous (weights [N,K] or, swap-AB, activations)
+    const void* b;
+    int64_t b_rows;
+    int64_t b_ld;
+    int in_dtype;            // WK_DTYPE_BF16 / WK_DTYPE_F16
+    // problem
+    int m_rows_per_batch;    // output rows per batch (== valid A rows per batch for this op)
+    int n;                   // valid output columns (<= b_rows)
+    int k;                   // K per tap (multiple of 64)
+    int taps;                // 1, or 3 for the conv stem
+    int tap_row_shift[3];    // A row offset per tap
+    int tap_col_off[3];      // A column offset per tap (elements)
+    int bn;                  // tile N (multiple of 16, <= 256)
+    int splits;              // split-K (GEMM_OUT_PARTIAL_T only), divides taps*k/64
+    // epilogue
+    int mode;
+    int gelu;
+    void* out;
+    int64_t ld_out;          // row stride of out (elements); PARTIAL_T: elements per [col] row = total M
+    int64_t out_rows_per_batch;  // global out row = batch*out_rows_per_batch + row_in_batch
+    int64_t partial_cols;    // PARTIAL_T: number of col rows per split (padded batch)
+    const float* bias;       // indexed by col (row for PARTIAL_T is not biased)
+    const float* pos;        // GELU_POS: [m_rows_per_batch, ld_pos]
+    int64_t ld_pos;
+    // HEADS scatter
+    int heads_T, heads_B, heads_H, heads_dmodel;
+};
+
+wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream);
+// plain CUDA-core reference for tests (same semantics, mode OUT_T16/OUT_F32 only)
+wk_status gemm_simt_reference(const void* a, const void* w, const float* bias, void* out, int M, int N, int K, int in_dtype,
+                              int out_dtype, int gelu, cudaStream_t stream);
+
+// ---------------------------------------------------------------- mel (mel.cu)
+struct MelTables;  // device tables (window, twiddles, sparse filterbank)
+wk_status mel_tables_create(int n_mels, MelTables** out);
+void mel_tables_free(MelTables* t);
+// pcm [n_windows, stride] f32 device; out [n_windows, 3002, 128] f16 (rows 0 and 3001 are the conv zero pad, mel
+// channels >= n_mels zero); gmax scratch [n_windows] int32
+wk_status mel_forward(const MelTables* t, const float* pcm, int64_t n_windows, int64_t stride, const int32_t* n_valid,
+                      void* out_f16, int32_t* gmax_scratch, cudaStream_t stream);
+constexpr int kMelRows = 3002;
+constexpr int kMelCols = 128;
+
+// ---------------------------------------------------------------- encoder ops (encoder_ops.cu)
+wk_status layernorm_f32_to_16(const float* x, const float* gamma, const float* beta, void* out, int64_t rows, int d, int dtype,
+                              cudaStream_t stream);
+wk_status layernorm_f32_to_f32(const float* x, const float* gamma, const float* beta, float* out, int64_t rows, int d,
+                               cudaStream_t stream);
+wk_status encoder_attention(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream);
+wk_status transpose_to_host_layout(const void* src, float* dst, int64_t B, int64_t rows, int64_t cols, int64_t src_rows_alloc,
+                                   int64_t src_row_off, int64_t src_ld, int dtype, cudaStream_t stream);
+wk_status fill_random_16(void* dst, int64_t n, uint64_t seed, float std, float mean, int dtype, cudaStream_t stream);
+wk_status fill_random_f32(float* dst, int64_t n, uint64_t seed, float std, float mean, cudaStream_t stream);
+wk_status convert_to_16(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, cudaStream_t stream);
+
+// ---------------------------------------------------------------- decoder ops (decoder_ops.cu)
+struct DecodeState {
+    // all device pointers; B = bound batch, Bp = padded batch (multiple of 16)
+    int32_t* tokens;      // [Bmax, 224] currentTokens
+    int32_t* n_tokens;    // [Bmax]
+    float* logprobs;      // [Bmax, 224]
+    int32_t* next_token;  // [Bmax]
+    int32_t* done;        // [Bmax]
+    int32_t* first_low;   // [Bmax]
+    int32_t* steps;       // [Bmax] forward passes consumed
+    int32_t* step;        // [1] tokenIndex of the step about to run
+    int32_t* n_done;      // [1]
+    int32_t* input_ids;   // [Bmax] token fed at this step (written by embed)
+};
+
+struct SamplerParams {
+    wk_special_tokens st;
+    int vocab;
+    int is_multilingual;
+    int sample_begin_ts;     // TimestampRulesFilter.sampleBegin, <0 = filter absent
+    int sample_begin_blank;  // SuppressBlankFilter.sampleBegin, <0 = absent
+    const int32_t* suppress; int n_suppress;
+    const int32_t* language_tokens; int n_language_tokens; int language_sample_begin;
+    float temperature; int top_k; uint64_t seed;
+    int has_first_thr; float first_thr;
+    int prompt_len;          // initialPrompt.count (decode loop) ; <0 = stateless (wk_filter_sample)
+    int max_ctx;             // 224
+};
+
+wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gamma, const float* beta, DecodeState st,
+                           int prompt_len, int ts_begin, float* x, void* xn, int B, int d, int dtype, int explicit_inputs,
+                           const int32_t* explicit_pos, cudaStream_t stream);
+// x[b,:] += bias + sum_s partial[s][b][:]; xn = LN(x) (16-bit).  partial layout [S][Bp][d]
+wk_status decoder_reduce_resid_ln(const float* partial, int splits, int Bp, const float* bias, const float* gamma,
+                                  const float* beta, float* x, void* xn, int B, int d, int dtype, cudaStream_t stream);
+// h = gelu(bias + sum partial) 16-bit [B, n]
+wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, const float* bias, void* out, int B, int n,
+                                   int dtype, cudaStream_t stream);
+// self attention for one new token per sequence; reduces qkv partials [S][Bp][3d], appends K/V at pos
+wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
+                                 void* vcache, const int32_t* step, const int32_t* explicit_pos, void* out, int B, int H,
+                                 int max_len, int dtype, cudaStream_t stream);
+// cross attention over T encoder positions; reduces q partials [S][Bp][d]; K/V [B][H][T][64]
+wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
+                                  const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream);
+wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
+                                int ld_tokens, const int32_t* n_tokens, int32_t* token_out, float* logprob_out,
+                                float* filtered_out, int B, cudaStream_t stream);
+wk_status decode_state_init(DecodeState st, const int32_t* prompt_dev, int n_prompt, int B, cudaStream_t stream);
+
+}  // namespace wk
