@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py - RTFx (audio-seconds per second) of the WhisperKit hot path on B200.
+
+One "step" = one pass of the whole hot path (PCM -> log-mel -> encoder -> cross-KV -> KV-cached greedy decode with
+TimestampRules filter + sampler -> token IDs) over one batch of synthetic 30 s windows, whisper-large-v3 shapes,
+seeded random weights (no checkpoints offline), bf16 storage / f32 accumulate.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # own arm (CUDA engine, libwkb200.so)
+  python bench.py --impl reference [--steps K] [--warmup W]      # CPU restatement of the reference pipeline
+  torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU (weak scaling: B windows per GPU)
+
+`value`  : device-timed RTFx with the PCM already resident in HBM.
+`e2e`    : the same metric through the public API with HOST buffers: pinned PCM -> (N>1: NCCL scatter) -> GPU ->
+           token IDs -> (N>1: NCCL gather) -> host, copies inside the timed region.
+`roofline`: the dominant kernel (chosen by measured share of the step), timed live with CUDA events on the
+           library stream, against MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle (a restatement of the reference's scheduling: one decoder call per token, batch 1)
+           on the host cores, on one 30 s window of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+AUDIO_SECONDS_PER_WINDOW = 30.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--variant", default="large-v3")
+    ap.add_argument("--batch", type=int, default=64, help="30 s windows per GPU per step")
+    ap.add_argument("--sample-length", type=int, default=224, help="DecodingOptions.sampleLength (reference default 224)")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-windows", type=int, default=1)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=5)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_windows(first_idx: int, n: int) -> np.ndarray:
+    from whisperkit_b200.synthetic import synthetic_pcm
+    return np.stack([synthetic_pcm(first_idx + i) for i in range(n)])
+
+
+def special_tokens_for(vocab: int):
+    import whisperkit_b200 as wk
+    if vocab == 51866:
+        return wk.SpecialTokens(endToken=50257, englishToken=50259, noSpeechToken=50363, noTimestampsToken=50364,
+                                specialTokenBegin=50257, startOfPreviousToken=50362, startOfTranscriptToken=50258,
+                                timeTokenBegin=50365, transcribeToken=50360, translateToken=50359)
+    if vocab == 51864:
+        return wk.SpecialTokens(endToken=50256, englishToken=50258, noSpeechToken=50361, noTimestampsToken=50362,
+                                specialTokenBegin=50256, startOfPreviousToken=50360, startOfTranscriptToken=50257,
+                                timeTokenBegin=50363, transcribeToken=50358, translateToken=50357)
+    return wk.SpecialTokens()
+
+
+# ------------------------------------------------------------------------------------------------ CPU restatement
+_ORACLE_CACHE = {}
+
+
+def cpu_restatement(variant: str, sample_length: int, n_windows: int, threads: int, first_idx: int = 0):
+    """Times the CPU oracle: log-mel + fp32 Whisper + the reference's decode loop (one decoder call per token,
+    batch 1 per stream - exactly how the reference schedules CoreML).  Returns (rtfx, seconds, steps)."""
+    import torch
+    from oracle import decode_ref as D, mel_ref, model_ref as M
+    torch.set_num_threads(threads)
+    dims = M.VARIANTS[variant]
+    if variant not in _ORACLE_CACHE:  # weight generation (1.5 G parameters for large-v3) is setup, not timed work
+        _ORACLE_CACHE[variant] = M.WhisperOracle(dims, M.random_weights(dims, seed=1234, policy="fp32"), "fp32")
+    orc = _ORACLE_CACHE[variant]
+    st = D.SpecialTokens.large_v3() if dims.vocab == 51866 else (D.SpecialTokens.english_only() if dims.vocab == 51864 else D.SpecialTokens())
+    opts = D.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=sample_length)
+    multilingual = dims.vocab != 51864
+    prompt = D.prefill_prompt(opts, st, multilingual)
+    pcm = synthetic_windows(first_idx, n_windows)
+    steps = 0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(n_windows):
+            mel = mel_ref.log_mel(pcm[i], dims.n_mels, dtype=np.float32).astype(np.float16).astype(np.float32)
+            enc = orc.encode(torch.from_numpy(mel)[None])
+            cross = orc.cross_kv(enc)
+            cache = orc.new_cache(1)
+
+            def predict(tok, idx):
+                return orc.decode_step(torch.tensor([tok]), idx, cache, cross)[0].numpy()
+
+            r = D.decode_text(predict, prompt, opts, st, multilingual)
+            steps += r.steps
+    dt = time.perf_counter() - t0
+    return n_windows * AUDIO_SECONDS_PER_WINDOW / dt, dt, steps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    metric = "RTFx (audio-sec/s) whisper-large-v3 greedy" if args.variant == "large-v3" else f"RTFx (audio-sec/s) whisper-{args.variant} greedy"
+    times = []
+    budget_t0 = time.perf_counter()
+    warm = min(args.warmup, 1)  # CPU warm-up = first-touch of the weights; one pass is enough
+    for i in range(warm):
+        cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
+    done = 0
+    for i in range(args.steps):
+        rtfx, dt, _ = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads, first_idx=i)
+        times.append(dt)
+        done += 1
+        if time.perf_counter() - budget_t0 > 360 and done >= 1:
+            break
+    total = sum(times)
+    value = done * args.cpu_windows * AUDIO_SECONDS_PER_WINDOW / total
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": "audio-sec/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": warm, "ms_per_step": 1000.0 * total / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic 16 kHz PCM, seeded random weights",
+        "config": {"workload": f"whisper-{args.variant} greedy, {args.cpu_windows} x 30 s window per step (bounded CPU sample of the "
+                               f"batch={args.batch} x 30 s GPU workload), sampleLength={args.sample_length}, timestamps on",
+                   "sample_length": args.sample_length},
+        "cpu_baseline": {"value": value, "unit": "audio-sec/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.cpu_windows} window(s) x 30 s per step, full pipeline, fp32 PyTorch CPU restatement of the "
+                                   "WhisperKit pipeline (the Swift/CoreML reference cannot run on Linux)"},
+        "e2e": {"value": value, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def run_own_arm(args):
+    import torch
+    import whisperkit_b200 as wk
+    from whisperkit_b200._lib import check, wk_decode_result
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    B = args.batch
+    model = wk.Model(args.variant, device=local_rank, max_batch=B, dtype=args.dtype)
+    model.init_random(seed=1234)
+    dec = wk.TextDecoder(model, B)
+    lib = model.lib
+    info = model.info
+    st = special_tokens_for(info.vocab)
+    opts = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=args.sample_length)
+    prompt = dec.prefillDecoderInputs(opts, st)
+    st_c = st.to_c()
+    o_c, keep = opts.to_c()
+    p_c = (C.c_int32 * len(prompt))(*prompt)
+    res = (wk_decode_result * B)()
+    ext = torch.cuda.ExternalStream(model.stream, device=torch.device("cuda", local_rank))
+
+    pcm_np = synthetic_windows(rank * B, B)
+    pcm_host = torch.from_numpy(pcm_np).pin_memory()
+    pcm_dev = pcm_host.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(pcm_dev.data_ptr()), B, 480000, None, C.byref(st_c),
+                                        C.byref(o_c), p_c, len(prompt), res))
+
+    # e2e: host PCM in, token IDs on the host out.  N > 1: rank 0 owns all N*B windows in pinned memory, copies them
+    # to its GPU, NCCL scatters shards over NVLink, every rank transcribes, NCCL gathers token IDs back to rank 0.
+    if world > 1:
+        all_host = torch.from_numpy(synthetic_windows(0, world * B)).pin_memory() if rank == 0 else None
+        shard = torch.empty(B, 480000, device="cuda", dtype=torch.float32)
+        tok_dev = torch.empty(B, 228, device="cuda", dtype=torch.int32)
+        gather_list = [torch.empty_like(tok_dev) for _ in range(world)] if rank == 0 else None
+    d2h_bytes = B * (224 * 8 + 16)
+
+    def step_e2e():
+        if world == 1:
+            check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(pcm_host.data_ptr()), B, 480000, None,
+                                            C.byref(st_c), C.byref(o_c), p_c, len(prompt), res))
+            return
+        if rank == 0:
+            staged = all_host.cuda(non_blocking=True)
+            chunks = list(staged.chunk(world, dim=0))
+        else:
+            chunks = None
+        dist.scatter(shard, chunks, src=0)
+        torch.cuda.synchronize()
+        check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(shard.data_ptr()), B, 480000, None, C.byref(st_c),
+                                        C.byref(o_c), p_c, len(prompt), res))
+        host_tok = np.zeros((B, 228), dtype=np.int32)
+        for b in range(B):
+            host_tok[b, 0] = res[b].n_tokens
+            host_tok[b, 1:1 + res[b].n_tokens] = res[b].tokens[:res[b].n_tokens]
+        tok_dev.copy_(torch.from_numpy(host_tok), non_blocking=False)
+        dist.gather(tok_dev, gather_list, dst=0)
+        if rank == 0:
+            _ = torch.stack(gather_list).cpu()
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        lib.wk_kernel_launch_count(1)
+        if sampler:
+            sampler.__enter__()
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        barrier()
+        if sampler:
+            sampler.__exit__()
+        ms = e0.elapsed_time(e1)
+        launches = int(lib.wk_kernel_launch_count(0))
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            launches = int(lt.item())
+        return ms, launches, (sampler.summary() if sampler else None)
+
+    ms, launches, clocks = timed(step_device, args.steps, max(args.warmup, 3), True)
+    steps_run = [r.steps for r in res]
+    timings = model.last_timings()
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1, False)
+    audio = world * B * AUDIO_SECONDS_PER_WINDOW * args.steps
+    value = audio / (ms / 1000.0)
+    e2e_value = audio / (ms_e2e / 1000.0)
+    ms_per_step = ms / args.steps
+
+    line = {
+        "metric": "RTFx (audio-sec/s) whisper-large-v3 greedy" if args.variant == "large-v3" else f"RTFx (audio-sec/s) whisper-{args.variant} greedy",
+        "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic 16 kHz PCM (seeded noise + gated tones), seeded random weights of the large-v3 architecture",
+        "config": {"workload": f"whisper-{args.variant} greedy {args.dtype}, batch={B} x 30 s windows per GPU (BASELINE configs[1]), "
+                               f"DecodingOptions defaults except firstTokenLogProbThreshold=nil; sampleLength={args.sample_length} "
+                               f"(decode steps per window: {min(steps_run)}..{max(steps_run)}), timestamps on (TimestampRulesFilter active)",
+                   "windows_per_gpu": B, "sample_length": args.sample_length, "decode_steps": max(steps_run),
+                   "parallelism": f"dp{world} (windows sharded, weights replicated)",
+                   "l2": "inputs_larger_than_L2 (3.1 GB weights + 15.7 GB cross-KV streamed every step; no flush needed)",
+                   "stage_ms": timings},
+        "e2e": {"value": e2e_value, "unit": "audio-sec/s", "h2d_bytes_per_step": world * B * 480000 * 4,
+                "d2h_bytes_per_step": world * d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                "path": "wk_transcribe_windows(host pinned PCM)" + (" + NCCL scatter/gather" if world > 1 else "")},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_roofline:
+        peaks = measured_peaks()
+        f = C.c_float()
+        wk_ = C.c_double()
+        kernels = {}
+        L, Ld = info.enc_layers, info.dec_layers
+        nsteps = max(steps_run)
+        per_step = {0: Ld * nsteps, 1: L, 2: 1, 3: L, 4: Ld * nsteps, 5: L}
+        names = {0: "decoder_cross_attention_kernel", 1: "gemm_tcgen05_kernel[enc FC1 M=B*1500,N=5120,K=1280]", 2: "mel_pass1+pass2",
+                 3: "encoder_attention_kernel", 4: "gemm_tcgen05_kernel[dec QKV swap-AB N=3840,K=1280,split-K]",
+                 5: "gemm_tcgen05_kernel[enc QKV M=B*1500,N=3840,K=1280]"}
+        bound = {0: "hbm", 1: "tensor", 2: "hbm", 3: "tensor", 4: "hbm", 5: "tensor"}
+        for which in range(6):
+            check(lib.wk_bench_kernel(model.handle, dec.handle, which, B, 20 if which != 2 else 5, C.byref(f), C.byref(wk_)))
+            t_ms, work = float(f.value), float(wk_.value)
+            if bound[which] == "hbm":
+                ach, peak, unit = work / (t_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
+            else:
+                ach, peak, unit = work / (t_ms * 1e-3) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+            kernels[names[which]] = {"bound": bound[which], "ms": t_ms, "achieved": ach, "peak": peak, "unit": unit,
+                                     "frac": ach / peak, "launches_per_step": per_step[which],
+                                     "share_of_step": per_step[which] * t_ms / ms_per_step}
+        dom = max(kernels.items(), key=lambda kv: kv[1]["share_of_step"])
+        line["roofline"] = {"kernel": dom[0], "bound": dom[1]["bound"], "achieved": dom[1]["achieved"], "peak": dom[1]["peak"],
+                            "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": None,
+                            "peak_source": peaks["source"] + " (MEASURED_PEAKS.json burst figures; kernel timed alone)",
+                            "share_of_step": dom[1]["share_of_step"]}
+        line["kernels"] = kernels
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rtfx, dt, nst = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
+        line["cpu_baseline"] = {"value": rtfx, "unit": "audio-sec/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_windows} window(s) x 30 s, full pipeline ({nst} decoder steps), {dt:.1f} s of CPU "
+                                          "work; fp32 PyTorch CPU restatement of the WhisperKit pipeline (one decoder call per token, "
+                                          "batch 1) - the Swift/CoreML reference cannot run on Linux"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -209,6 +209,9 @@ wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, 
  * 2 log-mel, 3 encoder attention, 4 decoder QKV swap-AB GEMM, 5 encoder QKV GEMM.  Used by bench.py's roofline. */
 wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t batch, int32_t iters, float* ms_out, double* work_out);
 
+/* Debug readback of an internal device buffer converted to f32 (stage-by-stage parity debugging; see engine.cu). */
+wk_status wk_debug_read(wk_model* m, wk_session* s, int32_t which, int64_t offset_elems, float* dst, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

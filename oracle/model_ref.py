@@ -100,9 +100,9 @@ def random_weights(dims: WhisperDims, seed: int = 0, policy: str = "bf16", std: 
         w[name + ".bias"] = rnd(d)
 
     d = dims.d_model
-    w["model.encoder.conv1.weight"] = round_to(rnd(d, dims.n_mels, 3, s=0.05), "f16")
+    w["model.encoder.conv1.weight"] = round_to(rnd(d, dims.n_mels, 3, s=0.05), "f16" if policy != "fp32" else "fp32")
     w["model.encoder.conv1.bias"] = rnd(d)
-    w["model.encoder.conv2.weight"] = round_to(rnd(d, d, 3), "f16")  # conv stem runs in f16 end to end
+    w["model.encoder.conv2.weight"] = round_to(rnd(d, d, 3), "f16" if policy != "fp32" else "fp32")  # f16 conv stem
     w["model.encoder.conv2.bias"] = rnd(d)
     w["model.encoder.embed_positions.weight"] = sinusoids(dims.n_audio_ctx, d)
     for i in range(dims.enc_layers):
@@ -167,7 +167,9 @@ class WhisperOracle:
         (final LayerNorm output, unrounded)."""
         w, d = self.w, self.dims
         x = F.conv1d(mel, w["model.encoder.conv1.weight"], w["model.encoder.conv1.bias"], padding=1)
-        x = round_to(gelu(x), "f16")  # the conv stem is f16 (mel is f16): conv1 output is stored as f16
+        x = gelu(x)
+        if self.policy != "fp32":
+            x = round_to(x, "f16")  # the conv stem is f16 (mel is f16): conv1 output is stored as f16
         x = F.conv1d(x, w["model.encoder.conv2.weight"], w["model.encoder.conv2.bias"], stride=2, padding=1)
         x = gelu(x).transpose(1, 2) + w["model.encoder.embed_positions.weight"][None]
         scale = (d.d_model // d.n_heads) ** -0.5

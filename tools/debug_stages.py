@@ -1,0 +1,137 @@
+"""Stage-by-stage comparison of the CUDA engine against the oracle (debug tool, GPU box).
+python tools/debug_stages.py [variant] [policy]"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def child(variant, policy, stage):
+    import torch
+    import torch.nn.functional as F
+    import whisperkit_b200 as wk
+    from whisperkit_b200._lib import check
+    from oracle import mel_ref, model_ref as M
+
+    dims = M.VARIANTS[variant]
+    B = 2
+    w = M.random_weights(dims, seed=5, policy=policy)
+    orc = M.WhisperOracle(dims, w, policy)
+    model = wk.Model(variant, max_batch=B, dtype=policy)
+    model.load_state_dict(w)
+    lib = model.lib
+    d, T = dims.d_model, 1500
+
+    def rd(which, n, sess=None, off=0):
+        out = np.empty(n, np.float32)
+        check(lib.wk_debug_read(model.handle, sess.handle if sess is not None else None, which, off, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    pcm = np.stack([mel_ref.synthetic_pcm(10 + i) for i in range(B)])
+    fe, enc = wk.FeatureExtractor(model), wk.AudioEncoder(model)
+    mel_t = fe.logMelSpectrogram(pcm)
+    mel_gpu = mel_t.numpy()
+    enc_t = enc.encodeFeatures(mel_t)
+    r = orc.r
+    with torch.no_grad():
+        mel = torch.from_numpy(mel_gpu)
+        h1 = M.round_to(F.gelu(F.conv1d(mel, w["model.encoder.conv1.weight"], w["model.encoder.conv1.bias"], padding=1)), "f16")
+        x0 = F.gelu(F.conv1d(h1, w["model.encoder.conv2.weight"], w["model.encoder.conv2.bias"], stride=2, padding=1)).transpose(1, 2) \
+            + w["model.encoder.embed_positions.weight"][None]
+        if stage == "enc0":
+            g_h1 = rd(1, B * 3002 * d).reshape(B, 3002, d)
+            print("  h1 pad rows zero:", float(np.abs(g_h1[:, 0]).max()), float(np.abs(g_h1[:, 3001]).max()))
+            print("  conv1 (h1) rel err:", rel(g_h1[:, 1:3001], h1.transpose(1, 2).numpy()))
+            g_x = rd(2, B * T * d).reshape(B, T, d)
+            print("  conv2+gelu+pos (x) rel err:", rel(g_x, x0.numpy()))
+            g_e = rd(7, B * T * d).reshape(B, T, d)
+            print("  final LN of x rel err:", rel(g_e, r(orc._ln(x0, "model.encoder.layer_norm")).numpy()))
+            print("  enc_t.numpy() vs raw enc_out:", rel(enc_t.numpy(), g_e.transpose(0, 2, 1)))
+        if stage == "enc1":
+            p = "model.encoder.layers.0."
+            xn = r(orc._ln(x0, p + "self_attn_layer_norm"))
+            q, k, v = [r(orc._lin(xn, p + f"self_attn.{n}_proj")) for n in "qkv"]
+            g_qkv = rd(4, B * T * 3 * d).reshape(B, T, 3 * d)
+            print("  qkv rel err:", rel(g_qkv, torch.cat([q, k, v], -1).numpy()))
+            qh, kh, vh = orc._heads(q), orc._heads(k), orc._heads(v)
+            a = torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh
+            a = r(a.transpose(1, 2).reshape(B, T, d))
+            g_a = rd(5, B * T * d).reshape(B, T, d)
+            print("  attn rel err:", rel(g_a, a.numpy()))
+            x1 = x0 + orc._lin(a, p + "self_attn.out_proj")
+            xn2 = r(orc._ln(x1, p + "final_layer_norm"))
+            g_xn = rd(3, B * T * d).reshape(B, T, d)
+            print("  LN2 (xn) rel err:", rel(g_xn, xn2.numpy()))
+            h = r(F.gelu(orc._lin(xn2, p + "fc1")))
+            g_f = rd(6, B * T * 4 * d).reshape(B, T, 4 * d)
+            print("  fc1+gelu rel err:", rel(g_f, h.numpy()))
+            x2 = x1 + orc._lin(h, p + "fc2")
+            g_x = rd(2, B * T * d).reshape(B, T, d)
+            print("  x after layer 0 rel err:", rel(g_x, x2.numpy()))
+        if stage.startswith("dec"):
+            dec = wk.TextDecoder(model, B)
+            dec.bindEncoderOutput(enc_t)
+            enc_gpu = torch.from_numpy(enc_t.numpy()).transpose(1, 2).contiguous()
+            cross = orc.cross_kv(enc_gpu)
+            H = dims.n_heads
+            ck = rd(15, B * H * T * 64, dec).reshape(B, H, T, 64)
+            cv = rd(15, B * H * T * 64, dec, off=B * H * T * 64).reshape(B, H, T, 64)
+            print("  cross K layer0 rel err:", rel(ck, cross[0][0].numpy()), " cross V layer0:", rel(cv, cross[0][1].numpy()))
+            toks = np.array([7, 11])
+            lg = dec.predictLogits(toks, [0, 0])
+            tk = torch.from_numpy(toks)
+            x = w["model.decoder.embed_tokens.weight"][tk] + w["model.decoder.embed_positions.weight"][0][None]
+            if stage == "dec0":
+                print("  embed x rel err:", rel(rd(10, B * d, dec).reshape(B, d), x.numpy()))
+                xn = r(orc._ln(x, "model.decoder.layers.0.self_attn_layer_norm"))
+                print("  LN1 xn rel err:", rel(rd(11, B * d, dec).reshape(B, d), xn.numpy()))
+                print("  logits (0 layers) rel err:", rel(lg, F.linear(xn, w["model.decoder.embed_tokens.weight"]).numpy()))
+            else:
+                p = "model.decoder.layers.0."
+                x = x[:, None]
+                xn = r(orc._ln(x, p + "self_attn_layer_norm"))
+                v = r(orc._lin(xn, p + "self_attn.v_proj"))
+                a = r(v)  # single position: softmax over one key = 1
+                x1 = x + orc._lin(a, p + "self_attn.out_proj")
+                xn = r(orc._ln(x1, p + "encoder_attn_layer_norm"))
+                q = orc._heads(orc._lin(xn, p + "encoder_attn.q_proj"))
+                ckk, cvv = cross[0]
+                a = torch.softmax(q @ ckk.transpose(-1, -2) * 0.125, -1) @ cvv
+                a = r(a.transpose(1, 2).reshape(B, 1, d))
+                print("  cross-attn out rel err:", rel(rd(12, B * d, dec).reshape(B, d), a[:, 0].numpy()))
+                x2 = x1 + orc._lin(a, p + "encoder_attn.out_proj")
+                xn = r(orc._ln(x2, p + "final_layer_norm"))
+                h = r(F.gelu(orc._lin(xn, p + "fc1")))
+                print("  fc1+gelu rel err:", rel(rd(13, B * 4 * d, dec).reshape(B, 4 * d), h[:, 0].numpy()))
+                x3 = x2 + orc._lin(h, p + "fc2")
+                print("  x after layer 0 rel err:", rel(rd(10, B * d, dec).reshape(B, d), x3[:, 0].numpy()))
+                xn = r(orc._ln(x3, "model.decoder.layer_norm"))
+                print("  final LN rel err:", rel(rd(11, B * d, dec).reshape(B, d), xn[:, 0].numpy()))
+                print("  logits (1 layer) rel err:", rel(lg, F.linear(xn[:, 0], w["model.decoder.embed_tokens.weight"]).numpy()))
+                sk = rd(16, B * H * 224 * 64, dec).reshape(B, H, 224, 64)[:, :, 0]
+                kk = orc._heads(r(orc._lin(r(orc._ln(x, p + "self_attn_layer_norm")), p + "self_attn.k_proj")))[:, :, 0]
+                print("  self K cache pos0 rel err:", rel(sk, kk.numpy()))
+
+
+if __name__ == "__main__":
+    variant = sys.argv[1] if len(sys.argv) > 1 else "toy128"
+    policy = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    if len(sys.argv) > 3:
+        child(variant, policy, sys.argv[3])
+        sys.exit(0)
+    for stage, env in (("enc0", {"WKB200_DEBUG_ENC_LAYERS": "0"}), ("enc1", {"WKB200_DEBUG_ENC_LAYERS": "1"}),
+                       ("dec0", {"WKB200_DEBUG_DEC_LAYERS": "0"}), ("dec1", {"WKB200_DEBUG_DEC_LAYERS": "1"})):
+        print(f"== {variant}/{policy} stage {stage}", flush=True)
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, __file__, variant, policy, stage], env=e, timeout=300)

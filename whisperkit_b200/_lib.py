@@ -111,6 +111,7 @@ SYMBOLS = [
     ("wk_test_gemm", I32, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32]),
     ("wk_test_gemm_splitk", I32, [P, P, P, P, I32, I32, I32, I32, I32]),
     ("wk_test_attention", I32, [P, P, P, I32, I32, I32, I32]),
+    ("wk_debug_read", I32, [P, P, I32, I64, P, I64]),
     ("wk_bench_kernel", I32, [P, P, I32, I32, I32, PF32, C.POINTER(C.c_double)]),
 ]
 

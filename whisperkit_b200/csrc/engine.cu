@@ -342,7 +342,9 @@ static wk_status encode_chunk(wk_model* m, int B) {
         g.out = m->x; g.ld_out = d; g.out_rows_per_batch = T; g.bias = m->conv2_b; g.pos = m->enc_pos; g.ld_pos = d;
         WK_CHECK(gemm_tcgen05(g, m->num_sms, s));
     }
-    for (int li = 0; li < c.enc_layers; ++li) {
+    int n_layers = c.enc_layers;
+    if (const char* e = getenv("WKB200_DEBUG_ENC_LAYERS")) n_layers = std::min(n_layers, atoi(e));  // stage debugging only
+    for (int li = 0; li < n_layers; ++li) {
         EncLayer& l = m->enc[li];
         WK_CHECK(layernorm_f32_to_16(m->x, l.ln1.g, l.ln1.b, m->xn, M, d, dt, s));
         WK_CHECK(gemm_tcgen05(plain_gemm(m->xn, M, d, l.wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, l.bqkv, 0), m->num_sms, s));
@@ -384,7 +386,9 @@ static wk_status decoder_forward(wk_session* s, int prompt_len, int ts_begin, co
     int sp = 1;
     WK_CHECK(decoder_embed_ln(m->emb, m->dec_pos, m->dec[0].ln1.g, m->dec[0].ln1.b, s->st, prompt_len, ts_begin, s->x, s->xn, B, d, dt,
                               explicit_pos ? 1 : 0, explicit_pos, st));
-    for (int li = 0; li < c.dec_layers; ++li) {
+    int n_layers = c.dec_layers;
+    if (const char* e = getenv("WKB200_DEBUG_DEC_LAYERS")) n_layers = std::min(n_layers, atoi(e));  // stage debugging only
+    for (int li = 0; li < n_layers; ++li) {
         DecLayer& l = m->dec[li];
         WK_CHECK(dec_gemm(s, l.wqkv, 3 * d, d, s->xn, &sp));
         WK_CHECK(decoder_self_attention(s->partial, sp, Bp, l.bq, l.bv, (char*)s->self_k + li * self_layer, (char*)s->self_v + li * self_layer,
@@ -399,7 +403,7 @@ static wk_status decoder_forward(wk_session* s, int prompt_len, int ts_begin, co
         WK_CHECK(dec_gemm(s, l.w1, 4 * d, d, s->xn, &sp));
         WK_CHECK(decoder_reduce_bias_gelu(s->partial, sp, Bp, l.b1, s->ffn, B, 4 * d, dt, st));
         WK_CHECK(dec_gemm(s, l.w2, d, 4 * d, s->ffn, &sp));
-        const LayerNormW& nxt = (li + 1 < c.dec_layers) ? m->dec[li + 1].ln1 : m->dec_ln;
+        const LayerNormW& nxt = (li + 1 < n_layers) ? m->dec[li + 1].ln1 : m->dec_ln;
         WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.b2, nxt.g, nxt.b, s->x, s->xn, B, d, dt, st));
     }
     // logits = xn . E^T  (tied embedding), written [B][V] f32 by the transposed-store epilogue (splits = 1)
@@ -1203,6 +1207,48 @@ wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t bat
     cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
     *ms_out = t / iters;
     return WK_OK;
+}
+
+// Debug readback of an internal buffer as f32 (tests/tools only).  which: 0 mel[Bm,3002,128] 1 h1[Bm,3002,d] 2 x[M,d]
+// 3 xn[M,d] 4 qkv[M,3d] 5 attn[M,d] 6 ffn[M,4d] 7 enc_out[M,d]; session: 10 x[Bp,d] 11 xn[Bp,d] 12 attn[Bp,d]
+// 13 ffn[Bp,4d] 14 logits[Bs,V] 15 cross_kv (all) 16 self_k (all) 17 self_v (all) 18 partial
+wk_status wk_debug_read(wk_model* m, wk_session* s, int32_t which, int64_t offset_elems, float* dst, int64_t n) {
+    if (!m || !dst) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    const void* src = nullptr;
+    int dt = m->cfg.dtype;
+    switch (which) {
+        case 0: src = m->mel; dt = WK_DTYPE_F16; break;
+        case 1: src = m->h1; dt = WK_DTYPE_F16; break;
+        case 2: src = m->x; dt = WK_DTYPE_F32; break;
+        case 3: src = m->xn; break;
+        case 4: src = m->qkv; break;
+        case 5: src = m->attn; break;
+        case 6: src = m->ffn; break;
+        case 7: src = m->enc_out; break;
+        case 10: src = s ? s->x : nullptr; dt = WK_DTYPE_F32; break;
+        case 11: src = s ? s->xn : nullptr; break;
+        case 12: src = s ? s->attn : nullptr; break;
+        case 13: src = s ? s->ffn : nullptr; break;
+        case 14: src = s ? s->logits : nullptr; dt = WK_DTYPE_F32; break;
+        case 15: src = s ? s->cross_kv : nullptr; break;
+        case 16: src = s ? s->self_k : nullptr; break;
+        case 17: src = s ? s->self_v : nullptr; break;
+        case 18: src = s ? s->partial : nullptr; dt = WK_DTYPE_F32; break;
+        default: break;
+    }
+    if (!src) { set_error("wk_debug_read: unknown buffer %d", which); return WK_ERR_INVALID_ARGUMENT; }
+    float* tmp = nullptr;
+    WK_CUDA_CHECK(cudaMalloc(&tmp, n * 4));
+    WK_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    wk_status r = convert_to_16((const char*)src + offset_elems * esize(dt), dt, tmp, WK_DTYPE_F32, n, m->stream);
+    if (r == WK_OK) {
+        cudaError_t e = cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) { set_error("wk_debug_read: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
+    }
+    cudaFree(tmp);
+    return r;
 }
 
 wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, int32_t T, int32_t n_heads, int32_t dtype) {
