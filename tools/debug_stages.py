@@ -75,6 +75,19 @@ def child(variant, policy, stage):
             h = r(F.gelu(orc._lin(xn2, p + "fc1")))
             g_f = rd(6, B * T * 4 * d).reshape(B, T, 4 * d)
             print("  fc1+gelu rel err:", rel(g_f, h.numpy()))
+            # isolate the GEMM: recompute FC1 on the host from the GPU's own input / weight buffers
+            g_w1 = torch.from_numpy(rd(22, 4 * d * d).reshape(4 * d, d))
+            g_b1 = torch.from_numpy(rd(24, 4 * d))
+            print("  w1 readback vs weights rel err:", rel(g_w1.numpy(), w[p + "fc1.weight"].numpy()), " b1:", rel(g_b1.numpy(), w[p + "fc1.bias"].numpy()))
+            g_wq = rd(20, 3 * d * d).reshape(3 * d, d)
+            exp_wq = torch.cat([w[p + f"self_attn.{n}_proj.weight"] for n in "qkv"]).numpy()
+            print("  wqkv readback rel err:", rel(g_wq, exp_wq), " per-part:", [rel(g_wq[i * d:(i + 1) * d], exp_wq[i * d:(i + 1) * d]) for i in range(3)])
+            h_self = F.gelu(F.linear(torch.from_numpy(g_xn), g_w1, g_b1))
+            print("  fc1 GEMM vs host recompute on GPU buffers rel err:", rel(g_f, h_self.numpy()))
+            bad = np.abs(g_f - h_self.numpy()).reshape(B * T, 4 * d)
+            rows_bad = np.where(bad.max(1) > 0.05)[0]
+            cols_bad = np.where(bad.max(0) > 0.05)[0]
+            print("  bad rows:", len(rows_bad), rows_bad[:10], " bad cols:", len(cols_bad), cols_bad[:10], cols_bad[-5:])
             x2 = x1 + orc._lin(h, p + "fc2")
             g_x = rd(2, B * T * d).reshape(B, T, d)
             print("  x after layer 0 rel err:", rel(g_x, x2.numpy()))

@@ -520,6 +520,7 @@ wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model**
     wk_status s = model_alloc(m);
     if (s != WK_OK) return s;
     WK_CHECK(mel_tables_create(cfg->n_mels, &m->mel_tables));
+    WK_CUDA_CHECK(cudaDeviceSynchronize());  // setup memsets / table uploads ran on the legacy default stream
     m->mel_tensor = {m->mel, 0, WK_DTYPE_F16, 0, m};
     m->enc_tensor = {m->enc_out, 1, cfg->dtype, 0, m};
     *out = m;
@@ -543,7 +544,9 @@ wk_status wk_model_set_tensor(wk_model* m, const char* name, const void* data, i
     }
     void* tmp = nullptr;
     WK_CUDA_CHECK(cudaMalloc(&tmp, numel * esize(dtype)));
-    WK_CUDA_CHECK(cudaMemcpy(tmp, data, numel * esize(dtype), cudaMemcpyDefault));
+    // stream-ordered copy: a pageable-host cudaMemcpy may return before its DMA lands, and the library stream is
+    // non-blocking (it does not order against the legacy default stream)
+    WK_CUDA_CHECK(cudaMemcpyAsync(tmp, data, numel * esize(dtype), cudaMemcpyDefault, m->stream));
     wk_status st = WK_OK;
     if (dst.special) {
         float* f = nullptr;
@@ -799,6 +802,7 @@ wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
     WK_CHECK(dmalloc(&s->ntok_scratch, max_batch));
     WK_CHECK(dmalloc(&s->tokout_dev, max_batch));
     WK_CHECK(dmalloc(&s->lpout_dev, max_batch));
+    WK_CUDA_CHECK(cudaDeviceSynchronize());  // setup memsets ran on the legacy default stream
     *out = s;
     return WK_OK;
 }
@@ -1235,6 +1239,12 @@ wk_status wk_debug_read(wk_model* m, wk_session* s, int32_t which, int64_t offse
         case 16: src = s ? s->self_k : nullptr; break;
         case 17: src = s ? s->self_v : nullptr; break;
         case 18: src = s ? s->partial : nullptr; dt = WK_DTYPE_F32; break;
+        case 20: src = m->enc[0].wqkv; break;
+        case 21: src = m->emb; break;
+        case 22: src = m->enc[0].w1; break;
+        case 23: src = m->wckv; break;
+        case 24: src = m->enc[0].b1; dt = WK_DTYPE_F32; break;
+        case 25: src = m->enc[0].bqkv; dt = WK_DTYPE_F32; break;
         default: break;
     }
     if (!src) { set_error("wk_debug_read: unknown buffer %d", which); return WK_ERR_INVALID_ARGUMENT; }
