@@ -36,6 +36,12 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 AUDIO_SECONDS_PER_WINDOW = 30.0
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    sys.stderr.write(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}\n")
+    sys.stderr.flush()
 
 
 def parse_args():
@@ -218,9 +224,11 @@ def run_own_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     B = args.batch
+    log(f"rank {rank}/{world}: creating model {args.variant} max_batch {B}")
     model = wk.Model(args.variant, device=local_rank, max_batch=B, dtype=args.dtype)
     model.init_random(seed=1234)
     dec = wk.TextDecoder(model, B)
+    log("model + session ready; generating synthetic PCM")
     lib = model.lib
     info = model.info
     st = special_tokens_for(info.vocab)
@@ -305,10 +313,16 @@ def run_own_arm(args):
             launches = int(lt.item())
         return ms, launches, (sampler.summary() if sampler else None)
 
+    log("PCM ready; first (untimed) pass")
+    t_first = time.perf_counter()
+    step_device()
+    log(f"first pass took {time.perf_counter() - t_first:.2f} s, stage ms {model.last_timings()}")
     ms, launches, clocks = timed(step_device, args.steps, max(args.warmup, 3), True)
+    log(f"device-resident arm: {ms / args.steps:.1f} ms/step")
     steps_run = [r.steps for r in res]
     timings = model.last_timings()
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1, False)
+    log(f"e2e arm: {ms_e2e / args.steps:.1f} ms/step")
     audio = world * B * AUDIO_SECONDS_PER_WINDOW * args.steps
     value = audio / (ms / 1000.0)
     e2e_value = audio / (ms_e2e / 1000.0)
@@ -355,6 +369,7 @@ def run_own_arm(args):
             kernels[names[which]] = {"bound": bound[which], "ms": t_ms, "achieved": ach, "peak": peak, "unit": unit,
                                      "frac": ach / peak, "launches_per_step": per_step[which],
                                      "share_of_step": per_step[which] * t_ms / ms_per_step}
+        log("per-kernel timings done")
         dom = max(kernels.items(), key=lambda kv: kv[1]["share_of_step"])
         line["roofline"] = {"kernel": dom[0], "bound": dom[1]["bound"], "achieved": dom[1]["achieved"], "peak": dom[1]["peak"],
                             "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": None,
@@ -364,7 +379,9 @@ def run_own_arm(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
+        log(f"CPU restatement on {threads} threads")
         rtfx, dt, nst = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
+        log(f"CPU restatement: {dt:.1f} s")
         line["cpu_baseline"] = {"value": rtfx, "unit": "audio-sec/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_windows} window(s) x 30 s, full pipeline ({nst} decoder steps), {dt:.1f} s of CPU "
                                           "work; fp32 PyTorch CPU restatement of the WhisperKit pipeline (one decoder call per token, "
