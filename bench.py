@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-windows", type=int, default=1)
+    ap.add_argument("--profile-pass", action="store_true", help="one untimed pass of the hot path and exit (for ncu)")
     return ap.parse_args()
 
 
@@ -143,14 +144,34 @@ _ORACLE_CACHE = {}
 
 def cpu_restatement(variant: str, sample_length: int, n_windows: int, threads: int, first_idx: int = 0):
     """Times the CPU oracle: log-mel + fp32 Whisper + the reference's decode loop (one decoder call per token,
-    batch 1 per stream - exactly how the reference schedules CoreML).  Returns (rtfx, seconds, steps)."""
+    batch 1 per stream - exactly how the reference schedules CoreML).  Returns (rtfx, seconds, steps, threads_used).
+    The encoder runs on all `threads`; the token loop (GEMV-sized ops) runs on the thread count that a short
+    calibration finds fastest (intra-op parallelism over >32 threads slows M=1 decoding down)."""
     import torch
     from oracle import decode_ref as D, mel_ref, model_ref as M
-    torch.set_num_threads(threads)
     dims = M.VARIANTS[variant]
     if variant not in _ORACLE_CACHE:  # weight generation (1.5 G parameters for large-v3) is setup, not timed work
-        _ORACLE_CACHE[variant] = M.WhisperOracle(dims, M.random_weights(dims, seed=1234, policy="fp32"), "fp32")
-    orc = _ORACLE_CACHE[variant]
+        log(f"CPU restatement: generating {variant} fp32 weights")
+        torch.set_num_threads(min(threads, 32))
+        orc = M.WhisperOracle(dims, M.random_weights(dims, seed=1234, policy="fp32", pool_size=1 << 24), "fp32")
+        cands = sorted({t for t in (4, 8, 16, 32, 64, threads) if t <= threads})
+        best, best_t = cands[0], float("inf")
+        with torch.no_grad():
+            enc = torch.zeros(1, dims.n_audio_ctx, dims.d_model)
+            cross = orc.cross_kv(enc)
+            for t in cands:
+                torch.set_num_threads(t)
+                cache = orc.new_cache(1)
+                orc.decode_step(torch.tensor([1]), 0, cache, cross)
+                t0 = time.perf_counter()
+                for i in range(1, 4):
+                    orc.decode_step(torch.tensor([1]), i, cache, cross)
+                dt = time.perf_counter() - t0
+                log(f"  decode calibration: {t} threads -> {dt / 3 * 1000:.1f} ms/step")
+                if dt < best_t:
+                    best, best_t = t, dt
+        _ORACLE_CACHE[variant] = (orc, best)
+    orc, dec_threads = _ORACLE_CACHE[variant]
     st = D.SpecialTokens.large_v3() if dims.vocab == 51866 else (D.SpecialTokens.english_only() if dims.vocab == 51864 else D.SpecialTokens())
     opts = D.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=sample_length)
     multilingual = dims.vocab != 51864
@@ -160,10 +181,12 @@ def cpu_restatement(variant: str, sample_length: int, n_windows: int, threads: i
     t0 = time.perf_counter()
     with torch.no_grad():
         for i in range(n_windows):
+            torch.set_num_threads(threads)
             mel = mel_ref.log_mel(pcm[i], dims.n_mels, dtype=np.float32).astype(np.float16).astype(np.float32)
             enc = orc.encode(torch.from_numpy(mel)[None])
             cross = orc.cross_kv(enc)
             cache = orc.new_cache(1)
+            torch.set_num_threads(dec_threads)
 
             def predict(tok, idx):
                 return orc.decode_step(torch.tensor([tok]), idx, cache, cross)[0].numpy()
@@ -171,7 +194,7 @@ def cpu_restatement(variant: str, sample_length: int, n_windows: int, threads: i
             r = D.decode_text(predict, prompt, opts, st, multilingual)
             steps += r.steps
     dt = time.perf_counter() - t0
-    return n_windows * AUDIO_SECONDS_PER_WINDOW / dt, dt, steps
+    return n_windows * AUDIO_SECONDS_PER_WINDOW / dt, dt, steps, (threads, dec_threads)
 
 
 def run_reference_arm(args):
@@ -186,8 +209,10 @@ def run_reference_arm(args):
     for i in range(warm):
         cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
     done = 0
+    used = (threads, threads)
     for i in range(args.steps):
-        rtfx, dt, _ = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads, first_idx=i)
+        rtfx, dt, _, used = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads, first_idx=i)
+        log(f"reference step {i}: {dt:.1f} s")
         times.append(dt)
         done += 1
         if time.perf_counter() - budget_t0 > 360 and done >= 1:
@@ -203,7 +228,8 @@ def run_reference_arm(args):
                    "sample_length": args.sample_length},
         "cpu_baseline": {"value": value, "unit": "audio-sec/s", "cores": threads, "kind": "port",
                          "sample": f"{args.cpu_windows} window(s) x 30 s per step, full pipeline, fp32 PyTorch CPU restatement of the "
-                                   "WhisperKit pipeline (the Swift/CoreML reference cannot run on Linux)"},
+                                   f"WhisperKit pipeline (the Swift/CoreML reference cannot run on Linux); encoder on {used[0]} "
+                                   f"threads, token loop on {used[1]} threads (calibrated fastest)"},
         "e2e": {"value": value, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -317,6 +343,10 @@ def run_own_arm(args):
     t_first = time.perf_counter()
     step_device()
     log(f"first pass took {time.perf_counter() - t_first:.2f} s, stage ms {model.last_timings()}")
+    if args.profile_pass:
+        step_device()
+        log(f"profile pass done, launches {int(lib.wk_kernel_launch_count(0))}")
+        return
     ms, launches, clocks = timed(step_device, args.steps, max(args.warmup, 3), True)
     log(f"device-resident arm: {ms / args.steps:.1f} ms/step")
     steps_run = [r.steps for r in res]
@@ -380,12 +410,13 @@ def run_own_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         log(f"CPU restatement on {threads} threads")
-        rtfx, dt, nst = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
+        rtfx, dt, nst, used = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
         log(f"CPU restatement: {dt:.1f} s")
         line["cpu_baseline"] = {"value": rtfx, "unit": "audio-sec/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_windows} window(s) x 30 s, full pipeline ({nst} decoder steps), {dt:.1f} s of CPU "
                                           "work; fp32 PyTorch CPU restatement of the WhisperKit pipeline (one decoder call per token, "
-                                          "batch 1) - the Swift/CoreML reference cannot run on Linux"}
+                                          f"batch 1; encoder on {used[0]} threads, token loop on {used[1]} threads) - the Swift/CoreML reference "
+                                          "cannot run on Linux"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

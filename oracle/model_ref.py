@@ -80,15 +80,32 @@ def sinusoids(length: int, channels: int) -> torch.Tensor:
 
 
 def random_weights(dims: WhisperDims, seed: int = 0, policy: str = "bf16", std: float = 0.02,
-                   device: str = "cpu") -> dict:
+                   device: str = "cpu", pool_size: int = 0) -> dict:
     """Seeded N(0, std) weights (LN gamma ~ 1 + N(0,0.02), small biases) under HF names.
     Values are pre-rounded to the 16-bit policy so CPU oracle and GPU engine see
     identical numbers.  conv1 is rounded to f16 (the engine feeds it f16 mel)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     w = {}
+    pool = torch.randn(pool_size, generator=g, dtype=torch.float32) if pool_size else None
+    cursor = [0]
 
     def rnd(*shape, s=std):
-        return torch.randn(*shape, generator=g, dtype=torch.float32) * s
+        if pool is None:
+            return torch.randn(*shape, generator=g, dtype=torch.float32) * s
+        # fast path for multi-billion-parameter CPU baselines: distinct memory per tensor, values drawn by
+        # sliding a window over a fixed seeded pool (same distribution; timing does not depend on values)
+        n = 1
+        for v in shape:
+            n *= v
+        out = torch.empty(n, dtype=torch.float32)
+        done = 0
+        while done < n:
+            off = (cursor[0] * 7919) % max(1, pool_size // 2)
+            take = min(n - done, pool_size - off)
+            out[done:done + take] = pool[off:off + take]
+            done += take
+            cursor[0] += 1
+        return out.view(*shape) * s
 
     def lin(name, out_f, in_f, bias=True):
         w[name + ".weight"] = round_to(rnd(out_f, in_f), policy)
