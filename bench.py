@@ -162,7 +162,11 @@ def cpu_restatement(variant: str, sample_length: int, n_windows: int, threads: i
             for t in cands:
                 torch.set_num_threads(t)
                 cache = orc.new_cache(1)
+                t0 = time.perf_counter()
                 orc.decode_step(torch.tensor([1]), 0, cache, cross)
+                if time.perf_counter() - t0 > 5 * best_t / 3 + 0.5:
+                    log(f"  decode calibration: {t} threads slower than {best} - stopping")
+                    break
                 t0 = time.perf_counter()
                 for i in range(1, 4):
                     orc.decode_step(torch.tensor([1]), i, cache, cross)
@@ -170,8 +174,26 @@ def cpu_restatement(variant: str, sample_length: int, n_windows: int, threads: i
                 log(f"  decode calibration: {t} threads -> {dt / 3 * 1000:.1f} ms/step")
                 if dt < best_t:
                     best, best_t = t, dt
-        _ORACLE_CACHE[variant] = (orc, best)
-    orc, dec_threads = _ORACLE_CACHE[variant]
+                elif dt > 2 * best_t:
+                    break
+            # encoder-sized work (one layer's FFN on 1500 rows): same search, separately
+            xx = torch.randn(1, dims.n_audio_ctx, dims.d_model)
+            w1, w2 = orc.w["model.encoder.layers.0.fc1.weight"], orc.w["model.encoder.layers.0.fc2.weight"]
+            ebest, ebest_t = cands[0], float("inf")
+            for t in cands:
+                torch.set_num_threads(t)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(xx, w1)), w2)
+                dt = time.perf_counter() - t0
+                log(f"  encoder calibration: {t} threads -> {dt / 2 * 1000:.1f} ms/FFN")
+                if dt < ebest_t:
+                    ebest, ebest_t = t, dt
+                elif dt > 2 * ebest_t:
+                    break
+        _ORACLE_CACHE[variant] = (orc, best, ebest)
+    orc, dec_threads, enc_threads = _ORACLE_CACHE[variant]
+    threads = enc_threads
     st = D.SpecialTokens.large_v3() if dims.vocab == 51866 else (D.SpecialTokens.english_only() if dims.vocab == 51864 else D.SpecialTokens())
     opts = D.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=sample_length)
     multilingual = dims.vocab != 51864
@@ -226,7 +248,7 @@ def run_reference_arm(args):
         "config": {"workload": f"whisper-{args.variant} greedy, {args.cpu_windows} x 30 s window per step (bounded CPU sample of the "
                                f"batch={args.batch} x 30 s GPU workload), sampleLength={args.sample_length}, timestamps on",
                    "sample_length": args.sample_length},
-        "cpu_baseline": {"value": value, "unit": "audio-sec/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "audio-sec/s", "cores": max(used), "host_cores": threads, "kind": "port",
                          "sample": f"{args.cpu_windows} window(s) x 30 s per step, full pipeline, fp32 PyTorch CPU restatement of the "
                                    f"WhisperKit pipeline (the Swift/CoreML reference cannot run on Linux); encoder on {used[0]} "
                                    f"threads, token loop on {used[1]} threads (calibrated fastest)"},
@@ -283,10 +305,10 @@ def run_own_arm(args):
     # e2e: host PCM in, token IDs on the host out.  N > 1: rank 0 owns all N*B windows in pinned memory, copies them
     # to its GPU, NCCL scatters shards over NVLink, every rank transcribes, NCCL gathers token IDs back to rank 0.
     if world > 1:
+        from whisperkit_b200 import distributed as WD
+        from whisperkit_b200.api import DecodingResult
         all_host = torch.from_numpy(synthetic_windows(0, world * B)).pin_memory() if rank == 0 else None
-        shard = torch.empty(B, 480000, device="cuda", dtype=torch.float32)
-        tok_dev = torch.empty(B, 228, device="cuda", dtype=torch.int32)
-        gather_list = [torch.empty_like(tok_dev) for _ in range(world)] if rank == 0 else None
+        dev = torch.device("cuda", local_rank)
     d2h_bytes = B * (224 * 8 + 16)
 
     def step_e2e():
@@ -294,23 +316,17 @@ def run_own_arm(args):
             check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(pcm_host.data_ptr()), B, 480000, None,
                                             C.byref(st_c), C.byref(o_c), p_c, len(prompt), res))
             return
+
+        def local(shard):
+            torch.cuda.synchronize()  # NCCL ran on torch's stream; the library has its own
+            check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(shard.data_ptr()), shard.shape[0], 480000, None,
+                                            C.byref(st_c), C.byref(o_c), p_c, len(prompt), res))
+            return [DecodingResult.from_c(res[b]) for b in range(shard.shape[0])]
+
+        staged = all_host.to(dev, non_blocking=True) if rank == 0 else None
+        toks = WD.transcribe_sharded(staged, world * B, 480000, dev, local)
         if rank == 0:
-            staged = all_host.cuda(non_blocking=True)
-            chunks = list(staged.chunk(world, dim=0))
-        else:
-            chunks = None
-        dist.scatter(shard, chunks, src=0)
-        torch.cuda.synchronize()
-        check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(shard.data_ptr()), B, 480000, None, C.byref(st_c),
-                                        C.byref(o_c), p_c, len(prompt), res))
-        host_tok = np.zeros((B, 228), dtype=np.int32)
-        for b in range(B):
-            host_tok[b, 0] = res[b].n_tokens
-            host_tok[b, 1:1 + res[b].n_tokens] = res[b].tokens[:res[b].n_tokens]
-        tok_dev.copy_(torch.from_numpy(host_tok), non_blocking=False)
-        dist.gather(tok_dev, gather_list, dst=0)
-        if rank == 0:
-            _ = torch.stack(gather_list).cpu()
+            assert len(toks) == world * B
 
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
@@ -401,8 +417,15 @@ def run_own_arm(args):
                                      "share_of_step": per_step[which] * t_ms / ms_per_step}
         log("per-kernel timings done")
         dom = max(kernels.items(), key=lambda kv: kv[1]["share_of_step"])
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel (same batch / model only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if args.variant == "large-v3" and B == 64 and dom[0] in tj:
+                traffic = tj[dom[0]]["bytes"]
+        except Exception:
+            pass
         line["roofline"] = {"kernel": dom[0], "bound": dom[1]["bound"], "achieved": dom[1]["achieved"], "peak": dom[1]["peak"],
-                            "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": None,
+                            "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": traffic,
                             "peak_source": peaks["source"] + " (MEASURED_PEAKS.json burst figures; kernel timed alone)",
                             "share_of_step": dom[1]["share_of_step"]}
         line["kernels"] = kernels
@@ -412,7 +435,7 @@ def run_own_arm(args):
         log(f"CPU restatement on {threads} threads")
         rtfx, dt, nst, used = cpu_restatement(args.variant, args.sample_length, args.cpu_windows, threads)
         log(f"CPU restatement: {dt:.1f} s")
-        line["cpu_baseline"] = {"value": rtfx, "unit": "audio-sec/s", "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": rtfx, "unit": "audio-sec/s", "cores": max(used), "host_cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_windows} window(s) x 30 s, full pipeline ({nst} decoder steps), {dt:.1f} s of CPU "
                                           "work; fp32 PyTorch CPU restatement of the WhisperKit pipeline (one decoder call per token, "
                                           f"batch 1; encoder on {used[0]} threads, token loop on {used[1]} threads) - the Swift/CoreML reference "
