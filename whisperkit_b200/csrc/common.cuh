@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace wk {
 
@@ -182,6 +183,13 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int fmt, int M, int N) {
     return d;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// launch_dependents: lets the next kernel in the stream start its prologue while this grid is still running;
+// wait: blocks until the upstream grid has completed and its memory is visible.  Both are no-ops when the kernel
+// was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
     uint32_t sz = pred ? 16u : 0u;
@@ -191,6 +199,26 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Host-side launcher: cudaLaunchKernelEx with the PDL attribute when enabled (WKB200_NO_PDL=1 disables it).
+bool pdl_enabled();
+void pdl_disable();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace wk

@@ -73,6 +73,8 @@ decoder_embed_ln_kernel(const T* __restrict__ emb, const float* __restrict__ pos
                         T* __restrict__ xn, int d, int explicit_inputs, const int32_t* __restrict__ explicit_pos) {
     __shared__ float scratch[32];
     const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     int tok, pos;
     if (explicit_inputs) {
         tok = st.input_ids[b];
@@ -126,9 +128,9 @@ wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gam
                            const int32_t* explicit_pos, cudaStream_t stream) {
     if (d > 2048) { set_error("decoder_embed_ln: d_model %d > 2048", d); return WK_ERR_INVALID_ARGUMENT; }
     if (dtype == WK_DTYPE_F16)
-        decoder_embed_ln_kernel<__half><<<B, 256, 0, stream>>>((const __half*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__half*)xn, d, explicit_inputs, explicit_pos);
+        launch_k(decoder_embed_ln_kernel<__half>, dim3(B), dim3(256), 0, stream, true, (const __half*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__half*)xn, d, explicit_inputs, explicit_pos);
     else
-        decoder_embed_ln_kernel<__nv_bfloat16><<<B, 256, 0, stream>>>((const __nv_bfloat16*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_inputs, explicit_pos);
+        launch_k(decoder_embed_ln_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, stream, true, (const __nv_bfloat16*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_inputs, explicit_pos);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_embed_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -138,48 +140,79 @@ wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gam
 // =====================================================================================================
 // split-K reduce + bias + residual + LayerNorm      (partials [S][Bp][d] f32, written by the swap-AB GEMM)
 // =====================================================================================================
+static constexpr int kReduceThreads = 320;   // one float4 per thread at d = 1280
+static constexpr int kMaxSplits = 20;
+
+// All split-K partial loads of a thread are issued back to back (fully unrolled, predicated) so the kernel pays one
+// L2 round trip instead of `splits` serial ones; the sum runs in a fixed order (deterministic).
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReduceThreads)
 decoder_reduce_resid_ln_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bias,
                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x,
                                T* __restrict__ xn, int d) {
     __shared__ float scratch[32];
     const int b = blockIdx.x, tid = threadIdx.x;
-    float v[8];
+    const int d4 = d >> 2;
+    pdl_launch_dependents();
+    pdl_wait();
+    float4 v[2];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i = tid + k * 256;
-        v[k] = 0.f;
-        if (i < d) {
-            float a = x[(long long)b * d + i] + (bias ? bias[i] : 0.f);
-            for (int sp = 0; sp < splits; ++sp) a += partial[((long long)sp * Bp + b) * d + i];
+    for (int k = 0; k < 2; ++k) {
+        const int i4 = tid + k * kReduceThreads;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < d4) {
+            float4 p[kMaxSplits];
+#pragma unroll
+            for (int sp = 0; sp < kMaxSplits; ++sp)
+                if (sp < splits) p[sp] = __ldcg(reinterpret_cast<const float4*>(partial + ((long long)sp * Bp + b) * d) + i4);
+            float4 a = reinterpret_cast<const float4*>(x + (long long)b * d)[i4];
+            if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + i4);
+                a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+            }
+#pragma unroll
+            for (int sp = 0; sp < kMaxSplits; ++sp)
+                if (sp < splits) { a.x += p[sp].x; a.y += p[sp].y; a.z += p[sp].z; a.w += p[sp].w; }
             v[k] = a;
-            x[(long long)b * d + i] = a;
-            s += a;
+            reinterpret_cast<float4*>(x + (long long)b * d)[i4] = a;
+            s += a.x + a.y + a.z + a.w;
         }
     }
     const float mean = block_sum(s, scratch) / d;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i = tid + k * 256;
-        if (i < d) { const float a = v[k] - mean; q += a * a; }
+    for (int k = 0; k < 2; ++k) {
+        const int i4 = tid + k * kReduceThreads;
+        if (i4 < d4) {
+            const float a0 = v[k].x - mean, a1 = v[k].y - mean, a2 = v[k].z - mean, a3 = v[k].w - mean;
+            q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        }
     }
     const float rstd = rsqrtf(block_sum(q, scratch) / d + 1e-5f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i = tid + k * 256;
-        if (i < d) xn[(long long)b * d + i] = T16<T>::from_f((v[k] - mean) * rstd * gamma[i] + beta[i]);
+    for (int k = 0; k < 2; ++k) {
+        const int i4 = tid + k * kReduceThreads;
+        if (i4 < d4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i4), bb = __ldg(reinterpret_cast<const float4*>(beta) + i4);
+            uint2 pk;
+            pk.x = T16<T>::pack2((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
+            pk.y = T16<T>::pack2((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+            reinterpret_cast<uint2*>(xn + (long long)b * d)[i4] = pk;
+        }
     }
 }
 
 wk_status decoder_reduce_resid_ln(const float* partial, int splits, int Bp, const float* bias, const float* gamma,
                                   const float* beta, float* x, void* xn, int B, int d, int dtype, cudaStream_t stream) {
+    if (splits > kMaxSplits || d > 8 * kReduceThreads || (d & 3)) {
+        set_error("decoder_reduce_resid_ln: unsupported splits %d / d %d", splits, d);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
     if (dtype == WK_DTYPE_F16)
-        decoder_reduce_resid_ln_kernel<__half><<<B, 256, 0, stream>>>(partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
+        launch_k(decoder_reduce_resid_ln_kernel<__half>, dim3(B), dim3(kReduceThreads), 0, stream, true, partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
     else
-        decoder_reduce_resid_ln_kernel<__nv_bfloat16><<<B, 256, 0, stream>>>(partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
+        launch_k(decoder_reduce_resid_ln_kernel<__nv_bfloat16>, dim3(B), dim3(kReduceThreads), 0, stream, true, partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_reduce_resid_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -190,13 +223,22 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 decoder_reduce_bias_gelu_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bias,
                                 T* __restrict__ out, int B, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (idx >= (long long)B * n) return;
     const int b = (int)(idx / n), i = (int)(idx - (long long)b * n);
     float4 a = *reinterpret_cast<const float4*>(bias + i);
-    for (int sp = 0; sp < splits; ++sp) {
-        const float4 p = *reinterpret_cast<const float4*>(partial + ((long long)sp * Bp + b) * n + i);
-        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    float4 p[8];
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp)
+        if (sp < splits) p[sp] = __ldcg(reinterpret_cast<const float4*>(partial + ((long long)sp * Bp + b) * n + i));
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp)
+        if (sp < splits) { a.x += p[sp].x; a.y += p[sp].y; a.z += p[sp].z; a.w += p[sp].w; }
+    for (int sp = 8; sp < splits; ++sp) {
+        const float4 pp = __ldcg(reinterpret_cast<const float4*>(partial + ((long long)sp * Bp + b) * n + i));
+        a.x += pp.x; a.y += pp.y; a.z += pp.z; a.w += pp.w;
     }
     uint2 pk;
     pk.x = T16<T>::pack2(gelu_erf(a.x), gelu_erf(a.y));
@@ -209,9 +251,9 @@ wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, con
     const long long threads = (long long)B * n / 4;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (dtype == WK_DTYPE_F16)
-        decoder_reduce_bias_gelu_kernel<__half><<<grid, 256, 0, stream>>>(partial, splits, Bp, bias, (__half*)out, B, n);
+        launch_k(decoder_reduce_bias_gelu_kernel<__half>, dim3(grid), dim3(256), 0, stream, true, partial, splits, Bp, bias, (__half*)out, B, n);
     else
-        decoder_reduce_bias_gelu_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
+        launch_k(decoder_reduce_bias_gelu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, true, partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_reduce_bias_gelu launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -235,6 +277,8 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     __shared__ float sp[4][kMaxCtx];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x * 4 + warp;
+    pdl_launch_dependents();
+    pdl_wait();
     if (bh >= B * H) return;
     const int b = bh / H, h = bh % H;
     const int dm = H * 64;
@@ -303,7 +347,19 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     // output: lane handles dims e, e+1
     float2 acc = make_float2(0.f, 0.f);
     const T* vb = vcache + (long long)bh * max_len * 64 + e;
-    for (int t = 0; t < pos; ++t) {
+    int t = 0;
+    for (; t + 8 <= pos; t += 8) {   // 8 independent 128-byte row reads in flight per warp
+        uint32_t u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = *reinterpret_cast<const uint32_t*>(vb + (long long)(t + j) * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 vv = T16<T>::unpack2(u[j]);
+            const float p = sp[warp][t + j];
+            acc.x += p * vv.x; acc.y += p * vv.y;
+        }
+    }
+    for (; t < pos; ++t) {
         const float2 vv = T16<T>::unpack2(*reinterpret_cast<const uint32_t*>(vb + (long long)t * 64));
         const float p = sp[warp][t];
         acc.x += p * vv.x; acc.y += p * vv.y;
@@ -322,9 +378,9 @@ wk_status decoder_self_attention(const float* partial, int splits, int Bp, const
     if (max_len > kMaxCtx) { set_error("decoder_self_attention: max_len %d > %d", max_len, kMaxCtx); return WK_ERR_INVALID_ARGUMENT; }
     const unsigned grid = (unsigned)((B * H + 3) / 4);
     if (dtype == WK_DTYPE_F16)
-        decoder_self_attention_kernel<__half><<<grid, 128, 0, stream>>>(partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, step, explicit_pos, (__half*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, true, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, step, explicit_pos, (__half*)out, B, H, max_len);
     else
-        decoder_self_attention_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, step, explicit_pos, (__nv_bfloat16*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, true, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, step, explicit_pos, (__nv_bfloat16*)out, B, H, max_len);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_self_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -359,10 +415,12 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
     const int bh = blockIdx.x, b = bh / H, h = bh % H;
     const int dm = H * 64;
     const int chunks = Tlen / kCrossRows;  // per K and per V
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < kCrossStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
         fence_barrier_init();
     }
+    pdl_wait();
     if (tid < 64) {
         float q = bq[h * 64 + tid];
         for (int s = 0; s < splits; ++s) q += partial[((long long)s * Bp + b) * dm + h * 64 + tid];
@@ -494,9 +552,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
         attr_set[ti] = true;
     }
     if (dtype == WK_DTYPE_F16)
-        decoder_cross_attention_kernel<__half><<<B * H, kCrossThreads, smem, stream>>>(partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T);
+        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T);
     else
-        decoder_cross_attention_kernel<__nv_bfloat16><<<B * H, kCrossThreads, smem, stream>>>(partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T);
+        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_cross_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -528,6 +586,8 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
     const int b = blockIdx.x, tid = threadIdx.x;
     const int V = p.vocab;
     const bool loop_mode = p.prompt_len >= 0;
+    pdl_launch_dependents();
+    pdl_wait();
     const int32_t* toks = loop_mode ? st.tokens + b * kMaxCtx : tokens_in + (long long)b * ld_tokens;
     const int n_tok = loop_mode ? st.n_tokens[b] : n_tokens_in[b];
     const wk_special_tokens& S = p.st;
@@ -692,7 +752,11 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
     }
 }
 
-__global__ void advance_step_kernel(DecodeState st) { *st.step += 1; }
+__global__ void advance_step_kernel(DecodeState st) {
+    pdl_launch_dependents();
+    pdl_wait();
+    *st.step += 1;
+}
 
 wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
                                 int ld_tokens, const int32_t* n_tokens, int32_t* token_out, float* logprob_out,
@@ -709,11 +773,11 @@ wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerP
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(sampler): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
         attr_set = true;
     }
-    sampler_kernel<<<B, kSamplerThreads, smem, stream>>>(logits, (long long)ld_logits, p, st, tokens, ld_tokens, n_tokens, token_out,
-                                                        logprob_out, filtered_out);
+    launch_k(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, stream, true, logits, (long long)ld_logits, p, st, tokens, ld_tokens,
+             n_tokens, token_out, logprob_out, filtered_out);
     count_launch();
     if (p.prompt_len >= 0) {
-        advance_step_kernel<<<1, 1, 0, stream>>>(st);
+        launch_k(advance_step_kernel, dim3(1), dim3(1), 0, stream, true, st);
         count_launch();
     }
     cudaError_t e = cudaGetLastError();

@@ -28,6 +28,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 static std::atomic<long long> g_launches{0};
+static int g_pdl = -1;
+bool pdl_enabled() {
+    if (g_pdl < 0) g_pdl = getenv("WKB200_NO_PDL") ? 0 : 1;
+    return g_pdl == 1;
+}
+void pdl_disable() { g_pdl = 0; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -137,7 +143,7 @@ static int choose_splits(int tiles, int total_kb, int num_sms) {
     for (int s = 1; s <= total_kb; ++s) {
         if (total_kb % s) continue;
         best = s;
-        if (tiles * s >= (num_sms * 9) / 10) break;
+        if (tiles * s >= (num_sms * 13) / 20) break;  // >= 0.65 * SMs pulling weights; fewer partials to reduce
     }
     return best;
 }
@@ -370,6 +376,7 @@ static wk_status dec_gemm(wk_session* s, const void* w, int N, int K, const void
     const int tiles = (N + 127) / 128;
     g.splits = choose_splits(tiles, K / 64, m->num_sms);
     g.mode = GEMM_OUT_PARTIAL_T; g.out = s->partial; g.ld_out = N; g.out_rows_per_batch = N; g.partial_cols = s->bp;
+    g.pdl = 1;
     if ((size_t)g.splits * s->bp * N > s->partial_elems) { set_error("partial workspace too small"); return WK_ERR_DECODING_FAILED; }
     *splits_out = g.splits;
     return gemm_tcgen05(g, m->num_sms, m->stream);
@@ -414,6 +421,7 @@ static wk_status decoder_forward(wk_session* s, int prompt_len, int ts_begin, co
         g.b = s->xn; g.b_rows = Bp; g.b_ld = d; g.in_dtype = dt;
         g.m_rows_per_batch = c.vocab; g.n = Bp; g.k = d; g.taps = 1; g.bn = Bp; g.splits = 1;
         g.mode = GEMM_OUT_PARTIAL_T; g.out = s->logits; g.ld_out = c.vocab; g.out_rows_per_batch = c.vocab; g.partial_cols = B;
+        g.pdl = 1;
         WK_CHECK(gemm_tcgen05(g, m->num_sms, st));
     }
     return WK_OK;
@@ -1004,6 +1012,14 @@ wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_de
                 if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
                 e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
                 cudaGraphDestroy(graph);
+                if (e != cudaSuccess && pdl_enabled()) {
+                    // programmatic edges rejected by this driver: fall back to plain serialisation and re-capture
+                    cudaGetLastError();
+                    pdl_disable();
+                    s->graph_exec = nullptr;
+                    --step;
+                    continue;
+                }
                 if (e != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             }
             WK_CUDA_CHECK(cudaGraphLaunch(s->graph_exec, stream));

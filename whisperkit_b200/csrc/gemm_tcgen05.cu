@@ -67,6 +67,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();   // the next kernel may start its prologue; it still waits for our completion
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -89,6 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                // upstream results visible from here on (barrier init / TMEM alloc overlapped its tail)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -401,7 +403,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             attr_set = true;
         }
-        gemm_tcgen05_kernel<__half><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+        e = launch_k(gemm_tcgen05_kernel<__half>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0, tmA, tmB, p);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
@@ -409,7 +411,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             attr_set = true;
         }
-        gemm_tcgen05_kernel<__nv_bfloat16><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+        e = launch_k(gemm_tcgen05_kernel<__nv_bfloat16>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0, tmA, tmB, p);
     }
     count_launch();
     e = cudaGetLastError();

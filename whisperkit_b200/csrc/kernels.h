@@ -57,6 +57,7 @@ struct GemmDesc {
     int64_t ld_pos;
     // HEADS scatter
     int heads_T, heads_B, heads_H, heads_dmodel;
+    int pdl;                 // launch with programmatic dependent launch (decode-step chain)
 };
 
 wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream);
