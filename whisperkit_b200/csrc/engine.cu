@@ -30,7 +30,7 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static int g_pdl = -1;
 bool pdl_enabled() {
-    if (g_pdl < 0) g_pdl = getenv("WKB200_NO_PDL") ? 0 : 1;
+    if (g_pdl < 0) g_pdl = getenv("WKB200_PDL") ? 1 : 0;   // measured slower on B200 (1491 vs 1388 ms/step): opt-in only
     return g_pdl == 1;
 }
 void pdl_disable() { g_pdl = 0; }
@@ -1206,6 +1206,16 @@ wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t bat
             case 3: return encoder_attention(m->qkv, m->attn, B, T, H, dt, st);
             case 4: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].wqkv, 3 * d, d, s->xn, &sp); }
             case 5: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, m->enc[0].bqkv, 0), m->num_sms, st);
+            case 6: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].wo, d, d, s->attn, &sp); }
+            case 7: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].w2, d, 4 * d, s->ffn, &sp); }
+            case 8: { if (!s) return WK_ERR_INVALID_ARGUMENT;
+                      return decoder_reduce_resid_ln(s->partial, choose_splits((d + 127) / 128, d / 64, m->num_sms), round_up(B, 16), m->dec[0].bo,
+                                                     m->dec[0].lnx.g, m->dec[0].lnx.b, s->x, s->xn, B, d, dt, st); }
+            case 9: { if (!s) return WK_ERR_INVALID_ARGUMENT;
+                      static int32_t* pos100 = nullptr;
+                      if (!pos100) { std::vector<int32_t> h(256, 100); cudaMalloc(&pos100, 256 * 4); cudaMemcpy(pos100, h.data(), 256 * 4, cudaMemcpyHostToDevice); }
+                      return decoder_self_attention(s->partial, 1, round_up(B, 16), m->dec[0].bq, m->dec[0].bv, s->self_k, s->self_v, s->st.step, pos100,
+                                                    s->attn, B, H, kKvMaxLen, dt, st); }
             default: set_error("wk_bench_kernel: unknown kernel %d", which); return WK_ERR_INVALID_ARGUMENT;
         }
     };
@@ -1216,15 +1226,36 @@ wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t bat
         case 3: *work_out = 4.0 * (double)B * H * T * T * 64; break;                       // FLOPs
         case 4: *work_out = 3.0 * d * d * 2; break;                                        // weight bytes
         case 5: *work_out = 2.0 * (double)M * d * 3 * d; break;
+        case 6: *work_out = 1.0 * d * d * 2; break;
+        case 7: *work_out = 4.0 * d * d * 2; break;
         default: *work_out = 0; break;
     }
     for (int i = 0; i < 2; ++i) WK_CHECK(run());
-    WK_CUDA_CHECK(cudaEventRecord(m->ev[6], st));
-    for (int i = 0; i < iters; ++i) WK_CHECK(run());
-    WK_CUDA_CHECK(cudaEventRecord(m->ev[7], st));
-    WK_CUDA_CHECK(cudaEventSynchronize(m->ev[7]));
     float t = 0.f;
-    cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
+    if (getenv("WKB200_BENCH_GRAPH")) {   // host launch cost removed: `iters` launches replayed as one CUDA graph
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        WK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        wk_status r = WK_OK;
+        for (int i = 0; i < iters && r == WK_OK; ++i) r = run();
+        WK_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+        if (r != WK_OK) return r;
+        WK_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        WK_CUDA_CHECK(cudaGraphLaunch(exec, st));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[6], st));
+        WK_CUDA_CHECK(cudaGraphLaunch(exec, st));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[7], st));
+        WK_CUDA_CHECK(cudaEventSynchronize(m->ev[7]));
+        cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    } else {
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[6], st));
+        for (int i = 0; i < iters; ++i) WK_CHECK(run());
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[7], st));
+        WK_CUDA_CHECK(cudaEventSynchronize(m->ev[7]));
+        cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
+    }
     *ms_out = t / iters;
     return WK_OK;
 }

@@ -17,6 +17,9 @@
 // Sources/WhisperKit/Core/TextDecoder.swift:394-417).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -48,6 +51,8 @@ struct GemmKParams {
     const float* pos;
     long long ld_pos;
     int heads_T, heads_B, heads_H, heads_dmodel;
+    int debug_mode;   // 0 normal; 1 exit after setup; 2 skip the epilogue stores (latency decomposition, WKB200_GEMM_DEBUG)
+    int tmem_cols;
 };
 
 template <typename T>
@@ -83,7 +88,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_alloc(tmem_slot, p.tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -92,6 +97,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                // upstream results visible from here on (barrier init / TMEM alloc overlapped its tail)
 
+    if (p.debug_mode == 1) {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+        return;
+    }
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -180,7 +190,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld_wait();
                 const int col0 = col_base + c;
                 if (p.mode == GEMM_OUT_PARTIAL_T) {
-                    if (row_ok) {
+                    if (row_ok && p.debug_mode != 2) {
                         float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -264,7 +274,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -359,7 +369,14 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > total_kb / p.splits + 2) stages = total_kb / p.splits + 2;
     if (stages < 2) stages = 2;
+    if (const char* e = getenv("WKB200_GEMM_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     p.stages = stages;
+    p.debug_mode = 0;
+    if (const char* e = getenv("WKB200_GEMM_DEBUG")) p.debug_mode = atoi(e);
+    // TMEM: two accumulator stages of kAccStride columns when a CTA may run several tiles, else the smallest power of two >= BN
+    p.tmem_cols = kTmemCols;
+    if (p.work <= num_sms) { int c = 32; while (c < d.bn) c <<= 1; p.tmem_cols = c; }
+    if (const char* e = getenv("WKB200_GEMM_TMEM")) p.tmem_cols = atoi(e);
     p.mode = d.mode;
     p.gelu = d.gelu;
     p.out = d.out;
