@@ -344,32 +344,48 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     }
     ssum = warp_sum(ssum);
     __syncwarp();
-    // output: lane handles dims e, e+1
-    float2 acc = make_float2(0.f, 0.f);
-    const T* vb = vcache + (long long)bh * max_len * 64 + e;
-    int t = 0;
-    for (; t + 8 <= pos; t += 8) {   // 8 independent 128-byte row reads in flight per warp
-        uint32_t u[8];
+    // output: 16-byte loads, 4 cache rows per warp instruction, 8 instructions in flight: lane = (row % 4, 8-dim chunk)
+    const int sub = lane & 7, rsel = lane >> 3;
+    float o8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = *reinterpret_cast<const uint32_t*>(vb + (long long)(t + j) * 64);
+    for (int j = 0; j < 8; ++j) o8[j] = 0.f;
+    const T* vb = vcache + (long long)bh * max_len * 64 + sub * 8;
+    for (int t0 = 0; t0 < pos; t0 += 32) {
+        uint4 u[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float2 vv = T16<T>::unpack2(u[j]);
-            const float p = sp[warp][t + j];
-            acc.x += p * vv.x; acc.y += p * vv.y;
+            const int t = t0 + 4 * j + rsel;
+            u[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + (long long)t * 64) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = t0 + 4 * j + rsel;
+            const float p = (t < pos) ? sp[warp][t] : 0.f;
+            const float2 a0 = T16<T>::unpack2(u[j].x), a1 = T16<T>::unpack2(u[j].y), a2 = T16<T>::unpack2(u[j].z), a3 = T16<T>::unpack2(u[j].w);
+            o8[0] += p * a0.x; o8[1] += p * a0.y; o8[2] += p * a1.x; o8[3] += p * a1.y;
+            o8[4] += p * a2.x; o8[5] += p * a2.y; o8[6] += p * a3.x; o8[7] += p * a3.y;
         }
     }
-    for (; t < pos; ++t) {
-        const float2 vv = T16<T>::unpack2(*reinterpret_cast<const uint32_t*>(vb + (long long)t * 64));
-        const float p = sp[warp][t];
-        acc.x += p * vv.x; acc.y += p * vv.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        o8[j] += __shfl_xor_sync(0xffffffffu, o8[j], 8);
+        o8[j] += __shfl_xor_sync(0xffffffffu, o8[j], 16);
     }
+    // the current position comes from registers/smem (its cache row was written by this warp just above)
     {
         const float p = sp[warp][pos];
-        acc.x += p * svc[warp][e]; acc.y += p * svc[warp][e + 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] += p * svc[warp][sub * 8 + j];
     }
     const float inv = 1.f / ssum;
-    *reinterpret_cast<uint32_t*>(out + (long long)b * dm + h * 64 + e) = T16<T>::pack2(acc.x * inv, acc.y * inv);
+    if (rsel == 0) {
+        uint4 pk;
+        pk.x = T16<T>::pack2(o8[0] * inv, o8[1] * inv);
+        pk.y = T16<T>::pack2(o8[2] * inv, o8[3] * inv);
+        pk.z = T16<T>::pack2(o8[4] * inv, o8[5] * inv);
+        pk.w = T16<T>::pack2(o8[6] * inv, o8[7] * inv);
+        *reinterpret_cast<uint4*>(out + (long long)b * dm + h * 64 + sub * 8) = pk;
+    }
 }
 
 wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
