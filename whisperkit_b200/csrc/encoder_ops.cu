@@ -2,6 +2,8 @@
 // layout conversion for host readback, weight initialisation.
 // Reference counterpart: the inside of AudioEncoder.mlmodelc (Sources/WhisperKit/Core/AudioEncoder.swift:50-63).
 #include <curand_kernel.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -273,6 +275,9 @@ encoder_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tle
 }
 
 wk_status encoder_attention(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream) {
+    static int legacy = -1;
+    if (legacy < 0) { const char* e = getenv("WKB200_ATTN"); legacy = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
+    if (!legacy) return encoder_attention_tcgen05(qkv, out, B, T, n_heads, dtype, stream);
     const int dm = n_heads * 64;
     dim3 grid((T + kAttnBM - 1) / kAttnBM, B * n_heads);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
