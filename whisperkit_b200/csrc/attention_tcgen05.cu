@@ -37,6 +37,12 @@ struct FaParams {
     uint32_t v_lbo, v_sbo, v_kstep;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2: 2^x, ex2(-inf) = +0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -187,15 +193,16 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             const int sb = i & 1;
             mbar_wait(&o_full[sb], (i >> 1) & 1);
             tc_fence_after();
-            const float corr = exp2f((m_acc - m_i) * c);   // m_acc = -inf on first use -> 0
+            const float corr = ex2_approx((m_acc - m_i) * c);   // m_acc = -inf on first use -> 0
             m_acc = m_i;
+            uint32_t r[2][32];
+            tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64, r[0]);
+            tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + 32, r[1]);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + half * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int t = 0; t < 32; ++t) o[half * 32 + t] = o[half * 32 + t] * corr + __uint_as_float(r[t]);
+            for (int t = 0; t < 32; ++t) {
+                o[t] = fmaf(o[t], corr, __uint_as_float(r[0][t]));
+                o[32 + t] = fmaf(o[32 + t], corr, __uint_as_float(r[1][t]));
             }
             tc_fence_before();
             __syncwarp();
@@ -207,37 +214,49 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             const uint32_t ph = (j >> 1) & 1;
             mbar_wait(&s_full[sb], ph);
             tc_fence_after();
-            const int valid = min(kFaBN, p.T - j * kFaBN);   // keys of this tile that exist
-            // pass 1: row max
-            float mx = m_run;
+            // whole S row (128 scores) into registers with all four TMEM loads in flight, then free the S buffer at once
+            uint32_t sr[4][32];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem + lane_addr + sb * 128 + ch * 32, r);
-                tmem_ld_wait();
+            for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem + lane_addr + sb * 128 + ch * 32, sr[ch]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[sb]);
+            const int valid = p.T - j * kFaBN;   // >= 128 except on the last tile
+            if (valid < kFaBN) {
 #pragma unroll
-                for (int t = 0; t < 32; ++t)
-                    if (ch * 32 + t < valid) mx = fmaxf(mx, __uint_as_float(r[t]));
+                for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                    for (int t = 0; t < 32; ++t)
+                        if (ch * 32 + t >= valid) sr[ch][t] = 0xff800000u;   // -inf: key does not exist
             }
-            const float l_corr = exp2f((m_run - mx) * c);
+            float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                mx0 = fmaxf(mx0, __uint_as_float(sr[0][t]));
+                mx1 = fmaxf(mx1, __uint_as_float(sr[1][t]));
+                mx2 = fmaxf(mx2, __uint_as_float(sr[2][t]));
+                mx3 = fmaxf(mx3, __uint_as_float(sr[3][t]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            const float l_corr = ex2_approx((m_run - mx) * c);
             const float msc = mx * c;
             m_run = mx;
             // P buffer free?  (PV of tile j-2 has consumed it)
             mbar_wait(&p_empty[sb], ph ^ 1);
-            // pass 2: p = exp2(s*c - m*c), row sum (unrounded), 16-bit P into the swizzled A-operand layout
-            float ls = 0.f;
+            float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem + lane_addr + sb * 128 + ch * 32, r);
-                tmem_ld_wait();
                 uint32_t pk[16];
 #pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    const float p0 = (ch * 32 + t < valid) ? exp2f(__uint_as_float(r[t]) * c - msc) : 0.f;
-                    const float p1 = (ch * 32 + t + 1 < valid) ? exp2f(__uint_as_float(r[t + 1]) * c - msc) : 0.f;
-                    ls += p0 + p1;
+                for (int t = 0; t < 32; t += 4) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sr[ch][t]), c, -msc));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sr[ch][t + 1]), c, -msc));
+                    const float p2 = ex2_approx(fmaf(__uint_as_float(sr[ch][t + 2]), c, -msc));
+                    const float p3 = ex2_approx(fmaf(__uint_as_float(sr[ch][t + 3]), c, -msc));
+                    ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
                     pk[t >> 1] = T16<T>::pack2(p0, p1);
+                    pk[(t >> 1) + 1] = T16<T>::pack2(p2, p3);
                 }
                 // 32 keys = 64 bytes = four 16-byte chunks of this row; chunk index inside the 128-byte row: (ch&1)*4 + q
                 uint8_t* base = prow[sb] + (ch >> 1) * (kFaPBytes / 2);
@@ -247,12 +266,10 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
                     *reinterpret_cast<uint4*>(base + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
-            l_run = l_run * l_corr + ls;
-            // S consumed, P produced
-            tc_fence_before();
+            l_run = l_run * l_corr + ((ls0 + ls1) + (ls2 + ls3));
             fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[sb]); }
+            if (lane == 0) mbar_arrive(&p_full[sb]);
             // fold in the previous tile's PV while this tile's second MMA runs
             if (j > 0) accumulate(j - 1, m_tile_prev);
             m_tile_prev = mx;
