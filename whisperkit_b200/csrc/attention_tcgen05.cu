@@ -4,10 +4,12 @@
 //   warp 0      TMA producer: Q tile once, then K / V tiles of 128 keys through 3-deep smem rings (128B swizzle)
 //   warp 1      MMA issuer:   S_j = Q K_j^T   (tcgen05.mma 128x128x16 x4, accumulator S in TMEM, double buffered)
 //                             PV_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P_j from smem, B = V_j MN-major from smem)
-//   warps 2..5  softmax:      thread = query row.  tcgen05.ld S_j -> running max / exp2 / row sum in registers,
+//   warps 2..9  softmax:      two threads per query row (warps w and w+4 share a TMEM lane quarter): each takes 64
+//                             of the tile's 128 keys and 32 of the 64 output columns.  tcgen05.ld S_j -> max / exp2 /
+//                             row sum in registers (only the row max is exchanged, through smem, once per tile),
 //                             P_j (16-bit) -> swizzled smem for the second MMA; PV_j is read back from TMEM and
 //                             accumulated into a register-resident O with the online-softmax rescale (no TMEM
-//                             read-modify-write, no cross-thread shuffles: one thread owns one row end to end).
+//                             read-modify-write).  Two softmax warps per scheduler hide each other's latencies.
 // Q/K/V are read in place from the packed qkv activation [B*T, 3*d_model] through one 3-D tensor map (per-window
 // out-of-bounds rows are zero-filled by TMA; keys >= T are masked to -inf before the softmax).
 // Reference counterpart: inside AudioEncoder.mlmodelc (Sources/WhisperKit/Core/AudioEncoder.swift:59-62).
@@ -19,14 +21,14 @@
 
 namespace wk {
 
-static constexpr int kFaThreads = 192;
+static constexpr int kFaThreads = 320;      // TMA warp + MMA warp + 8 softmax warps
 static constexpr int kFaBM = 128;          // queries per CTA
 static constexpr int kFaBN = 128;          // keys per tile
 static constexpr int kFaD = 64;
 static constexpr int kFaTile = kFaBN * kFaD * 2;   // 16 KiB: one K or V or Q tile, 128-byte rows
 static constexpr int kFaStages = 3;
 static constexpr int kFaPBytes = kFaBM * kFaBN * 2;  // 32 KiB: P tile = two 64-key chunks of 16 KiB
-static constexpr int kFaSmem = kFaTile /*Q*/ + 2 * kFaStages * kFaTile /*K,V rings*/ + 2 * kFaPBytes + 1024 /*align*/ + 512 /*barriers*/;
+static constexpr int kFaSmem = kFaTile /*Q*/ + 2 * kFaStages * kFaTile /*K,V rings*/ + 2 * kFaPBytes + 1024 /*align*/ + 512 /*barriers*/ + 4096 /*row-max / row-sum exchange*/;
 static constexpr int kFaTmemCols = 512;    // S0 @0, S1 @128, O0 @256, O1 @320
 
 struct FaParams {
@@ -75,6 +77,7 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
     uint64_t* o_full = p_empty + 2;               // 2
     uint64_t* o_empty = o_full + 2;               // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+    float* xch = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parity][2 halves][128 rows] row-max exchange (+ final sums)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, bh = blockIdx.y;
@@ -90,9 +93,9 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-            mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+            mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
         }
         fence_barrier_init();
     }
@@ -173,37 +176,32 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
         }
     } else {
         // ============================ softmax / accumulate / epilogue ============================
-        const int quarter = warp & 3;
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;             // 0: keys 0..63 / out cols 0..31, 1: keys 64..127 / out cols 32..63
         const int row = quarter * 32 + lane;          // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        float o[kFaD];
+        const uint32_t pair_bar = 1 + quarter;        // named barrier shared by the two warps of this lane quarter
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < kFaD; ++i) o[i] = 0.f;
-        float m_run = -INFINITY;      // running max of raw scores
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        float m_run = -INFINITY;      // running max of raw scores (identical in both threads of a row)
         float m_acc = -INFINITY;      // max the register accumulator o[] is currently scaled to
-        float l_run = 0.f;
+        float l_run = 0.f;            // this thread's share of the row sum
         float m_tile_prev = -INFINITY;
         const float c = p.scale_log2e;
-        uint8_t* prow[2];
-        prow[0] = sP + row * 128;
-        prow[1] = sP + kFaPBytes + row * 128;
         const int sw = row & 7;
 
-        auto accumulate = [&](int i, float m_i) {   // o += PV_i, PV_i is relative to max m_i
+        auto accumulate = [&](int i, float m_i) {   // o += PV_i[:, half*32 .. +32], PV_i is relative to max m_i
             const int sb = i & 1;
             mbar_wait(&o_full[sb], (i >> 1) & 1);
             tc_fence_after();
             const float corr = ex2_approx((m_acc - m_i) * c);   // m_acc = -inf on first use -> 0
             m_acc = m_i;
-            uint32_t r[2][32];
-            tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64, r[0]);
-            tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + 32, r[1]);
+            uint32_t r[32];
+            tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + half * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                o[t] = fmaf(o[t], corr, __uint_as_float(r[0][t]));
-                o[32 + t] = fmaf(o[32 + t], corr, __uint_as_float(r[1][t]));
-            }
+            for (int t = 0; t < 32; ++t) o[t] = fmaf(o[t], corr, __uint_as_float(r[t]));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[sb]);
@@ -214,39 +212,42 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             const uint32_t ph = (j >> 1) & 1;
             mbar_wait(&s_full[sb], ph);
             tc_fence_after();
-            // whole S row (128 scores) into registers with all four TMEM loads in flight, then free the S buffer at once
-            uint32_t sr[4][32];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem + lane_addr + sb * 128 + ch * 32, sr[ch]);
+            // this thread's 64 scores into registers (both TMEM loads in flight), then release the S buffer
+            uint32_t sr[2][32];
+            tmem_ld_32x32(tmem + lane_addr + sb * 128 + half * 64, sr[0]);
+            tmem_ld_32x32(tmem + lane_addr + sb * 128 + half * 64 + 32, sr[1]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[sb]);
-            const int valid = p.T - j * kFaBN;   // >= 128 except on the last tile
-            if (valid < kFaBN) {
+            const int valid = p.T - j * kFaBN - half * 64;   // keys of this thread's half that exist (>= 64 except at the end)
+            if (valid < 64) {
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
+                for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
                     for (int t = 0; t < 32; ++t)
                         if (ch * 32 + t >= valid) sr[ch][t] = 0xff800000u;   // -inf: key does not exist
             }
-            float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 mx0 = fmaxf(mx0, __uint_as_float(sr[0][t]));
                 mx1 = fmaxf(mx1, __uint_as_float(sr[1][t]));
-                mx2 = fmaxf(mx2, __uint_as_float(sr[2][t]));
-                mx3 = fmaxf(mx3, __uint_as_float(sr[3][t]));
             }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            // exchange the half-row max with the partner thread (same row, other 64 keys)
+            float* slot = xch + (j & 1) * 256;
+            slot[half * 128 + row] = fmaxf(mx0, mx1);
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const float mx = fmaxf(m_run, fmaxf(slot[row], slot[128 + row]));
             const float l_corr = ex2_approx((m_run - mx) * c);
             const float msc = mx * c;
             m_run = mx;
             // P buffer free?  (PV of tile j-2 has consumed it)
             mbar_wait(&p_empty[sb], ph ^ 1);
             float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+            uint8_t* prow = sP + sb * kFaPBytes + half * (kFaPBytes / 2) + row * 128;   // this half = one 64-key chunk block
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {
@@ -258,12 +259,10 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
                     pk[t >> 1] = T16<T>::pack2(p0, p1);
                     pk[(t >> 1) + 1] = T16<T>::pack2(p2, p3);
                 }
-                // 32 keys = 64 bytes = four 16-byte chunks of this row; chunk index inside the 128-byte row: (ch&1)*4 + q
-                uint8_t* base = prow[sb] + (ch >> 1) * (kFaPBytes / 2);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int chunk = (ch & 1) * 4 + q;
-                    *reinterpret_cast<uint4*>(base + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const int chunk = ch * 4 + q;   // 16-byte chunk inside the 128-byte row
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
             l_run = l_run * l_corr + ((ls0 + ls1) + (ls2 + ls3));
@@ -275,13 +274,16 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             m_tile_prev = mx;
         }
         accumulate(n - 1, m_tile_prev);
-        // ---- epilogue: normalise and store this row (64 values = 128 contiguous bytes)
+        // ---- epilogue: total row sum = both halves; normalise and store this thread's 32 columns (64 contiguous bytes)
+        float* fin = xch + 512;   // [2][128]
+        fin[half * 128 + row] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         const int q = q0 + row;
         if (q < p.T) {
-            const float inv = 1.f / l_run;
-            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kFaD);
+            const float inv = 1.f / (fin[row] + fin[128 + row]);
+            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kFaD + half * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 uint4 v;
                 v.x = T16<T>::pack2(o[8 * i] * inv, o[8 * i + 1] * inv);
                 v.y = T16<T>::pack2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
