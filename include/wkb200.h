@@ -135,6 +135,8 @@ wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model**
 /* HuggingFace parameter names ("model.encoder.layers.0.self_attn.q_proj.weight", ...); data host or device. */
 wk_status wk_model_set_tensor(wk_model* m, const char* name, const void* data, int32_t dtype, const int64_t* shape, int32_t ndim);
 wk_status wk_model_finalize(wk_model* m);
+/* HuggingFace checkpoint directory (config.json + *.safetensors, F32/F16/BF16); replaces loadModels (WhisperKit.swift:358-442). */
+wk_status wk_model_load(const char* weights_dir, int32_t device, int32_t max_batch, int32_t dtype, wk_model** out);
 /* Seeded synthetic weights generated on the device (benchmarks: no checkpoints are available offline). */
 wk_status wk_model_init_random(wk_model* m, uint64_t seed, float std);
 wk_status wk_model_info_get(const wk_model* m, wk_model_info* out);

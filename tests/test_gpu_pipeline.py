@@ -186,3 +186,39 @@ def test_whisperkit_transcribe_batch_and_chunking():
     with pytest.raises(wk.WhisperError) as ei:
         kit.textDecoder.decodeText(None, [99999], o, kit.specialTokens)
     assert ei.value.case == "prepareDecoderInputsFailed"
+
+
+def test_model_load_from_safetensors_checkpoint(tmp_path):
+    """wk_model_load: HuggingFace-style directory (config.json + model.safetensors) == the set_tensor path, bit for bit."""
+    import json
+    from safetensors.torch import save_file
+    dims = M.VARIANTS["toy"]
+    w = M.random_weights(dims, seed=21, policy="bf16")
+    sd = {k: v.contiguous() for k, v in M.to_hf_state_dict(w).items()}
+    sd["proj_out.weight"] = sd["proj_out.weight"].clone()
+    half = sorted(sd)[: len(sd) // 2]
+    save_file({k: sd[k] for k in half}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k: (sd[k].to(torch.bfloat16) if k.endswith("fc1.weight") else sd[k]) for k in sd if k not in half},
+              str(tmp_path / "model-00002-of-00002.safetensors"))
+    cfg = dict(num_mel_bins=dims.n_mels, d_model=dims.d_model, encoder_attention_heads=dims.n_heads, encoder_layers=dims.enc_layers,
+               decoder_layers=dims.dec_layers, vocab_size=dims.vocab, max_source_positions=1500, max_target_positions=448)
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    m1 = wk.Model.from_pretrained(str(tmp_path), max_batch=2, dtype="bf16")
+    m2 = wk.Model("toy", max_batch=2, dtype="bf16")
+    m2.load_state_dict(w)
+    assert m1.info.d_model == dims.d_model and m1.info.vocab == dims.vocab
+    pcm = np.stack([mel_ref.synthetic_pcm(1), mel_ref.synthetic_pcm(2)])
+    outs = []
+    for m in (m1, m2):
+        fe, enc, dec = wk.FeatureExtractor(m), wk.AudioEncoder(m), wk.TextDecoder(m, 2)
+        e = enc.encodeFeatures(fe.logMelSpectrogram(pcm))
+        dec.bindEncoderOutput(e)
+        outs.append((e.numpy(), dec.predictLogits([5, 6], [0, 0])))
+        dec.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    with pytest.raises(wk.WhisperError) as ei:
+        wk.Model.from_pretrained(str(tmp_path / "missing"))
+    assert ei.value.case == "modelsUnavailable"
+    m1.close()
+    m2.close()

@@ -84,6 +84,7 @@ SYMBOLS = [
     ("wk_model_create", I32, [C.POINTER(wk_model_config), I32, C.POINTER(P)]),
     ("wk_model_set_tensor", I32, [P, C.c_char_p, P, I32, PI64, I32]),
     ("wk_model_finalize", I32, [P]),
+    ("wk_model_load", I32, [C.c_char_p, I32, I32, I32, C.POINTER(P)]),
     ("wk_model_init_random", I32, [P, C.c_uint64, F32]),
     ("wk_model_info_get", I32, [P, C.POINTER(wk_model_info)]),
     ("wk_model_free", None, [P]),

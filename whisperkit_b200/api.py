@@ -15,6 +15,7 @@ All arithmetic happens in libwkb200.so (sm_100a kernels); this module only marsh
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -175,6 +176,21 @@ class Model:
         check(self.lib.wk_model_create(C.byref(cfg), device, C.byref(self.handle)))
         self.variant = variant
         self.device = device
+
+    @classmethod
+    def from_pretrained(cls, weights_dir: str, device: int = 0, max_batch: int = 16, dtype: str = "bf16") -> "Model":
+        """HuggingFace checkpoint directory (config.json + *.safetensors)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        check(self.lib.wk_model_load(weights_dir.encode(), device, max_batch, _DT[dtype], C.byref(self.handle)))
+        info = wk_model_info()
+        check(self.lib.wk_model_info_get(self.handle, C.byref(info)))
+        cfg = wk_model_config()
+        for f in ("n_mels", "d_model", "n_heads", "enc_layers", "dec_layers", "vocab", "n_audio_ctx", "dtype", "max_batch"):
+            setattr(cfg, f, getattr(info, f))
+        self.cfg, self.variant, self.device = cfg, os.path.basename(weights_dir.rstrip("/")), device
+        return self
 
     def set_tensor(self, name: str, t) -> None:
         if hasattr(t, "data_ptr"):

@@ -8,7 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <dirent.h>
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <string>
@@ -571,6 +573,156 @@ wk_status wk_model_set_tensor(wk_model* m, const char* name, const void* data, i
     }
     cudaFree(tmp);
     return st;
+}
+
+// ---------------------------------------------------------------------------------------------- safetensors loader
+// HuggingFace checkpoint directory: config.json + *.safetensors (8-byte LE header length, JSON header, raw tensors).
+// The reference loads CoreML bundles instead (WhisperKit.swift:358-442); on B200 weights come from safetensors.
+namespace {
+struct JsonScan {
+    const char* p; const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r' || *p == ',')) ++p; }
+    bool str(std::string* out) {
+        ws();
+        if (p >= end || *p != '"') return false;
+        ++p; out->clear();
+        while (p < end && *p != '"') { if (*p == '\\' && p + 1 < end) ++p; out->push_back(*p++); }
+        if (p < end) ++p;
+        return true;
+    }
+    void skip_value() {   // skips any JSON value
+        ws();
+        if (p >= end) return;
+        if (*p == '"') { std::string t; str(&t); return; }
+        if (*p == '{' || *p == '[') {
+            const char open = *p, close = open == '{' ? '}' : ']';
+            int depth = 0;
+            while (p < end) {
+                if (*p == '"') { std::string t; str(&t); continue; }
+                if (*p == open) ++depth;
+                else if (*p == close) { if (--depth == 0) { ++p; return; } }
+                ++p;
+            }
+            return;
+        }
+        while (p < end && *p != ',' && *p != '}' && *p != ']') ++p;
+    }
+};
+static bool json_int(const std::string& js, const char* key, long long* out) {
+    const std::string k = std::string("\"") + key + "\"";
+    size_t pos = js.find(k);
+    if (pos == std::string::npos) return false;
+    pos = js.find(':', pos + k.size());
+    if (pos == std::string::npos) return false;
+    *out = atoll(js.c_str() + pos + 1);
+    return true;
+}
+static bool read_file(const std::string& path, std::vector<char>* buf) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf->resize((size_t)n);
+    const size_t got = fread(buf->data(), 1, (size_t)n, f);
+    fclose(f);
+    return got == (size_t)n;
+}
+}  // namespace
+
+static wk_status load_safetensors_file(wk_model* m, const std::string& path, int* n_loaded) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { set_error("cannot open %s", path.c_str()); return WK_ERR_MODELS_UNAVAILABLE; }
+    uint64_t hlen = 0;
+    if (fread(&hlen, 8, 1, f) != 1 || hlen > (1ull << 28)) { fclose(f); set_error("%s: bad safetensors header", path.c_str()); return WK_ERR_MODELS_UNAVAILABLE; }
+    std::vector<char> hdr((size_t)hlen);
+    if (fread(hdr.data(), 1, (size_t)hlen, f) != (size_t)hlen) { fclose(f); set_error("%s: truncated header", path.c_str()); return WK_ERR_MODELS_UNAVAILABLE; }
+    const long long data0 = 8 + (long long)hlen;
+    JsonScan js{hdr.data(), hdr.data() + hdr.size()};
+    js.ws();
+    if (js.p < js.end && *js.p == '{') ++js.p;
+    std::vector<char> buf;
+    std::string name;
+    while (js.str(&name)) {
+        js.ws();
+        if (js.p < js.end && *js.p == ':') ++js.p;
+        if (name == "__metadata__") { js.skip_value(); continue; }
+        const char* v0 = js.p;
+        js.skip_value();
+        const std::string obj(v0, js.p);
+        // {"dtype":"F32","shape":[a,b],"data_offsets":[s,e]}
+        size_t dp = obj.find("\"dtype\"");
+        size_t sp = obj.find("\"shape\"");
+        size_t op = obj.find("\"data_offsets\"");
+        if (dp == std::string::npos || sp == std::string::npos || op == std::string::npos) continue;
+        const size_t dq = obj.find('"', obj.find(':', dp) + 1);
+        const std::string dts = obj.substr(dq + 1, obj.find('"', dq + 1) - dq - 1);
+        int dt = -1;
+        if (dts == "F32") dt = WK_DTYPE_F32; else if (dts == "F16") dt = WK_DTYPE_F16; else if (dts == "BF16") dt = WK_DTYPE_BF16;
+        int64_t shape[8]; int nd = 0;
+        { const char* q = obj.c_str() + obj.find('[', sp) + 1;
+          while (*q && *q != ']' && nd < 8) { while (*q == ' ' || *q == ',') ++q; if (*q == ']') break; shape[nd++] = atoll(q); while (*q && *q != ',' && *q != ']') ++q; } }
+        long long off[2] = {0, 0};
+        { const char* q = obj.c_str() + obj.find('[', op) + 1; off[0] = atoll(q); while (*q && *q != ',') ++q; if (*q) off[1] = atoll(q + 1); }
+        Dest d;
+        if (dt < 0 || !resolve_name(m, name, &d)) continue;   // not a hot-path parameter (or unsupported dtype)
+        const size_t bytes = (size_t)(off[1] - off[0]);
+        buf.resize(bytes);
+        if (fseek(f, data0 + off[0], SEEK_SET) != 0 || fread(buf.data(), 1, bytes, f) != bytes) { fclose(f); set_error("%s: truncated tensor %s", path.c_str(), name.c_str()); return WK_ERR_MODELS_UNAVAILABLE; }
+        wk_status st = wk_model_set_tensor(m, name.c_str(), buf.data(), dt, shape, nd);
+        if (st != WK_OK) { fclose(f); return st; }
+        ++*n_loaded;
+    }
+    fclose(f);
+    return WK_OK;
+}
+
+wk_status wk_model_load(const char* weights_dir, int32_t device, int32_t max_batch, int32_t dtype, wk_model** out) {
+    if (!weights_dir || !out) { set_error("wk_model_load: null argument"); return WK_ERR_INVALID_ARGUMENT; }
+    const std::string dir = weights_dir;
+    std::vector<char> cfgbuf;
+    if (!read_file(dir + "/config.json", &cfgbuf)) { set_error("wk_model_load: %s/config.json not found", weights_dir); return WK_ERR_MODELS_UNAVAILABLE; }
+    const std::string cj(cfgbuf.begin(), cfgbuf.end());
+    wk_model_config c;
+    memset(&c, 0, sizeof(c));
+    long long v;
+    c.n_mels = json_int(cj, "num_mel_bins", &v) ? (int)v : 80;
+    c.d_model = json_int(cj, "d_model", &v) ? (int)v : 0;
+    c.n_heads = json_int(cj, "encoder_attention_heads", &v) ? (int)v : 0;
+    c.enc_layers = json_int(cj, "encoder_layers", &v) ? (int)v : 0;
+    c.dec_layers = json_int(cj, "decoder_layers", &v) ? (int)v : 0;
+    c.vocab = json_int(cj, "vocab_size", &v) ? (int)v : 0;
+    c.n_audio_ctx = json_int(cj, "max_source_positions", &v) ? (int)v : 1500;
+    c.n_text_ctx = json_int(cj, "max_target_positions", &v) ? (int)v : 448;
+    c.dtype = dtype ? dtype : WK_DTYPE_BF16;
+    c.max_batch = max_batch > 0 ? max_batch : 16;
+    wk_model* m = nullptr;
+    WK_CHECK(wk_model_create(&c, device, &m));
+    // every *.safetensors in the directory (single file or HF shards)
+    int n_loaded = 0;
+    std::vector<std::string> files;
+    {
+        std::string cmd_dir = dir;
+        DIR* d = opendir(dir.c_str());
+        if (d) {
+            while (dirent* e = readdir(d)) {
+                const std::string fn = e->d_name;
+                if (fn.size() > 12 && fn.substr(fn.size() - 12) == ".safetensors") files.push_back(dir + "/" + fn);
+            }
+            closedir(d);
+        }
+    }
+    std::sort(files.begin(), files.end());
+    if (files.empty()) { wk_model_free(m); set_error("wk_model_load: no *.safetensors in %s", weights_dir); return WK_ERR_MODELS_UNAVAILABLE; }
+    for (const auto& fp : files) {
+        wk_status st = load_safetensors_file(m, fp, &n_loaded);
+        if (st != WK_OK) { wk_model_free(m); return st; }
+    }
+    const int expected = 4 + 1 + 2 + c.enc_layers * 15 + 1 + 1 + 2 + c.dec_layers * 24;
+    if (n_loaded < expected) { wk_model_free(m); set_error("wk_model_load: only %d of %d expected tensors found in %s", n_loaded, expected, weights_dir); return WK_ERR_MODELS_UNAVAILABLE; }
+    WK_CHECK(wk_model_finalize(m));
+    *out = m;
+    return WK_OK;
 }
 
 wk_status wk_model_finalize(wk_model* m) {
