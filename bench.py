@@ -400,7 +400,11 @@ def run_own_arm(args):
         kernels = {}
         L, Ld = info.enc_layers, info.dec_layers
         nsteps = max(steps_run)
-        per_step = {0: Ld * nsteps, 1: L, 2: 1, 3: L, 4: Ld * nsteps, 5: L}
+        nl, lb = C.c_int32(), (C.c_int32 * 2)()
+        check(lib.wk_session_lanes(dec.handle, C.byref(nl), lb))
+        n_lanes = int(nl.value)   # lane-local kernels (decoder) launch once per lane per layer-step, on lane_batch windows
+        per_step = {0: Ld * nsteps * n_lanes, 1: L, 2: 1, 3: L, 4: Ld * nsteps * n_lanes, 5: L}
+        line["config"]["decode_lanes"] = n_lanes
         names = {0: "decoder_cross_attention_kernel", 1: "gemm_tcgen05_kernel[enc FC1 M=B*1500,N=5120,K=1280]", 2: "mel_pass1+pass2",
                  3: "encoder_attention_kernel", 4: "gemm_tcgen05_kernel[dec QKV swap-AB N=3840,K=1280,split-K]",
                  5: "gemm_tcgen05_kernel[enc QKV M=B*1500,N=3840,K=1280]"}

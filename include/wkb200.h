@@ -180,6 +180,8 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
  * results: array of `batch` wk_decode_result. */
 wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* opts,
                          const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
+/* Concurrent decode lanes of the session (2 once max_batch >= 32) and the windows bound to each. */
+wk_status wk_session_lanes(const wk_session* s, int32_t* n_lanes, int32_t* lane_batch2);
 /* Device logits of the last step, copied to host (debug / parity). */
 wk_status wk_session_last_logits(wk_session* s, float* logits_out);
 

@@ -222,3 +222,29 @@ def test_model_load_from_safetensors_checkpoint(tmp_path):
     assert ei.value.case == "modelsUnavailable"
     m1.close()
     m2.close()
+
+
+def test_two_decode_lanes_match_single_lane(monkeypatch):
+    """A session with >= 32 windows decodes on two concurrent lanes (own streams / KV caches); results must be
+    bit-identical to the single-lane schedule and keep the window order."""
+    import os
+    dims, orc, model = build("toy", "bf16", 35, seed=8)
+    st = wk.SpecialTokens.from_any(D.SpecialTokens.toy(dims.vocab))
+    fe, enc = wk.FeatureExtractor(model), wk.AudioEncoder(model)
+    pcm = np.stack([mel_ref.synthetic_pcm(40 + (i % 7)) * (1.0 + 0.01 * i) for i in range(35)]).astype(np.float32)
+    enc_t = enc.encodeFeatures(fe.logMelSpectrogram(pcm))
+    o = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=14)
+    dual = wk.TextDecoder(model, 35)
+    prompt = dual.prefillDecoderInputs(o, st)
+    r2 = dual.decodeText(enc_t, prompt, o, st)
+    lg2 = dual.lastLogits()
+    monkeypatch.setenv("WKB200_SINGLE_LANE", "1")
+    single = wk.TextDecoder(model, 35)
+    r1 = single.decodeText(enc_t, prompt, o, st)
+    lg1 = single.lastLogits()
+    assert [x.tokens for x in r1] == [x.tokens for x in r2]
+    np.testing.assert_array_equal(lg1, lg2)
+    assert len({tuple(x.tokens) for x in r2}) > 20  # windows really differ, so an order mix-up would be caught
+    dual.close()
+    single.close()
+    model.close()

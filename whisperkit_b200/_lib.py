@@ -104,6 +104,7 @@ SYMBOLS = [
     ("wk_decode_text", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), PI32, I32,
                              C.POINTER(wk_decode_result)]),
     ("wk_session_last_logits", I32, [P, P]),
+    ("wk_session_lanes", I32, [P, PI32, PI32]),
     ("wk_transcribe_windows", I32, [P, P, P, I64, I64, PI32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts),
                                     PI32, I32, C.POINTER(wk_decode_result)]),
     ("wk_kernel_launch_count", I64, [I32]),

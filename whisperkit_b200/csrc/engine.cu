@@ -123,9 +123,13 @@ struct wk_model {
     wk_tensor mel_tensor, enc_tensor;
 };
 
-struct wk_session {
+// One decode lane: a contiguous slice of the session's windows with its own stream, KV caches and decode state.
+// A session with >= 32 windows runs two lanes concurrently so that one lane's latency-bound kernels (small GEMMs,
+// split-K reduce + LayerNorm, self-attention) overlap the other lane's HBM-bound cross-attention.
+struct Lane {
     wk_model* m;
-    int max_batch, batch = 0, bp = 16;
+    cudaStream_t stream = nullptr;
+    int max_batch = 0, batch = 0, bp = 16, b0 = 0;
     void* cross_kv = nullptr;   // [2L][Bs][H][T][64]
     void* self_k = nullptr;     // [L][Bs][H][224][64]
     void* self_v = nullptr;
@@ -134,8 +138,17 @@ struct wk_session {
     float* logits = nullptr;
     DecodeState st;
     int32_t* prompt_dev = nullptr; int32_t* pos_dev = nullptr; int32_t* suppress_dev = nullptr; int32_t* lang_dev = nullptr;
-    int32_t* tok_scratch = nullptr; int32_t* ntok_scratch = nullptr; int32_t* tokout_dev = nullptr; float* lpout_dev = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    long long launches_per_step = 0;
+    int gemm_max_stages = 0;
+};
+
+struct wk_session {
+    wk_model* m;
+    int max_batch = 0, batch = 0;
+    int n_lanes = 1;
+    Lane* lane[2] = {nullptr, nullptr};
+    cudaEvent_t ev_enc = nullptr;
 };
 
 namespace wk {
@@ -367,7 +380,7 @@ static wk_status encode_chunk(wk_model* m, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------- decoder schedule
-static wk_status dec_gemm(wk_session* s, const void* w, int N, int K, const void* act, int* splits_out) {
+static wk_status dec_gemm(Lane* s, const void* w, int N, int K, const void* act, int* splits_out) {
     wk_model* m = s->m;
     GemmDesc g;
     memset(&g, 0, sizeof(g));
@@ -381,15 +394,16 @@ static wk_status dec_gemm(wk_session* s, const void* w, int N, int K, const void
     g.pdl = 1;
     if ((size_t)g.splits * s->bp * N > s->partial_elems) { set_error("partial workspace too small"); return WK_ERR_DECODING_FAILED; }
     *splits_out = g.splits;
-    return gemm_tcgen05(g, m->num_sms, m->stream);
+    g.max_stages = s->gemm_max_stages;
+    return gemm_tcgen05(g, m->num_sms, s->stream);
 }
 
 // one decoder forward for every bound sequence.  explicit_pos == nullptr: loop mode (token/position from DecodeState)
-static wk_status decoder_forward(wk_session* s, int prompt_len, int ts_begin, const int32_t* explicit_pos) {
+static wk_status decoder_forward(Lane* s, int prompt_len, int ts_begin, const int32_t* explicit_pos) {
     wk_model* m = s->m;
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, H = c.n_heads, dt = c.dtype, B = s->batch, Bp = s->bp, T = c.n_audio_ctx;
-    cudaStream_t st = m->stream;
+    cudaStream_t st = s->stream;
     const size_t self_layer = (size_t)s->max_batch * H * kKvMaxLen * 64 * 2;   // bytes per layer
     const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;          // bytes per (layer, k|v)
     int sp = 1;
@@ -424,12 +438,13 @@ static wk_status decoder_forward(wk_session* s, int prompt_len, int ts_begin, co
         g.m_rows_per_batch = c.vocab; g.n = Bp; g.k = d; g.taps = 1; g.bn = Bp; g.splits = 1;
         g.mode = GEMM_OUT_PARTIAL_T; g.out = s->logits; g.ld_out = c.vocab; g.out_rows_per_batch = c.vocab; g.partial_cols = B;
         g.pdl = 1;
+        g.max_stages = s->gemm_max_stages;
         WK_CHECK(gemm_tcgen05(g, m->num_sms, st));
     }
     return WK_OK;
 }
 
-static SamplerParams make_sampler_params(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, int is_multilingual,
+static SamplerParams make_sampler_params(Lane* s, const wk_special_tokens* st, const wk_decode_opts* o, int is_multilingual,
                                          int sample_begin_ts, int sample_begin_blank, int prompt_len) {
     SamplerParams p;
     memset(&p, 0, sizeof(p));
@@ -448,12 +463,12 @@ static SamplerParams make_sampler_params(wk_session* s, const wk_special_tokens*
 }
 
 // uploads the (< specialTokenBegin) suppress list (TextDecoder.swift:876-879); returns count
-static wk_status upload_suppress(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, int* n_out) {
+static wk_status upload_suppress(Lane* s, const wk_special_tokens* st, const wk_decode_opts* o, int* n_out) {
     std::vector<int32_t> sup;
     for (int i = 0; i < o->n_suppress_tokens; ++i)
         if (o->suppress_tokens[i] < st->special_token_begin && o->suppress_tokens[i] >= 0) sup.push_back(o->suppress_tokens[i]);
     if (sup.size() > 4096) { set_error("too many suppress tokens"); return WK_ERR_INVALID_ARGUMENT; }
-    if (!sup.empty()) WK_CUDA_CHECK(cudaMemcpyAsync(s->suppress_dev, sup.data(), sup.size() * 4, cudaMemcpyHostToDevice, s->m->stream));
+    if (!sup.empty()) WK_CUDA_CHECK(cudaMemcpyAsync(s->suppress_dev, sup.data(), sup.size() * 4, cudaMemcpyHostToDevice, s->stream));
     *n_out = (int)sup.size();
     return WK_OK;
 }
@@ -918,14 +933,13 @@ wk_status wk_encode(wk_model* m, const wk_tensor* mel, wk_tensor** enc_out) {
 }
 
 // ---------------------------------------------------------------------------------------------- session
-wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
-    if (!m || !out || max_batch < 1 || max_batch > 256) { set_error("wk_session_create: bad arguments (max_batch %d)", max_batch); return WK_ERR_INVALID_ARGUMENT; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
+static wk_status lane_create(wk_model* m, int max_batch, Lane** out) {
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, H = c.n_heads, L = c.dec_layers, T = c.n_audio_ctx;
-    wk_session* s = new wk_session();
+    Lane* s = new Lane();
     s->m = m;
     s->max_batch = max_batch;
+    WK_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     const int bpm = round_up(max_batch, 16);
     WK_CHECK(alloc16(&s->cross_kv, (size_t)2 * L * max_batch * H * T * 64));
     WK_CHECK(alloc16(&s->self_k, (size_t)L * max_batch * H * kKvMaxLen * 64));
@@ -958,10 +972,39 @@ wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
     WK_CHECK(dmalloc(&s->pos_dev, max_batch));
     WK_CHECK(dmalloc(&s->suppress_dev, 4096));
     WK_CHECK(dmalloc(&s->lang_dev, 4096));
-    WK_CHECK(dmalloc(&s->tok_scratch, (size_t)max_batch * kKvMaxLen));
-    WK_CHECK(dmalloc(&s->ntok_scratch, max_batch));
-    WK_CHECK(dmalloc(&s->tokout_dev, max_batch));
-    WK_CHECK(dmalloc(&s->lpout_dev, max_batch));
+    *out = s;
+    return WK_OK;
+}
+
+static void lane_free(Lane* s) {
+    if (!s) return;
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
+                    s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.step, s->st.n_done, s->st.input_ids,
+                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
+    if (!m || !out || max_batch < 1 || max_batch > 512) { set_error("wk_session_create: bad arguments (max_batch %d)", max_batch); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    wk_session* s = new wk_session();
+    s->m = m;
+    s->max_batch = max_batch;
+    // two concurrent lanes once the batch is large enough for a lane's cross-attention to fill the machine
+    s->n_lanes = (max_batch >= 32 && !getenv("WKB200_SINGLE_LANE")) ? 2 : 1;
+    if (max_batch > 256 && s->n_lanes == 1) { set_error("wk_session_create: max_batch %d > 256 needs two lanes", max_batch); return WK_ERR_INVALID_ARGUMENT; }
+    const int cap0 = s->n_lanes == 2 ? (max_batch + 1) / 2 : max_batch;
+    WK_CHECK(lane_create(m, cap0, &s->lane[0]));
+    if (s->n_lanes == 2) {
+        WK_CHECK(lane_create(m, max_batch - cap0 > 0 ? max_batch - cap0 : 1, &s->lane[1]));
+        // leave shared memory for the other lane's kernels on the same SM
+        s->lane[0]->gemm_max_stages = 3;
+        s->lane[1]->gemm_max_stages = 3;
+    }
+    WK_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_enc, cudaEventDisableTiming));
     WK_CUDA_CHECK(cudaDeviceSynchronize());  // setup memsets ran on the legacy default stream
     *out = s;
     return WK_OK;
@@ -971,11 +1014,9 @@ void wk_session_free(wk_session* s) {
     if (!s) return;
     cudaSetDevice(s->m->device);
     cudaDeviceSynchronize();
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-    void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
-                    s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.step, s->st.n_done, s->st.input_ids,
-                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev, s->tok_scratch, s->ntok_scratch, s->tokout_dev, s->lpout_dev};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    lane_free(s->lane[0]);
+    lane_free(s->lane[1]);
+    if (s->ev_enc) cudaEventDestroy(s->ev_enc);
     delete s;
 }
 
@@ -983,9 +1024,12 @@ wk_status wk_session_reset(wk_session* s) {
     if (!s) return WK_ERR_INVALID_ARGUMENT;
     WK_CUDA_CHECK(cudaSetDevice(s->m->device));
     const wk_model_config& c = s->m->cfg;
-    const size_t n = (size_t)c.dec_layers * s->max_batch * c.n_heads * kKvMaxLen * 64 * 2;
-    WK_CUDA_CHECK(cudaMemsetAsync(s->self_k, 0, n, s->m->stream));
-    WK_CUDA_CHECK(cudaMemsetAsync(s->self_v, 0, n, s->m->stream));
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        const size_t n = (size_t)c.dec_layers * ln->max_batch * c.n_heads * kKvMaxLen * 64 * 2;
+        WK_CUDA_CHECK(cudaMemsetAsync(ln->self_k, 0, n, ln->stream));
+        WK_CUDA_CHECK(cudaMemsetAsync(ln->self_v, 0, n, ln->stream));
+    }
     return WK_OK;
 }
 
@@ -998,11 +1042,22 @@ wk_status wk_session_set_encoder_output(wk_session* s, const wk_tensor* enc) {
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, T = c.n_audio_ctx;
     s->batch = (int)enc->batch;
-    s->bp = round_up(s->batch, 16);
-    const int64_t M = enc->batch * T;
-    GemmDesc g = plain_gemm(enc->data, M, d, m->wckv, 2 * c.dec_layers * d, c.dtype, GEMM_OUT_T16_HEADS, s->cross_kv, 0, m->bckv, 0);
-    g.heads_T = T; g.heads_B = s->max_batch; g.heads_H = c.n_heads; g.heads_dmodel = d;
-    WK_CHECK(gemm_tcgen05(g, m->num_sms, m->stream));
+    const int B0 = s->n_lanes == 2 ? (s->batch + 1) / 2 : s->batch;
+    // the encoder ran on the model stream; lanes consume its output on their own streams
+    WK_CUDA_CHECK(cudaEventRecord(s->ev_enc, m->stream));
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        ln->b0 = li == 0 ? 0 : B0;
+        ln->batch = li == 0 ? B0 : s->batch - B0;
+        ln->bp = round_up(ln->batch > 0 ? ln->batch : 1, 16);
+        if (ln->batch == 0) continue;
+        WK_CUDA_CHECK(cudaStreamWaitEvent(ln->stream, s->ev_enc, 0));
+        const int64_t M = (int64_t)ln->batch * T;
+        const char* a = (const char*)enc->data + (size_t)ln->b0 * T * d * 2;
+        GemmDesc g = plain_gemm(a, M, d, m->wckv, 2 * c.dec_layers * d, c.dtype, GEMM_OUT_T16_HEADS, ln->cross_kv, 0, m->bckv, 0);
+        g.heads_T = T; g.heads_B = ln->max_batch; g.heads_H = c.n_heads; g.heads_dmodel = d;
+        WK_CHECK(gemm_tcgen05(g, m->num_sms, ln->stream));
+    }
     return WK_OK;
 }
 
@@ -1050,20 +1105,42 @@ wk_status wk_decode_step(wk_session* s, const int32_t* input_ids, const int32_t*
         if (cache_length[i] < 0 || cache_length[i] >= kKvMaxLen) { set_error("wk_decode_step: cache_length[%d]=%d out of range", i, cache_length[i]); return WK_ERR_DECODING_LOGITS_FAILED; }
         if (input_ids[i] < 0 || input_ids[i] >= m->cfg.vocab) { set_error("wk_decode_step: input_ids[%d]=%d out of range", i, input_ids[i]); return WK_ERR_DECODING_LOGITS_FAILED; }
     }
-    WK_CUDA_CHECK(cudaMemcpyAsync(s->st.input_ids, input_ids, s->batch * 4, cudaMemcpyHostToDevice, m->stream));
-    WK_CUDA_CHECK(cudaMemcpyAsync(s->pos_dev, cache_length, s->batch * 4, cudaMemcpyHostToDevice, m->stream));
-    WK_CHECK(decoder_forward(s, 0, 0, s->pos_dev));
-    if (logits_out) WK_CUDA_CHECK(cudaMemcpyAsync(logits_out, s->logits, (size_t)s->batch * m->cfg.vocab * 4, cudaMemcpyDeviceToHost, m->stream));
-    cudaError_t e = cudaStreamSynchronize(m->stream);
-    if (e != cudaSuccess) { set_error("wk_decode_step: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_LOGITS_FAILED; }
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        if (ln->batch == 0) continue;
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.input_ids, input_ids + ln->b0, ln->batch * 4, cudaMemcpyHostToDevice, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->pos_dev, cache_length + ln->b0, ln->batch * 4, cudaMemcpyHostToDevice, ln->stream));
+        WK_CHECK(decoder_forward(ln, 0, 0, ln->pos_dev));
+        if (logits_out)
+            WK_CUDA_CHECK(cudaMemcpyAsync(logits_out + (size_t)ln->b0 * m->cfg.vocab, ln->logits, (size_t)ln->batch * m->cfg.vocab * 4,
+                                          cudaMemcpyDeviceToHost, ln->stream));
+    }
+    for (int li = 0; li < s->n_lanes; ++li) {
+        if (s->lane[li]->batch == 0) continue;
+        cudaError_t e = cudaStreamSynchronize(s->lane[li]->stream);
+        if (e != cudaSuccess) { set_error("wk_decode_step: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_LOGITS_FAILED; }
+    }
     return WK_OK;
 }
 
 wk_status wk_session_last_logits(wk_session* s, float* logits_out) {
     if (!s || !logits_out) return WK_ERR_INVALID_ARGUMENT;
     WK_CUDA_CHECK(cudaSetDevice(s->m->device));
-    WK_CUDA_CHECK(cudaMemcpyAsync(logits_out, s->logits, (size_t)s->batch * s->m->cfg.vocab * 4, cudaMemcpyDeviceToHost, s->m->stream));
-    WK_CUDA_CHECK(cudaStreamSynchronize(s->m->stream));
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        if (ln->batch == 0) continue;
+        WK_CUDA_CHECK(cudaMemcpyAsync(logits_out + (size_t)ln->b0 * s->m->cfg.vocab, ln->logits, (size_t)ln->batch * s->m->cfg.vocab * 4,
+                                      cudaMemcpyDeviceToHost, ln->stream));
+        WK_CUDA_CHECK(cudaStreamSynchronize(ln->stream));
+    }
+    return WK_OK;
+}
+
+// Number of concurrent decode lanes and the windows currently bound to each (bench / tests).
+wk_status wk_session_lanes(const wk_session* s, int32_t* n_lanes, int32_t* lane_batch2) {
+    if (!s || !n_lanes) return WK_ERR_INVALID_ARGUMENT;
+    *n_lanes = s->n_lanes;
+    if (lane_batch2) { lane_batch2[0] = s->lane[0]->batch; lane_batch2[1] = s->n_lanes == 2 ? s->lane[1]->batch : 0; }
     return WK_OK;
 }
 
@@ -1120,6 +1197,42 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
     return r;
 }
 
+// finalisation of one window on the host: finalize + slicing + averages (TextDecoder.swift:776-853)
+static void finalize_result(wk_decode_result& r, const int32_t* tokens, const float* lps, int n_tok, int steps, int first_low,
+                            const wk_special_tokens* st, const wk_decode_opts* o) {
+    memset(&r, 0, sizeof(r));
+    std::vector<int32_t> seg(tokens, tokens + n_tok);
+    std::vector<float> slp(lps, lps + n_tok);
+    r.n_current_tokens = n_tok;
+    r.steps = steps;
+    r.first_token_logprob_too_low = first_low;
+    if (seg.empty() || seg.back() != st->end_token) { seg.push_back(st->end_token); slp.push_back(0.f); }  // sampler.finalize
+    size_t start = 0, end = seg.size();
+    for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->start_of_transcript_token) { start = i; break; }
+    for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->end_token) { end = i; break; }
+    if (end >= seg.size()) end = seg.size() - 1;
+    if (end < start) start = 0;
+    float sum = 0.f;
+    std::vector<int32_t> words;
+    r.n_tokens = 0;
+    for (size_t i = start; i <= end && r.n_tokens < 226; ++i) {
+        r.tokens[r.n_tokens] = seg[i];
+        r.token_logprobs[r.n_tokens] = slp[i];
+        sum += slp[i];
+        if (seg[i] < st->special_token_begin) words.push_back(seg[i]);
+        ++r.n_tokens;
+    }
+    r.avg_logprob = sum / (float)r.n_tokens;
+    r.compression_ratio = compression_ratio(words);
+    r.temperature = roundf(o->temperature * 1000.f) / 1000.f;
+    // DecodingFallback (Models.swift:357-381); noSpeechProb is always 0 in the reference (TextDecoder.swift:802)
+    r.needs_fallback = 0; r.fallback_reason = 0;
+    if (first_low) { r.needs_fallback = 1; r.fallback_reason = 1; }
+    else if (o->has_no_speech_threshold && 0.f > o->no_speech_threshold) { r.needs_fallback = 0; r.fallback_reason = 2; }
+    else if (o->has_compression_ratio_threshold && r.compression_ratio > o->compression_ratio_threshold) { r.needs_fallback = 1; r.fallback_reason = 3; }
+    else if (o->has_logprob_threshold && r.avg_logprob < o->logprob_threshold) { r.needs_fallback = 1; r.fallback_reason = 4; }
+}
+
 wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, const int32_t* prompt, int32_t n_prompt,
                          wk_decode_result* results) {
     if (!s || !st || !o || !prompt || !results) { set_error("wk_decode_text: null argument"); return WK_ERR_INVALID_ARGUMENT; }
@@ -1129,104 +1242,92 @@ wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_de
     for (int i = 0; i < n_prompt; ++i)
         if (prompt[i] < 0 || prompt[i] >= m->cfg.vocab) { set_error("wk_decode_text: prompt token %d out of range", prompt[i]); return WK_ERR_PREPARE_DECODER_INPUTS; }
     WK_CUDA_CHECK(cudaSetDevice(m->device));
-    cudaStream_t stream = m->stream;
-    const int B = s->batch;
     const bool multilingual = m->cfg.vocab != 51864;
-    WK_CUDA_CHECK(cudaMemcpyAsync(s->prompt_dev, prompt, n_prompt * 4, cudaMemcpyHostToDevice, stream));
-    WK_CHECK(decode_state_init(s->st, s->prompt_dev, n_prompt, B, stream));
-    // createLogitsFilters (TextDecoder.swift:857-899): SuppressBlank(sampleBegin = prefilledIndex = 0),
-    // SuppressTokens(< specialTokenBegin), TimestampRules(sampleBegin = initialPrompt.count)
-    SamplerParams sp = make_sampler_params(s, st, o, multilingual ? 1 : 0, o->without_timestamps ? -1 : n_prompt,
-                                           o->suppress_blank ? 0 : -1, n_prompt);
-    WK_CHECK(upload_suppress(s, st, o, &sp.n_suppress));
     const int loop_count = std::min(o->sample_length, kKvMaxLen - 1);  // TextDecoder.swift:566
     const bool use_graph = getenv("WKB200_NO_GRAPH") == nullptr;
-    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-    auto one_step = [&]() -> wk_status {
-        WK_CHECK(decoder_forward(s, n_prompt, st->time_token_begin, nullptr));
-        return sampler_filter_sample(s->logits, m->cfg.vocab, sp, s->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, B, stream);
+    // createLogitsFilters (TextDecoder.swift:857-899): SuppressBlank(sampleBegin = prefilledIndex = 0),
+    // SuppressTokens(< specialTokenBegin), TimestampRules(sampleBegin = initialPrompt.count)
+    SamplerParams sp[2];
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        if (ln->batch == 0) continue;
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->prompt_dev, prompt, n_prompt * 4, cudaMemcpyHostToDevice, ln->stream));
+        WK_CHECK(decode_state_init(ln->st, ln->prompt_dev, n_prompt, ln->batch, ln->stream));
+        sp[li] = make_sampler_params(ln, st, o, multilingual ? 1 : 0, o->without_timestamps ? -1 : n_prompt, o->suppress_blank ? 0 : -1, n_prompt);
+        WK_CHECK(upload_suppress(ln, st, o, &sp[li].n_suppress));
+        if (ln->graph_exec) { cudaGraphExecDestroy(ln->graph_exec); ln->graph_exec = nullptr; }
+        ln->launches_per_step = 0;
+    }
+    auto one_step = [&](int li) -> wk_status {
+        Lane* ln = s->lane[li];
+        WK_CHECK(decoder_forward(ln, n_prompt, st->time_token_begin, nullptr));
+        return sampler_filter_sample(ln->logits, m->cfg.vocab, sp[li], ln->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, ln->batch, ln->stream);
     };
-    int32_t n_done = 0;
-    long long launches_per_step = 0;
     for (int step = 0; step < loop_count; ++step) {
-        if (step == 0 || !use_graph) {
-            WK_CHECK(one_step());
-        } else {
-            if (!s->graph_exec) {
+        bool redo = false;
+        for (int li = 0; li < s->n_lanes && !redo; ++li) {
+            Lane* ln = s->lane[li];
+            if (ln->batch == 0) continue;
+            if (step == 0 || !use_graph) {
+                WK_CHECK(one_step(li));
+                continue;
+            }
+            if (!ln->graph_exec) {
                 cudaGraph_t graph = nullptr;
                 const long long before = g_launches.load();
-                WK_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                wk_status r = one_step();
-                cudaError_t e = cudaStreamEndCapture(stream, &graph);
-                launches_per_step = g_launches.load() - before;
-                g_launches.fetch_sub(launches_per_step);  // captured, not executed
+                WK_CUDA_CHECK(cudaStreamBeginCapture(ln->stream, cudaStreamCaptureModeThreadLocal));
+                wk_status r = one_step(li);
+                cudaError_t e = cudaStreamEndCapture(ln->stream, &graph);
+                ln->launches_per_step = g_launches.load() - before;
+                g_launches.fetch_sub(ln->launches_per_step);  // captured, not executed
                 if (r != WK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
                 if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-                e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+                e = cudaGraphInstantiate(&ln->graph_exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess && pdl_enabled()) {
                     // programmatic edges rejected by this driver: fall back to plain serialisation and re-capture
                     cudaGetLastError();
                     pdl_disable();
-                    s->graph_exec = nullptr;
-                    --step;
-                    continue;
+                    ln->graph_exec = nullptr;
+                    redo = true;
+                    break;
                 }
                 if (e != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             }
-            WK_CUDA_CHECK(cudaGraphLaunch(s->graph_exec, stream));
-            count_launch((int)launches_per_step);
+            WK_CUDA_CHECK(cudaGraphLaunch(ln->graph_exec, ln->stream));
+            count_launch((int)ln->launches_per_step);
         }
+        if (redo) { --step; continue; }
         if ((step & 15) == 15) {  // early exit when every window has completed
-            WK_CUDA_CHECK(cudaMemcpyAsync(&n_done, s->st.n_done, 4, cudaMemcpyDeviceToHost, stream));
-            WK_CUDA_CHECK(cudaStreamSynchronize(stream));
-            if (n_done >= B) break;
+            int done = 0, total = 0;
+            for (int li = 0; li < s->n_lanes; ++li) {
+                Lane* ln = s->lane[li];
+                if (ln->batch == 0) continue;
+                int32_t nd = 0;
+                WK_CUDA_CHECK(cudaMemcpyAsync(&nd, ln->st.n_done, 4, cudaMemcpyDeviceToHost, ln->stream));
+                WK_CUDA_CHECK(cudaStreamSynchronize(ln->stream));
+                done += nd; total += ln->batch;
+            }
+            if (done >= total) break;
         }
     }
-    // ---- read back and finalise on the host (finalize + slicing + averages: TextDecoder.swift:776-853)
-    std::vector<int32_t> tokens((size_t)B * kKvMaxLen), n_tok(B), done(B), first_low(B), steps(B);
-    std::vector<float> lps((size_t)B * kKvMaxLen);
-    WK_CUDA_CHECK(cudaMemcpyAsync(tokens.data(), s->st.tokens, tokens.size() * 4, cudaMemcpyDeviceToHost, stream));
-    WK_CUDA_CHECK(cudaMemcpyAsync(lps.data(), s->st.logprobs, lps.size() * 4, cudaMemcpyDeviceToHost, stream));
-    WK_CUDA_CHECK(cudaMemcpyAsync(n_tok.data(), s->st.n_tokens, B * 4, cudaMemcpyDeviceToHost, stream));
-    WK_CUDA_CHECK(cudaMemcpyAsync(done.data(), s->st.done, B * 4, cudaMemcpyDeviceToHost, stream));
-    WK_CUDA_CHECK(cudaMemcpyAsync(first_low.data(), s->st.first_low, B * 4, cudaMemcpyDeviceToHost, stream));
-    WK_CUDA_CHECK(cudaMemcpyAsync(steps.data(), s->st.steps, B * 4, cudaMemcpyDeviceToHost, stream));
-    cudaError_t e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) { set_error("wk_decode_text: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
-    for (int b = 0; b < B; ++b) {
-        wk_decode_result& r = results[b];
-        memset(&r, 0, sizeof(r));
-        std::vector<int32_t> seg(tokens.begin() + (size_t)b * kKvMaxLen, tokens.begin() + (size_t)b * kKvMaxLen + n_tok[b]);
-        std::vector<float> slp(lps.begin() + (size_t)b * kKvMaxLen, lps.begin() + (size_t)b * kKvMaxLen + n_tok[b]);
-        r.n_current_tokens = n_tok[b];
-        r.steps = steps[b];
-        r.first_token_logprob_too_low = first_low[b];
-        if (seg.empty() || seg.back() != st->end_token) { seg.push_back(st->end_token); slp.push_back(0.f); }  // sampler.finalize
-        size_t start = 0, end = seg.size();
-        for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->start_of_transcript_token) { start = i; break; }
-        for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->end_token) { end = i; break; }
-        if (end >= seg.size()) end = seg.size() - 1;
-        if (end < start) start = 0;
-        float sum = 0.f;
-        std::vector<int32_t> words;
-        r.n_tokens = 0;
-        for (size_t i = start; i <= end && r.n_tokens < 226; ++i) {
-            r.tokens[r.n_tokens] = seg[i];
-            r.token_logprobs[r.n_tokens] = slp[i];
-            sum += slp[i];
-            if (seg[i] < st->special_token_begin) words.push_back(seg[i]);
-            ++r.n_tokens;
-        }
-        r.avg_logprob = sum / (float)r.n_tokens;
-        r.compression_ratio = compression_ratio(words);
-        r.temperature = roundf(o->temperature * 1000.f) / 1000.f;
-        // DecodingFallback (Models.swift:357-381); noSpeechProb is always 0 in the reference (TextDecoder.swift:802)
-        r.needs_fallback = 0; r.fallback_reason = 0;
-        if (first_low[b]) { r.needs_fallback = 1; r.fallback_reason = 1; }
-        else if (o->has_no_speech_threshold && 0.f > o->no_speech_threshold) { r.needs_fallback = 0; r.fallback_reason = 2; }
-        else if (o->has_compression_ratio_threshold && r.compression_ratio > o->compression_ratio_threshold) { r.needs_fallback = 1; r.fallback_reason = 3; }
-        else if (o->has_logprob_threshold && r.avg_logprob < o->logprob_threshold) { r.needs_fallback = 1; r.fallback_reason = 4; }
+    // ---- read back and finalise on the host
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        const int B = ln->batch;
+        if (B == 0) continue;
+        std::vector<int32_t> tokens((size_t)B * kKvMaxLen), n_tok(B), first_low(B), steps(B);
+        std::vector<float> lps((size_t)B * kKvMaxLen);
+        WK_CUDA_CHECK(cudaMemcpyAsync(tokens.data(), ln->st.tokens, tokens.size() * 4, cudaMemcpyDeviceToHost, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(lps.data(), ln->st.logprobs, lps.size() * 4, cudaMemcpyDeviceToHost, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(n_tok.data(), ln->st.n_tokens, B * 4, cudaMemcpyDeviceToHost, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(first_low.data(), ln->st.first_low, B * 4, cudaMemcpyDeviceToHost, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(steps.data(), ln->st.steps, B * 4, cudaMemcpyDeviceToHost, ln->stream));
+        cudaError_t e = cudaStreamSynchronize(ln->stream);
+        if (e != cudaSuccess) { set_error("wk_decode_text: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
+        for (int b = 0; b < B; ++b)
+            finalize_result(results[ln->b0 + b], tokens.data() + (size_t)b * kKvMaxLen, lps.data() + (size_t)b * kKvMaxLen, n_tok[b], steps[b],
+                            first_low[b], st, o);
     }
     return WK_OK;
 }
@@ -1262,8 +1363,8 @@ wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_hos
         WK_CHECK(wk_encode(m, mel, &enc));
         WK_CUDA_CHECK(cudaEventRecord(m->ev[3], m->stream));
         WK_CHECK(wk_session_set_encoder_output(s, enc));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[4], m->stream));
-        WK_CHECK(wk_decode_text(s, st, opts, prompt, n_prompt, results + w0));
+        WK_CUDA_CHECK(cudaEventRecord(m->ev[4], s->lane[0]->stream));   // lane 0's cross-KV projection done
+        WK_CHECK(wk_decode_text(s, st, opts, prompt, n_prompt, results + w0));   // returns with both lanes drained
         WK_CUDA_CHECK(cudaEventRecord(m->ev[5], m->stream));
         WK_CUDA_CHECK(cudaEventSynchronize(m->ev[5]));
         float t;
@@ -1342,32 +1443,34 @@ wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t bat
     WK_CUDA_CHECK(cudaSetDevice(m->device));
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, T = c.n_audio_ctx, H = c.n_heads, dt = c.dtype;
-    const int B = batch;
-    if (B < 1 || B > c.max_batch || (s && B > s->max_batch)) { set_error("wk_bench_kernel: bad batch"); return WK_ERR_INVALID_ARGUMENT; }
+    Lane* ln = s ? s->lane[0] : nullptr;
+    int B = batch;
+    if (ln && which != 1 && which != 2 && which != 3 && which != 5 && B > ln->max_batch) B = ln->max_batch;   // lane-local kernels run per lane
+    if (B < 1 || B > c.max_batch) { set_error("wk_bench_kernel: bad batch"); return WK_ERR_INVALID_ARGUMENT; }
     const int64_t M = (int64_t)B * T;
-    cudaStream_t st = m->stream;
+    cudaStream_t st = (ln && which != 1 && which != 2 && which != 3 && which != 5) ? ln->stream : m->stream;
     auto run = [&]() -> wk_status {
         switch (which) {
             case 0: {
-                if (!s) return WK_ERR_INVALID_ARGUMENT;
-                const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;
-                return decoder_cross_attention(s->partial, 1, round_up(B, 16), m->dec[0].bcq, s->cross_kv, (char*)s->cross_kv + cross_block, s->attn, B, H, T, dt, st);
+                if (!ln) return WK_ERR_INVALID_ARGUMENT;
+                const size_t cross_block = (size_t)ln->max_batch * H * T * 64 * 2;
+                return decoder_cross_attention(ln->partial, 1, round_up(B, 16), m->dec[0].bcq, ln->cross_kv, (char*)ln->cross_kv + cross_block, ln->attn, B, H, T, dt, st);
             }
             case 1: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].w1, 4 * d, dt, GEMM_OUT_T16, m->ffn, 4 * d, m->enc[0].b1, 1), m->num_sms, st);
             case 2: return mel_forward(m->mel_tables, m->pcm_dev, B, kWindowSamples, nullptr, m->mel, m->gmax, st);
             case 3: return encoder_attention(m->qkv, m->attn, B, T, H, dt, st);
-            case 4: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].wqkv, 3 * d, d, s->xn, &sp); }
+            case 4: { if (!ln) return WK_ERR_INVALID_ARGUMENT; ln->bp = round_up(B, 16); int sp; return dec_gemm(ln, m->dec[0].wqkv, 3 * d, d, ln->xn, &sp); }
             case 5: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, m->enc[0].bqkv, 0), m->num_sms, st);
-            case 6: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].wo, d, d, s->attn, &sp); }
-            case 7: { if (!s) return WK_ERR_INVALID_ARGUMENT; s->bp = round_up(B, 16); int sp; return dec_gemm(s, m->dec[0].w2, d, 4 * d, s->ffn, &sp); }
-            case 8: { if (!s) return WK_ERR_INVALID_ARGUMENT;
-                      return decoder_reduce_resid_ln(s->partial, choose_splits((d + 127) / 128, d / 64, m->num_sms), round_up(B, 16), m->dec[0].bo,
-                                                     m->dec[0].lnx.g, m->dec[0].lnx.b, s->x, s->xn, B, d, dt, st); }
-            case 9: { if (!s) return WK_ERR_INVALID_ARGUMENT;
+            case 6: { if (!ln) return WK_ERR_INVALID_ARGUMENT; ln->bp = round_up(B, 16); int sp; return dec_gemm(ln, m->dec[0].wo, d, d, ln->attn, &sp); }
+            case 7: { if (!ln) return WK_ERR_INVALID_ARGUMENT; ln->bp = round_up(B, 16); int sp; return dec_gemm(ln, m->dec[0].w2, d, 4 * d, ln->ffn, &sp); }
+            case 8: { if (!ln) return WK_ERR_INVALID_ARGUMENT;
+                      return decoder_reduce_resid_ln(ln->partial, choose_splits((d + 127) / 128, d / 64, m->num_sms), round_up(B, 16), m->dec[0].bo,
+                                                     m->dec[0].lnx.g, m->dec[0].lnx.b, ln->x, ln->xn, B, d, dt, st); }
+            case 9: { if (!ln) return WK_ERR_INVALID_ARGUMENT;
                       static int32_t* pos100 = nullptr;
                       if (!pos100) { std::vector<int32_t> h(256, 100); cudaMalloc(&pos100, 256 * 4); cudaMemcpy(pos100, h.data(), 256 * 4, cudaMemcpyHostToDevice); }
-                      return decoder_self_attention(s->partial, 1, round_up(B, 16), m->dec[0].bq, m->dec[0].bv, s->self_k, s->self_v, s->st.step, pos100,
-                                                    s->attn, B, H, kKvMaxLen, dt, st); }
+                      return decoder_self_attention(ln->partial, 1, round_up(B, 16), m->dec[0].bq, m->dec[0].bv, ln->self_k, ln->self_v, ln->st.step, pos100,
+                                                    ln->attn, B, H, kKvMaxLen, dt, st); }
             default: set_error("wk_bench_kernel: unknown kernel %d", which); return WK_ERR_INVALID_ARGUMENT;
         }
     };
@@ -1418,6 +1521,7 @@ wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t bat
 wk_status wk_debug_read(wk_model* m, wk_session* s, int32_t which, int64_t offset_elems, float* dst, int64_t n) {
     if (!m || !dst) return WK_ERR_INVALID_ARGUMENT;
     WK_CUDA_CHECK(cudaSetDevice(m->device));
+    Lane* ln = s ? s->lane[0] : nullptr;
     const void* src = nullptr;
     int dt = m->cfg.dtype;
     switch (which) {
@@ -1429,15 +1533,15 @@ wk_status wk_debug_read(wk_model* m, wk_session* s, int32_t which, int64_t offse
         case 5: src = m->attn; break;
         case 6: src = m->ffn; break;
         case 7: src = m->enc_out; break;
-        case 10: src = s ? s->x : nullptr; dt = WK_DTYPE_F32; break;
-        case 11: src = s ? s->xn : nullptr; break;
-        case 12: src = s ? s->attn : nullptr; break;
-        case 13: src = s ? s->ffn : nullptr; break;
-        case 14: src = s ? s->logits : nullptr; dt = WK_DTYPE_F32; break;
-        case 15: src = s ? s->cross_kv : nullptr; break;
-        case 16: src = s ? s->self_k : nullptr; break;
-        case 17: src = s ? s->self_v : nullptr; break;
-        case 18: src = s ? s->partial : nullptr; dt = WK_DTYPE_F32; break;
+        case 10: src = ln ? ln->x : nullptr; dt = WK_DTYPE_F32; break;
+        case 11: src = ln ? ln->xn : nullptr; break;
+        case 12: src = ln ? ln->attn : nullptr; break;
+        case 13: src = ln ? ln->ffn : nullptr; break;
+        case 14: src = ln ? ln->logits : nullptr; dt = WK_DTYPE_F32; break;
+        case 15: src = ln ? ln->cross_kv : nullptr; break;
+        case 16: src = ln ? ln->self_k : nullptr; break;
+        case 17: src = ln ? ln->self_v : nullptr; break;
+        case 18: src = ln ? ln->partial : nullptr; dt = WK_DTYPE_F32; break;
         case 20: src = m->enc[0].wqkv; break;
         case 21: src = m->emb; break;
         case 22: src = m->enc[0].w1; break;

@@ -369,6 +369,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > total_kb / p.splits + 2) stages = total_kb / p.splits + 2;
     if (stages < 2) stages = 2;
+    if (d.max_stages > 0 && stages > d.max_stages) stages = d.max_stages;
     if (const char* e = getenv("WKB200_GEMM_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     p.stages = stages;
     p.debug_mode = 0;

@@ -58,6 +58,7 @@ struct GemmDesc {
     // HEADS scatter
     int heads_T, heads_B, heads_H, heads_dmodel;
     int pdl;                 // launch with programmatic dependent launch (decode-step chain)
+    int max_stages;          // 0 = as many smem stages as fit; >0 caps the ring (lets other kernels co-reside on the SM)
 };
 
 wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream);
