@@ -10,6 +10,7 @@
  *   wk_session_create/reset TextDecoding.prepareDecoderInputs     Sources/WhisperKit/Core/TextDecoder.swift:109-161
  *   wk_build_prompt         TextDecoding.prefillDecoderInputs     Sources/WhisperKit/Core/TextDecoder.swift:163-216
  *   wk_decode_step          TextDecoding.predictLogits            Sources/WhisperKit/Core/TextDecoder.swift:361-418
+ *   wk_detect_language      TextDecoding.detectLanguage           Sources/WhisperKit/Core/TextDecoder.swift:420-539
  *   wk_filter_sample        LogitsFiltering.filterLogits (x4) +   Sources/WhisperKit/Core/Text/LogitsFilter.swift:8-276
  *                           TokenSampling.update                  Sources/WhisperKit/Core/Text/TokenSampler.swift:8-11,215-240
  *   wk_decode_text          TextDecoding.decodeText (+ sampler    Sources/WhisperKit/Core/TextDecoder.swift:541-855
@@ -167,6 +168,9 @@ wk_status wk_session_reset(wk_session* s);
 wk_status wk_build_prompt(const wk_model* m, const wk_special_tokens* st, const wk_decode_opts* opts, int32_t use_options, int32_t* out, int32_t cap, int32_t* n);
 /* predictLogits for every bound window: input_ids[B], cache_length[B] (host) -> logits [B, vocab] f32 (host, may be NULL). */
 wk_status wk_decode_step(wk_session* s, const int32_t* input_ids, const int32_t* cache_length, float* logits_out);
+/* TextDecoding.detectLanguage (TextDecoder.swift:420-539): one step on [SOT] + LanguageLogitsFilter + sampler, per bound window. */
+wk_status wk_detect_language(wk_session* s, const wk_special_tokens* st, const int32_t* language_tokens, int32_t n_language_tokens,
+                             float temperature, int32_t* token_out, float* logprob_out);
 /* Filters + sampler alone (parity entry): logits [B, vocab] f32 host; tokens [B, ld_tokens], n_tokens[B] = currentTokens;
  * sample_begin_ts = TimestampRulesFilter.sampleBegin (<0: filter absent), sample_begin_blank = SuppressBlankFilter.sampleBegin
  * (<0: absent); language_tokens != NULL adds LanguageLogitsFilter(sampleBegin = language_sample_begin).

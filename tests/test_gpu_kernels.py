@@ -185,3 +185,34 @@ def test_filter_sampler_random_rows_vs_oracle(toy):
         r = D.GreedyTokenSampler(0.0, st_o.endToken, opts).update([], row, [])
         assert tok[b] == r.tokens[-1], b
         assert abs(lp[b] - r.logProbs[-1]) < 2e-4, (b, lp[b], r.logProbs[-1])
+
+
+def test_temperature_topk_sampling_vs_oracle(toy):
+    """GreedyTokenSampler with temperature > 0 (TokenSampler.swift:57-73): softmax(logits / T), top-k, multinomial draw inside
+    the top-k mass, logprob = log of the full-vocabulary softmax prob.  The draw itself is Philox-seeded here (Float.random in
+    the reference), so parity is: token in the oracle's top-k set, exact logprob, k = 1 == argmax, frequencies ~ probabilities."""
+    rng = np.random.default_rng(3)
+    V, B, T, K = 4096, 64, 0.7, 5
+    st_o = D.SpecialTokens.test_default(endToken=V - 1, timeTokenBegin=V, specialTokenBegin=V - 1)
+    st = wk.SpecialTokens.from_any(st_o)
+    base = rng.standard_normal(V).astype(np.float32) * 3
+    logits = np.tile(base, (B, 1))
+    x = base.astype(np.float64) / T
+    probs = np.exp(x - x.max())
+    probs /= probs.sum()
+    top = np.argsort(-probs, kind="stable")[:K]
+    counts = np.zeros(K)
+    n_draws = 0
+    for seed in range(20):
+        tok, lp, _ = wk.filter_and_sample(toy, logits, [[1]] * B, st, wk.DecodingOptions(temperature=T, topK=K, seed=seed))
+        for b in range(B):
+            assert tok[b] in top
+            j = int(np.where(top == tok[b])[0][0])
+            assert abs(lp[b] - np.log(probs[tok[b]])) < 2e-4
+            counts[j] += 1
+            n_draws += 1
+    expect = probs[top] / probs[top].sum()
+    assert np.abs(counts / n_draws - expect).max() < 0.05, (counts / n_draws, expect)
+    assert len(set(np.round(counts))) > 1
+    tok1, lp1, _ = wk.filter_and_sample(toy, logits[:4], [[1]] * 4, st, wk.DecodingOptions(temperature=T, topK=1, seed=9))
+    assert all(t == int(np.argmax(base)) for t in tok1)

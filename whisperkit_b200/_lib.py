@@ -99,6 +99,7 @@ SYMBOLS = [
     ("wk_session_reset", I32, [P]),
     ("wk_build_prompt", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), I32, PI32, I32, PI32]),
     ("wk_decode_step", I32, [P, PI32, PI32, P]),
+    ("wk_detect_language", I32, [P, C.POINTER(wk_special_tokens), PI32, I32, F32, PI32, PF32]),
     ("wk_filter_sample", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), I32, P, I32, I32, P, I32, P,
                                I32, I32, P, I32, I32, P, P, P]),
     ("wk_decode_text", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), PI32, I32,

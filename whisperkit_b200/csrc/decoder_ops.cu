@@ -5,6 +5,7 @@
 //   updateKVCache (host splice, eliminated)  Sources/WhisperKit/Core/TextDecoder.swift:218-270
 //   LogitsFiltering x4                       Sources/WhisperKit/Core/Text/LogitsFilter.swift:12-276
 //   GreedyTokenSampler.update                Sources/WhisperKit/Core/Text/TokenSampler.swift:42-83,215-240
+#include <curand_kernel.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -715,23 +716,17 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
         for (int i = tid; i < tsb; i += kSamplerThreads) srow[i] = -INFINITY;
         __syncthreads();
     }
-    // ---- argmax (first maximal index) over [lo, V)
-    ArgMax best = {-INFINITY, 0x7fffffff};
-    for (int i = lo + tid; i < V; i += kSamplerThreads) {
-        const float x = srow[i];
-        if (x > best.v) { best.v = x; best.i = i; }
+    if (filtered_out) {
+        for (int i = tid; i < V; i += kSamplerThreads) filtered_out[(long long)b * V + i] = srow[i];
+        __syncthreads();
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ArgMax other;
-        other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-        other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-        best = argmax_better(best, other);
-    }
-    if ((tid & 31) == 0) sarg[tid >> 5] = best;
-    __syncthreads();
-    if (tid < 32) {
-        best = sarg[tid];
+    // ---- block-wide argmax (first maximal index) over [lo, V); srow is only read
+    auto block_argmax = [&]() -> ArgMax {
+        ArgMax best = {-INFINITY, 0x7fffffff};
+        for (int i = lo + tid; i < V; i += kSamplerThreads) {
+            const float x = srow[i];
+            if (x > best.v) { best.v = x; best.i = i; }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ArgMax other;
@@ -739,13 +734,66 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
             other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
             best = argmax_better(best, other);
         }
-    }
-    if (filtered_out) {
-        for (int i = tid; i < V; i += kSamplerThreads) filtered_out[(long long)b * V + i] = srow[i];
+        __syncthreads();
+        if ((tid & 31) == 0) sarg[tid >> 5] = best;
+        __syncthreads();
+        best = sarg[tid & 31];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgMax other;
+            other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+            other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+            best = argmax_better(best, other);
+        }
+        return best;   // identical in every thread
+    };
+    ArgMax best;
+    float lp_sampled = 0.f;
+    if (p.temperature == 0.f) {
+        best = block_argmax();
+        lp_sampled = best.v - lse;
+    } else {
+        // GreedyTokenSampler with temperature (TokenSampler.swift:57-73 / :140-180): logits / T, softmax over the whole
+        // (filtered) vocabulary, top-k, multinomial draw inside the top-k mass, logprob = log softmax prob of the draw.
+        // The reference draws with Float.random (non-deterministic); here the draw is Philox(seed, row, step).
+        const float inv_t = 1.f / p.temperature;
+        const float zmax = (ts_wins ? mts : mall) * inv_t;
+        float z = 0.f;
+        for (int i = lo + tid; i < V; i += kSamplerThreads) {
+            const float x = srow[i];
+            if (x != -INFINITY) z += __expf(x * inv_t - zmax);
+        }
+        z = block_sum(z, scratch);
+        __shared__ float topv[32];
+        __shared__ int topi[32];
+        const int k = p.top_k < 1 ? 1 : (p.top_k > 32 ? 32 : p.top_k);
+        int kk = 0;
+        for (; kk < k; ++kk) {
+            const ArgMax a = block_argmax();
+            if (a.v == -INFINITY) break;
+            if (tid == 0) { topv[kk] = __expf(a.v * inv_t - zmax) / z; topi[kk] = a.i; srow[a.i] = -INFINITY; }
+            __syncthreads();
+        }
+        __syncthreads();
+        float mass = 0.f;
+        for (int j = 0; j < kk; ++j) mass += topv[j];
+        curandStatePhilox4_32_10_t rng;
+        curand_init(p.seed, (unsigned long long)b, (unsigned long long)(loop_mode ? *st.step : n_tok), &rng);
+        const float u = 1.f - curand_uniform(&rng);   // [0, 1)
+        const float rnd = u * mass;
+        float acc = 0.f;
+        int chosen = kk > 0 ? kk - 1 : 0;
+        for (int j = 0; j < kk; ++j) {
+            acc += topv[j];
+            if (rnd < acc) { chosen = j; break; }
+        }
+        best.i = kk > 0 ? topi[chosen] : 0x7fffffff;
+        best.v = 0.f;
+        lp_sampled = kk > 0 ? logf(topv[chosen]) : -INFINITY;
     }
     if (tid == 0) {
         const int tok = best.i;
-        const float lp = best.v - lse;
+        const float lp = lp_sampled;
         if (token_out) token_out[b] = tok;
         if (logprob_out) logprob_out[b] = lp;
         if (loop_mode && !st.done[b]) {
@@ -777,10 +825,6 @@ __global__ void advance_step_kernel(DecodeState st) {
 wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
                                 int ld_tokens, const int32_t* n_tokens, int32_t* token_out, float* logprob_out,
                                 float* filtered_out, int B, cudaStream_t stream) {
-    if (p.temperature != 0.f) {
-        set_error("sampler: temperature > 0 (top-k multinomial fallback sampling) is not implemented in this round");
-        return WK_ERR_INVALID_ARGUMENT;
-    }
     const size_t smem = (size_t)p.vocab * sizeof(float);
     if (smem > 220 * 1024) { set_error("sampler: vocab %d too large for the shared-memory row", p.vocab); return WK_ERR_INVALID_ARGUMENT; }
     static bool attr_set = false;

@@ -993,8 +993,10 @@ wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
     wk_session* s = new wk_session();
     s->m = m;
     s->max_batch = max_batch;
-    // two concurrent lanes once the batch is large enough for a lane's cross-attention to fill the machine
-    s->n_lanes = (max_batch >= 32 && !getenv("WKB200_SINGLE_LANE")) ? 2 : 1;
+    // Optional second lane (WKB200_DECODE_LANES=2): measured on B200 at 64 windows it is bit-identical but not faster
+    // (1371 vs 1324 ms/step) - every decode kernel already fills the machine, so the two chains serialise - hence opt-in.
+    const char* lanes_env = getenv("WKB200_DECODE_LANES");
+    s->n_lanes = (max_batch >= 32 && lanes_env && atoi(lanes_env) == 2) ? 2 : 1;
     if (max_batch > 256 && s->n_lanes == 1) { set_error("wk_session_create: max_batch %d > 256 needs two lanes", max_batch); return WK_ERR_INVALID_ARGUMENT; }
     const int cap0 = s->n_lanes == 2 ? (max_batch + 1) / 2 : max_batch;
     WK_CHECK(lane_create(m, cap0, &s->lane[0]));
@@ -1141,6 +1143,48 @@ wk_status wk_session_lanes(const wk_session* s, int32_t* n_lanes, int32_t* lane_
     if (!s || !n_lanes) return WK_ERR_INVALID_ARGUMENT;
     *n_lanes = s->n_lanes;
     if (lane_batch2) { lane_batch2[0] = s->lane[0]->batch; lane_batch2[1] = s->n_lanes == 2 ? s->lane[1]->batch : 0; }
+    return WK_OK;
+}
+
+// TextDecoder.detectLanguage (TextDecoder.swift:420-539): one decoder step on [SOT] at position 0, LanguageLogitsFilter
+// (keep only the language tokens), GreedyTokenSampler -> language token id + logprob for every bound window.
+wk_status wk_detect_language(wk_session* s, const wk_special_tokens* st, const int32_t* language_tokens, int32_t n_language_tokens,
+                             float temperature, int32_t* token_out, float* logprob_out) {
+    if (!s || !st || !language_tokens || n_language_tokens < 1 || n_language_tokens > 4096 || !token_out) {
+        set_error("wk_detect_language: bad arguments");
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    wk_model* m = s->m;
+    if (s->batch < 1) { set_error("wk_detect_language: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        const int B = ln->batch;
+        if (B == 0) continue;
+        std::vector<int32_t> ids(B, st->start_of_transcript_token), zeros(B, 0), ones(B, 1);
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.input_ids, ids.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->pos_dev, zeros.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));
+        WK_CHECK(decoder_forward(ln, 0, 0, ln->pos_dev));
+        // currentTokens = [SOT] for every window: reuse the decode-state arrays as the stateless token history
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.tokens, ids.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));   // ld_tokens = 1
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.n_tokens, ones.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(ln->lang_dev, language_tokens, n_language_tokens * 4, cudaMemcpyHostToDevice, ln->stream));
+        SamplerParams p;
+        memset(&p, 0, sizeof(p));
+        p.st = *st; p.vocab = m->cfg.vocab; p.is_multilingual = 1;
+        p.sample_begin_ts = -1; p.sample_begin_blank = -1;
+        p.language_tokens = ln->lang_dev; p.n_language_tokens = n_language_tokens; p.language_sample_begin = 0;
+        p.temperature = temperature; p.top_k = 5; p.seed = 0;
+        p.prompt_len = -1; p.max_ctx = kKvMaxLen;
+        DecodeState none;
+        memset(&none, 0, sizeof(none));
+        WK_CHECK(sampler_filter_sample(ln->logits, m->cfg.vocab, p, none, ln->st.tokens, 1, ln->st.n_tokens, ln->st.next_token,
+                                       ln->st.logprobs, nullptr, B, ln->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(token_out + ln->b0, ln->st.next_token, B * 4, cudaMemcpyDeviceToHost, ln->stream));
+        if (logprob_out) WK_CUDA_CHECK(cudaMemcpyAsync(logprob_out + ln->b0, ln->st.logprobs, B * 4, cudaMemcpyDeviceToHost, ln->stream));
+        cudaError_t e = cudaStreamSynchronize(ln->stream);
+        if (e != cudaSuccess) { set_error("wk_detect_language: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
+    }
     return WK_OK;
 }
 
