@@ -286,3 +286,55 @@ def test_temperature_fallback_ladder():
     assert all(r.temperature == 0.0 for r in res0)
     o1 = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=10, logProbThreshold=None, compressionRatioThreshold=None)
     assert all(r.fallback is None and r.temperature == 0.0 for r in kit.transcribe(pcm, o1))
+
+
+def test_tiny_en_jfk_config0():
+    """BASELINE configs[0] shapes: whisper-tiny.en (80 mels, d 384, 6 heads, 4+4 layers, vocab 51864, English-only prompt
+    [SOT, <|0.00|>]) on the reference's own jfk.wav clip (11 s, zero-padded to 30 s by padOrTrim), CLI-style options
+    (firstTokenLogProbThreshold nil).  Weights are seeded random (no checkpoints offline), so the check is parity with the
+    oracle: HF log-mel golden, logits, and the decode loop."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jfk_logmel_hf.npz"))
+    pcm = z["pcm16"].astype(np.float32) / 32768.0
+    dims, orc, model = build("tiny.en", "f16", 1, seed=31)
+    info = model.info
+    assert (info.n_mels, info.d_model, info.vocab, info.is_multilingual) == (80, 384, 51864, 0)
+    fe, enc, dec, dec2 = wk.FeatureExtractor(model), wk.AudioEncoder(model), wk.TextDecoder(model, 1), wk.TextDecoder(model, 1)
+    mel_t = fe.logMelSpectrogram(pcm[None], samples_per_window=[len(pcm)])    # stride 176000 < 480000: padOrTrim in the kernel
+    mel_gpu = mel_t.numpy()
+    assert np.abs(mel_gpu[0][:, ::8] - z["mel80_sub8"]).max() <= 1e-3          # vs HF / openai-whisper golden
+    enc_t = enc.encodeFeatures(mel_t)
+    st_o = D.SpecialTokens.english_only()
+    st = wk.SpecialTokens.from_any(st_o)
+    kw = dict(firstTokenLogProbThreshold=None, sampleLength=24)
+    o_ref, o_gpu = D.DecodingOptions(**kw), wk.DecodingOptions(**kw)
+    prompt = dec.prefillDecoderInputs(o_gpu, st)
+    assert prompt == D.prefill_prompt(o_ref, st_o, False) == [st_o.startOfTranscriptToken, st_o.timeTokenBegin]
+    res = dec.decodeText(enc_t, prompt, o_gpu, st)[0]
+    dec2.bindEncoderOutput(enc_t)
+    ref_g = _oracle_loop_on_gpu_logits(dec2, 1, prompt, o_ref, st_o, False, 0)
+    assert res.tokens == ref_g.tokens and res.steps == ref_g.steps == 24
+    ref = _oracle_decode(orc, enc_t.numpy(), prompt, o_ref, st_o, False, 0)
+    worst = max(rel_err(a, b) for a, b in zip(ref_g.stepLogits[:3], ref.stepLogits[:3]))
+    print(f"[tiny.en/f16 jfk] first-steps logits rel err vs CPU oracle {worst:.2e}; tokens equal: {res.tokens == ref.tokens}")
+    assert worst <= 1e-3
+    for d_ in (dec, dec2):
+        d_.close()
+    model.close()
+
+
+def test_ragged_and_silent_windows():
+    """Edge cases the reference handles in padOrTrimAudio / the mel front end: all-zero audio, a 1-sample window, a full
+    window; plus n_windows > max_batch chunking with per-window lengths."""
+    dims, orc, model = build("toy", "bf16", 2, seed=3)
+    fe = wk.FeatureExtractor(model)
+    pcm = np.zeros((2, 480000), np.float32)
+    pcm[1, 0] = 0.5
+    got = fe.logMelSpectrogram(pcm, samples_per_window=[0, 1]).numpy()
+    ref1 = mel_ref.log_mel(pcm[1], dims.n_mels)
+    assert np.abs(got[0] - mel_ref.log_mel(pcm[0], dims.n_mels)).max() <= 1e-3 and np.abs(got[1] - ref1).max() <= 1e-3
+    assert np.allclose(got[0], -1.5)   # silence: log10(1e-10) = -10 -> (-10 + 4) / 4
+    with pytest.raises(wk.WhisperError) as ei:
+        fe.logMelSpectrogram(np.zeros((3, 480000), np.float32))   # more windows than the model's max_batch
+    assert ei.value.case == "audioProcessingFailed"
+    model.close()

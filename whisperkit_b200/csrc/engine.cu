@@ -155,7 +155,7 @@ namespace wk {
 
 static int choose_splits(int tiles, int total_kb, int num_sms) {
     int best = 1;
-    for (int s = 1; s <= total_kb; ++s) {
+    for (int s = 1; s <= total_kb && s <= 20; ++s) {   // 20 = kMaxSplits of the fused reduce kernels
         if (total_kb % s) continue;
         best = s;
         if (tiles * s >= (num_sms * 13) / 20) break;  // >= 0.65 * SMs pulling weights; fewer partials to reduce

@@ -8,10 +8,11 @@
 //   * decoder (M = batch <= 256): swap-AB, A = weights (128 output features per tile), B = activations,
 //     split-K partials written transposed so the next fused reduce(+LN) kernel reads them coalesced.
 //
-// Structure (192 threads, 1 CTA / SM, persistent over work items):
+// Structure (320 threads, 1 CTA / SM, persistent over work items):
 //   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) into a ring of smem stages, mbarrier tx
 //   warp 1      MMA issuer: one lane issues tcgen05.mma kind::f16 128xBNx16, tcgen05.commit frees stages
-//   warps 2..5  epilogue: tcgen05.ld 32x32b from a double-buffered TMEM accumulator -> fused epilogue -> HBM
+//   warps 2..9  epilogue: tcgen05.ld 32x32b from a double-buffered TMEM accumulator -> fused epilogue -> HBM
+//               (two warps per TMEM lane quarter, alternating 32-column chunks, so erf-GELU epilogues keep up with the MMAs)
 // The WhisperKit reference has no counterpart source for this file: the contraction lives inside
 // AudioEncoder.mlmodelc / TextDecoder.mlmodelc (Sources/WhisperKit/Core/AudioEncoder.swift:59-62,
 // Sources/WhisperKit/Core/TextDecoder.swift:394-417).
@@ -30,7 +31,7 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;   // 64 x 2 B = one 128-byte swizzle row
 static constexpr int kUmmaK = 16;
 static constexpr int kStageA = kBlockM * kBlockK * 2;  // 16 KiB
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int kTmemCols = 512;
 static constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 static constexpr int kMaxStages = 10;
@@ -83,7 +84,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -165,6 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int csub = (warp - 2) >> 2;  // which of the two warps of this quarter: takes the 32-column chunks with (c / 32) % 2 == csub
         int it = 0;
         for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -183,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
             const int col_base = n_tile * p.bn;
 
-            for (int c = 0; c < p.bn; c += 32) {
+            for (int c = csub * 32; c < p.bn; c += 64) {
                 uint32_t r[32];
                 __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent tails below
                 tmem_ld_32x32(taddr + c, r);
