@@ -280,7 +280,9 @@ def run_own_arm(args):
     lib = model.lib
     info = model.info
     st = special_tokens_for(info.vocab)
-    opts = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=args.sample_length)
+    # one greedy pass per window: with random-init weights avgLogProb is always below logProbThreshold, so the temperature
+    # fallback ladder (retries, not part of the metric) is switched off; the CPU arm decodes one pass as well
+    opts = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=args.sample_length, temperatureFallbackCount=0)
     prompt = dec.prefillDecoderInputs(opts, st)
     st_c = st.to_c()
     o_c, keep = opts.to_c()
@@ -380,7 +382,8 @@ def run_own_arm(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic 16 kHz PCM (seeded noise + gated tones), seeded random weights of the large-v3 architecture",
         "config": {"workload": f"whisper-{args.variant} greedy {args.dtype}, batch={B} x 30 s windows per GPU (BASELINE configs[1]), "
-                               f"DecodingOptions defaults except firstTokenLogProbThreshold=nil; sampleLength={args.sample_length} "
+                               f"DecodingOptions defaults except firstTokenLogProbThreshold=nil and temperatureFallbackCount=0 (one greedy pass; random-init "
+                               f"weights would otherwise always retry); sampleLength={args.sample_length} "
                                f"(decode steps per window: {min(steps_run)}..{max(steps_run)}), timestamps on (TimestampRulesFilter active)",
                    "windows_per_gpu": B, "sample_length": args.sample_length, "decode_steps": max(steps_run),
                    "parallelism": f"dp{world} (windows sharded, weights replicated)",

@@ -108,6 +108,11 @@ typedef struct wk_decode_opts {
     int32_t has_first_token_logprob_threshold; float first_token_logprob_threshold; /* -1.5 */
     int32_t has_no_speech_threshold;         float no_speech_threshold;         /* 0.6 */
     uint64_t seed;                /* Philox seed for temperature > 0 (the reference uses Float.random) */
+    /* decodeWithFallback ladder (TranscribeTask.swift:316-411), applied by wk_transcribe_windows / wk_transcribe_streams only:
+     * a window whose DecodingFallback.needsFallback is set is decoded again (same encoder output) at
+     * Float16(temperature) + Float16(i) * Float16(increment), i = 1..count. */
+    int32_t temperature_fallback_count;        /* default 5; 0 = no retries */
+    float temperature_increment_on_fallback;   /* default 0.2 */
 } wk_decode_opts;
 
 /* Per-window DecodingResult (Models.swift:383-439) in flat arrays; tokens = SOT..EOT slice. */
@@ -193,6 +198,50 @@ wk_status wk_session_last_logits(wk_session* s, float* logits_out);
 wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_host /* host (pageable/pinned) or device */, int64_t n_windows, int64_t stride,
                                 const int32_t* samples_per_window, const wk_special_tokens* st, const wk_decode_opts* opts,
                                 const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
+
+/* ---- long-form windowing: host logic, callable without a GPU ---- */
+typedef struct wk_segment {             /* TranscriptionSegment (Models.swift), token-level fields */
+    int32_t stream, id;
+    int64_t seek;                       /* window start sample inside the stream */
+    float start, end;                   /* seconds from the start of the stream */
+    int64_t token_offset; int32_t n_tokens; /* slice of the flat token / logprob arrays */
+    float temperature, avg_logprob, compression_ratio, no_speech_prob;
+} wk_segment;
+/* SegmentSeeking.findSeekPointAndSegments (Sources/WhisperKit/Core/Text/SegmentSeeker.swift:41-189).
+ * *n_segs = -1 means the Swift function returned nil segments (window skipped as silent). token_offset is relative to `tokens`. */
+wk_status wk_find_seek_point_and_segments(const int32_t* tokens, const float* token_logprobs, int32_t n_tokens, float no_speech_prob,
+                                          float avg_logprob, float compression_ratio, float temperature, const wk_decode_opts* opts,
+                                          int32_t all_segments_count, int64_t current_seek, int64_t segment_size, int32_t sample_rate,
+                                          int32_t time_token, int64_t* new_seek, wk_segment* segs, int32_t cap, int32_t* n_segs);
+/* DecodingOptions.prepareSeekClips (Sources/WhisperKit/Utilities/Extensions+Internal.swift:111-130); clips = [start0,end0,start1,...] */
+wk_status wk_prepare_seek_clips(const float* clip_timestamps, int32_t n, int64_t content_frames, int64_t* clips, int32_t cap, int32_t* n_clips);
+/* EnergyVAD.voiceActivity (EnergyVAD.swift:41-56, AudioProcessor.swift:674-702): RMS per frame > threshold */
+wk_status wk_vad_voice_activity(const float* wav, int64_t n, int32_t frame_len, int32_t frame_overlap, float threshold, uint8_t* out,
+                                int64_t cap, int64_t* n_frames);
+/* VoiceActivityDetector.findLongestSilence (VoiceActivityDetector.swift:95-125); start = end = -1 when there is none */
+wk_status wk_vad_find_longest_silence(const uint8_t* vad, int64_t n, int64_t* start, int64_t* end);
+/* VoiceActivityDetector.calculateActiveChunks (:52-80); chunks = [start0,end0,...] */
+wk_status wk_vad_active_chunks(const float* wav, int64_t n, int32_t frame_len, int32_t frame_overlap, float threshold, int64_t* chunks,
+                               int32_t cap, int32_t* n_chunks);
+/* VADAudioChunker.chunkAll (Sources/WhisperKit/Core/Audio/AudioChunker.swift:53-107); chunks = [seekOffsetIndex0,end0,...] */
+wk_status wk_vad_chunk_all(const float* wav, int64_t n, int64_t max_chunk_len, const float* clip_timestamps, int32_t n_clip_timestamps,
+                           int64_t window_padding, int32_t frame_len, int32_t frame_overlap, float threshold, int64_t* chunks, int32_t cap,
+                           int32_t* n_chunks);
+/* TranscribeTask.run's seek loop (TranscribeTask.swift:98-279) for MANY audio streams at once: every round the next <= 30 s
+ * window of each unfinished stream is batched through the GPU path, then each stream's seek advances by its own decoded
+ * timestamps.  chunking_vad != 0 first splits every stream with VADAudioChunker (WhisperKit.swift:878-911) so chunks become
+ * independent units.  Word timestamps are not produced (section 8f-1b). */
+typedef struct wk_transcription wk_transcription;
+wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* audio, const int64_t* n_samples, int32_t n_streams,
+                                const wk_special_tokens* st, const wk_decode_opts* opts, const int32_t* prompt, int32_t n_prompt,
+                                const float* clip_timestamps, int32_t n_clip_timestamps, float window_clip_time, int64_t max_window_seek,
+                                int32_t chunking_vad, wk_transcription** out);
+int32_t wk_transcription_segment_count(const wk_transcription* t);
+int32_t wk_transcription_window_count(const wk_transcription* t);
+int64_t wk_transcription_token_count(const wk_transcription* t);
+wk_status wk_transcription_segments(const wk_transcription* t, wk_segment* segs, int32_t cap);
+wk_status wk_transcription_tokens(const wk_transcription* t, int32_t* tokens, float* logprobs, int64_t cap);
+void wk_transcription_free(wk_transcription* t);
 
 /* ---- instrumentation ---- */
 /* Number of kernels launched by this library on the calling process since the last reset. */

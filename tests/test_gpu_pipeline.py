@@ -338,3 +338,57 @@ def test_ragged_and_silent_windows():
         fe.logMelSpectrogram(np.zeros((3, 480000), np.float32))   # more windows than the model's max_batch
     assert ei.value.case == "audioProcessingFailed"
     model.close()
+
+
+def test_transcribe_streams_seek_loop_matches_oracle_loop():
+    """wk_transcribe_streams (batched TranscribeTask.run seek loop, csrc/longform.cu) against the oracle's loop
+    (oracle/seek_ref.seek_loop) driven window by window through the same GPU decode: same windows visited, same segments, same
+    timings, for streams of different lengths advancing in one batch, with clip timestamps and with the VAD chunker."""
+    from oracle import seek_ref as S
+    from whisperkit_b200 import longform as L
+    st_o = D.SpecialTokens.toy(1024)
+    kit = wk.WhisperKit(wk.WhisperKitConfig(model="toy", maxBatch=4, seed=9, specialTokens=wk.SpecialTokens.from_any(st_o)))
+    o = wk.DecodingOptions(firstTokenLogProbThreshold=None, logProbThreshold=None, compressionRatioThreshold=None, sampleLength=24,
+                           temperatureFallbackCount=0)
+    rng = np.random.default_rng(3)
+    lens = [480000 * 2 + 12345, 300000, 480000, 7000, 0, 1100000]
+    streams = [np.concatenate([mel_ref.synthetic_pcm(200 + 10 * i + k) for k in range(3)])[:n].astype(np.float32) for i, n in enumerate(lens)]
+
+    def oracle_stream(x, cts=(), base=0):
+        def decode_window(seek, size):
+            w = np.zeros(480000, np.float32)
+            w[:size] = x[seek:seek + size]
+            return kit.transcribe(w[None], o, samplesPerWindow=[size])[0]
+        return S.seek_loop(len(x), decode_window, clipTimestamps=cts, timeToken=st_o.timeTokenBegin, noSpeechThreshold=o.noSpeechThreshold,
+                           logProbThreshold=o.logProbThreshold)
+
+    for cts in ((), (1.0, 20.0, 31.5)):
+        got, windows = L.transcribe_streams(kit, streams, o, clipTimestamps=cts)
+        total = 0
+        for i, x in enumerate(streams):
+            ref, wins = oracle_stream(x, cts)
+            total += len(wins)
+            assert [g.tokens for g in got[i]] == [r.tokens for r in ref], (i, cts)
+            assert [g.seek for g in got[i]] == [r.seek for r in ref] and [g.id for g in got[i]] == [r.id for r in ref]
+            np.testing.assert_array_equal(np.float32([g.start for g in got[i]]), np.float32([r.start for r in ref]))
+            np.testing.assert_array_equal(np.float32([g.end for g in got[i]]), np.float32([r.end for r in ref]))
+            np.testing.assert_allclose([g.avgLogprob for g in got[i]], [r.avgLogprob for r in ref], atol=1e-5)
+        assert windows == total and total >= 8
+    # VAD chunking: each chunk is an independent unit whose seeks/timings are shifted by the chunk offset (WhisperKit.swift:896-911)
+    x = streams[5].copy()
+    x[500000:520000] = 0
+    got, windows = L.transcribe_streams(kit, [x], o, chunkingStrategy="vad")
+    chunks = S.vad_chunk_all(x, 480000)
+    assert len(chunks) >= 2
+    ref_all = []
+    for (a, b) in chunks:
+        ref, _ = oracle_stream(x[a:b])
+        for r in ref:
+            r.seek += a
+            r.start = float(np.float32(r.start) + np.float32(a) / np.float32(16000))
+            r.end = float(np.float32(r.end) + np.float32(a) / np.float32(16000))
+        ref_all += ref
+    assert [g.tokens for g in got[0]] == [r.tokens for r in ref_all]
+    assert [g.seek for g in got[0]] == [r.seek for r in ref_all]
+    np.testing.assert_allclose([g.start for g in got[0]], [r.start for r in ref_all], atol=1e-4)
+    np.testing.assert_allclose([g.end for g in got[0]], [r.end for r in ref_all], atol=1e-4)

@@ -60,6 +60,7 @@ class wk_decode_opts(C.Structure):
         ("has_first_token_logprob_threshold", C.c_int32), ("first_token_logprob_threshold", C.c_float),
         ("has_no_speech_threshold", C.c_int32), ("no_speech_threshold", C.c_float),
         ("seed", C.c_uint64),
+        ("temperature_fallback_count", C.c_int32), ("temperature_increment_on_fallback", C.c_float),
     ]
 
 
@@ -70,6 +71,12 @@ class wk_decode_result(C.Structure):
         ("needs_fallback", C.c_int32), ("fallback_reason", C.c_int32), ("first_token_logprob_too_low", C.c_int32),
         ("n_current_tokens", C.c_int32), ("steps", C.c_int32),
     ]
+
+
+class wk_segment(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("id", C.c_int32), ("seek", C.c_int64), ("start", C.c_float), ("end", C.c_float),
+                ("token_offset", C.c_int64), ("n_tokens", C.c_int32), ("temperature", C.c_float), ("avg_logprob", C.c_float),
+                ("compression_ratio", C.c_float), ("no_speech_prob", C.c_float)]
 
 
 # every symbol include/wkb200.h declares: (name, restype, argtypes)
@@ -108,6 +115,21 @@ SYMBOLS = [
     ("wk_session_lanes", I32, [P, PI32, PI32]),
     ("wk_transcribe_windows", I32, [P, P, P, I64, I64, PI32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts),
                                     PI32, I32, C.POINTER(wk_decode_result)]),
+    ("wk_find_seek_point_and_segments", I32, [PI32, PF32, I32, F32, F32, F32, F32, C.POINTER(wk_decode_opts), I32, I64, I64, I32, I32,
+                                              PI64, C.POINTER(wk_segment), I32, PI32]),
+    ("wk_prepare_seek_clips", I32, [PF32, I32, I64, PI64, I32, PI32]),
+    ("wk_vad_voice_activity", I32, [P, I64, I32, I32, F32, P, I64, PI64]),
+    ("wk_vad_find_longest_silence", I32, [P, I64, PI64, PI64]),
+    ("wk_vad_active_chunks", I32, [P, I64, I32, I32, F32, PI64, I32, PI32]),
+    ("wk_vad_chunk_all", I32, [P, I64, I64, PF32, I32, I64, I32, I32, F32, PI64, I32, PI32]),
+    ("wk_transcribe_streams", I32, [P, P, C.POINTER(P), PI64, I32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), PI32, I32,
+                                    PF32, I32, F32, I64, I32, C.POINTER(P)]),
+    ("wk_transcription_segment_count", I32, [P]),
+    ("wk_transcription_window_count", I32, [P]),
+    ("wk_transcription_token_count", I64, [P]),
+    ("wk_transcription_segments", I32, [P, C.POINTER(wk_segment), I32]),
+    ("wk_transcription_tokens", I32, [P, PI32, PF32, I64]),
+    ("wk_transcription_free", None, [P]),
     ("wk_kernel_launch_count", I64, [I32]),
     ("wk_last_timings", I32, [P, PF32]),
     ("wk_model_stream", P, [P]),

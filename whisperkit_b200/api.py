@@ -124,6 +124,8 @@ class DecodingOptions:
         o.has_first_token_logprob_threshold, o.first_token_logprob_threshold = opt(self.firstTokenLogProbThreshold)
         o.has_no_speech_threshold, o.no_speech_threshold = opt(self.noSpeechThreshold)
         o.seed = int(self.seed)
+        o.temperature_fallback_count = int(self.temperatureFallbackCount)
+        o.temperature_increment_on_fallback = float(self.temperatureIncrementOnFallback)
         return o, keep
 
 
@@ -501,28 +503,7 @@ class WhisperKit:
         check(self.model.lib.wk_transcribe_windows(self.model.handle, self.textDecoder.handle, _ptr(a), n, stride, spw,
                                                    C.byref(st), C.byref(o), p, len(prompt), res))
         self.textDecoder.batch = min(n, self.config.maxBatch)
+        # decodeWithFallback (TranscribeTask.swift:316-411) runs inside wk_transcribe_windows: windows whose
+        # DecodingFallback.needsFallback is set are decoded again from the same encoder output at the next ladder temperature.
         out = [DecodingResult.from_c(r) for r in res]
-        # decodeWithFallback (TranscribeTask.swift:316-411): windows whose DecodingFallback.needsFallback is set are decoded
-        # again at temperature + i * increment (computed in Float16 like the reference, :327), at most fallbackCount times.
-        pending = [i for i, r in enumerate(out) if r.fallback is not None and r.fallback.needsFallback]
-        for k in range(1, opts.temperatureFallbackCount + 1):
-            if not pending:
-                break
-            temp = float(np.float16(opts.temperature) + np.float16(k) * np.float16(opts.temperatureIncrementOnFallback))
-            sub = a[pending] if not hasattr(a, "data_ptr") else a[pending].contiguous()
-            sub = np.ascontiguousarray(sub) if not hasattr(sub, "data_ptr") else sub
-            o2 = DecodingOptions(**{**opts.__dict__, "temperature": temp, "seed": opts.seed + k})
-            oc, keep2 = o2.to_c()
-            spw2 = None
-            if samplesPerWindow is not None:
-                spw2 = (C.c_int32 * len(pending))(*[int(samplesPerWindow[i]) for i in pending])
-            res2 = (wk_decode_result * len(pending))()
-            check(self.model.lib.wk_transcribe_windows(self.model.handle, self.textDecoder.handle, _ptr(sub), len(pending), stride,
-                                                       spw2, C.byref(st), C.byref(oc), p, len(prompt), res2))
-            still = []
-            for j, i in enumerate(pending):
-                out[i] = DecodingResult.from_c(res2[j])
-                if out[i].fallback is not None and out[i].fallback.needsFallback:
-                    still.append(i)
-            pending = still
         return out

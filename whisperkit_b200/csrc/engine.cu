@@ -1409,6 +1409,22 @@ wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_hos
         WK_CHECK(wk_session_set_encoder_output(s, enc));
         WK_CUDA_CHECK(cudaEventRecord(m->ev[4], s->lane[0]->stream));   // lane 0's cross-KV projection done
         WK_CHECK(wk_decode_text(s, st, opts, prompt, n_prompt, results + w0));   // returns with both lanes drained
+        // decodeWithFallback (TranscribeTask.swift:316-411): the encoder output and cross-attention K/V of the chunk stay bound;
+        // only the token loop reruns, at Float16(temperature) + Float16(i) * Float16(increment) (:327), for windows that ask.
+        for (int i = 1; i <= opts->temperature_fallback_count; ++i) {
+            bool any = false;
+            for (int64_t b = 0; b < nb; ++b) any |= results[w0 + b].needs_fallback != 0;
+            if (!any) break;
+            wk_decode_opts o2 = *opts;
+            const float f16_t = __half2float(__float2half(opts->temperature));
+            const float f16_step = __half2float(__float2half(__half2float(__float2half((float)i)) * __half2float(__float2half(opts->temperature_increment_on_fallback))));
+            o2.temperature = __half2float(__float2half(f16_t + f16_step));
+            o2.seed = opts->seed + (uint64_t)i;
+            std::vector<wk_decode_result> retry((size_t)nb);
+            WK_CHECK(wk_decode_text(s, st, &o2, prompt, n_prompt, retry.data()));
+            for (int64_t b = 0; b < nb; ++b)
+                if (results[w0 + b].needs_fallback) results[w0 + b] = retry[b];
+        }
         WK_CUDA_CHECK(cudaEventRecord(m->ev[5], m->stream));
         WK_CUDA_CHECK(cudaEventSynchronize(m->ev[5]));
         float t;
