@@ -113,6 +113,7 @@ typedef struct wk_decode_opts {
      * Float16(temperature) + Float16(i) * Float16(increment), i = 1..count. */
     int32_t temperature_fallback_count;        /* default 5; 0 = no retries */
     float temperature_increment_on_fallback;   /* default 0.2 */
+    int32_t word_timestamps;      /* wordTimestamps: the decode loop also fills the alignmentWeights tensor (wk_session_alignment_weights) */
 } wk_decode_opts;
 
 /* Per-window DecodingResult (Models.swift:383-439) in flat arrays; tokens = SOT..EOT slice. */
@@ -200,6 +201,8 @@ wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_hos
                                 const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
 
 /* ---- long-form windowing: host logic, callable without a GPU ---- */
+typedef struct wk_tokenizer_hooks wk_tokenizer_hooks;   /* defined with the word-timestamp API below */
+typedef struct wk_word wk_word;
 typedef struct wk_segment {             /* TranscriptionSegment (Models.swift), token-level fields */
     int32_t stream, id;
     int64_t seek;                       /* window start sample inside the stream */
@@ -230,18 +233,77 @@ wk_status wk_vad_chunk_all(const float* wav, int64_t n, int64_t max_chunk_len, c
 /* TranscribeTask.run's seek loop (TranscribeTask.swift:98-279) for MANY audio streams at once: every round the next <= 30 s
  * window of each unfinished stream is batched through the GPU path, then each stream's seek advances by its own decoded
  * timestamps.  chunking_vad != 0 first splits every stream with VADAudioChunker (WhisperKit.swift:878-911) so chunks become
- * independent units.  Word timestamps are not produced (section 8f-1b). */
+ * independent units.  With opts->word_timestamps (and `hooks`, the host tokenizer) every window also runs addWordTimestamps
+ * (TranscribeTask.swift:197-239): segment bounds follow the word timings, zero-length segments are dropped and the last word end
+ * can pull the seek forward.  hooks may be NULL otherwise. */
 typedef struct wk_transcription wk_transcription;
 wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* audio, const int64_t* n_samples, int32_t n_streams,
                                 const wk_special_tokens* st, const wk_decode_opts* opts, const int32_t* prompt, int32_t n_prompt,
                                 const float* clip_timestamps, int32_t n_clip_timestamps, float window_clip_time, int64_t max_window_seek,
-                                int32_t chunking_vad, wk_transcription** out);
+                                int32_t chunking_vad, const wk_tokenizer_hooks* hooks, wk_transcription** out);
 int32_t wk_transcription_segment_count(const wk_transcription* t);
 int32_t wk_transcription_window_count(const wk_transcription* t);
 int64_t wk_transcription_token_count(const wk_transcription* t);
 wk_status wk_transcription_segments(const wk_transcription* t, wk_segment* segs, int32_t cap);
 wk_status wk_transcription_tokens(const wk_transcription* t, int32_t* tokens, float* logprobs, int64_t cap);
+int32_t wk_transcription_word_count(const wk_transcription* t);
+wk_status wk_transcription_word(const wk_transcription* t, int32_t i, wk_word* out);   /* .segment indexes wk_transcription_segments */
 void wk_transcription_free(wk_transcription* t);
+
+/* ---- word timestamps ----
+ * Device side: with wk_decode_opts.word_timestamps set, every decode step also writes the mean cross-attention softmax row of the
+ * model's alignment heads into row tokenIndex + 1 of a [224][1500] Float16 tensor per window - the decoder model's
+ * `alignment_heads_weights` output spliced by TextDecoder.updateAlignmentWeights (TextDecoder.swift:272-296,310,414,709-717).
+ * Host side (C++, callable without a GPU): SegmentSeeker's DTW / alignment / punctuation / duration logic
+ * (SegmentSeeker.swift:195-659).  The tokenizer stays with the host and is reached through wk_tokenizer_hooks. */
+/* (layer, head) pairs, e.g. openai-whisper's per-checkpoint alignment heads; n_pairs = 0 restores the default
+ * (all heads of the last half of the decoder layers). */
+wk_status wk_model_set_alignment_heads(wk_model* m, const int32_t* layer_head_pairs, int32_t n_pairs);
+/* DecodingResult.cache.alignmentWeights of one window of the last wk_decode_text, first `rows` rows, as f32 [rows][n_audio_ctx]. */
+wk_status wk_session_alignment_weights(wk_session* s, int32_t window, int32_t rows, float* out);
+
+struct wk_word {                   /* WordTiming (Models.swift:617-633) */
+    const char* word;              /* UTF-8, NUL-terminated */
+    const int32_t* tokens; int32_t n_tokens;
+    float start, end, probability;
+    int32_t segment;               /* set by the segment update: index of the segment that owns the word, else -1 */
+};
+typedef struct wk_words wk_words;  /* owning word list returned by the functions below */
+int32_t wk_words_count(const wk_words* w);
+wk_status wk_words_get(const wk_words* w, int32_t i, wk_word* out);   /* pointers stay valid until wk_words_free */
+void wk_words_free(wk_words* w);
+
+struct wk_tokenizer_hooks {
+    /* WhisperTokenizer.splitToWordTokens (Models.swift:1291-1306): write the words as consecutive NUL-terminated UTF-8 strings into
+     * `text` and each word's token count into `counts`; return the number of words, or < 0 on error / overflow. */
+    int32_t (*split_to_word_tokens)(void* user, const int32_t* tokens, int32_t n_tokens, char* text, int32_t text_cap, int32_t* counts, int32_t counts_cap);
+    /* WhisperTokenizer.decode(tokens:): NUL-terminated UTF-8 into `text`; return bytes written (without NUL) or < 0. May be NULL. */
+    int32_t (*decode)(void* user, const int32_t* tokens, int32_t n_tokens, char* text, int32_t text_cap);
+    void* user;
+};
+
+/* SegmentSeeker.dynamicTimeWarping (SegmentSeeker.swift:195-276); matrix row-major [rows][ld], dtype WK_DTYPE_F32 or WK_DTYPE_F16.
+ * The path has at most rows + cols entries. */
+wk_status wk_dtw(const void* matrix, int32_t dtype, int32_t rows, int32_t cols, int64_t ld, int32_t* text_indices, int32_t* time_indices,
+                 int32_t cap, int32_t* n_path);
+/* findAlignment (:340-408); `words` carry word + tokens (the host's splitToWordTokens), timings are ignored. */
+wk_status wk_find_alignment(const wk_word* words, int32_t n_words, const void* matrix, int32_t dtype, int32_t rows, int32_t cols, int64_t ld,
+                            const float* token_logprobs, int32_t n_logprobs, wk_words** out);
+/* mergePunctuations (:278-338); NULL prepended/appended = Constants.default{Prepend,Append}Punctuations (Models.swift:1459-1460). */
+wk_status wk_merge_punctuations(const wk_word* alignment, int32_t n, const char* prepended, const char* appended, wk_words** out);
+/* calculateWordDurationConstraints (:498-508) and truncateLongWordsAtSentenceBoundaries (:510-526). */
+wk_status wk_word_duration_constraints(const wk_word* alignment, int32_t n, float* constrained_median, float* max_duration);
+wk_status wk_truncate_long_words(const wk_word* alignment, int32_t n, float max_duration, wk_words** out);
+/* updateSegmentsWithWordTimings (:528-659): segs[i].start/end are updated in place; segment tokens are
+ * tokens[segs[i].token_offset .. + n_tokens); out = every word with .segment set. */
+wk_status wk_update_segments_with_word_timings(wk_segment* segs, int32_t n_segs, const int32_t* tokens, const wk_word* merged, int32_t n_merged,
+                                               int64_t seek, float last_speech_timestamp, float constrained_median, float max_duration,
+                                               int32_t special_token_begin, const wk_tokenizer_hooks* hooks, wk_words** out);
+/* addWordTimestamps (:410-496), the whole per-window word-timing pass; alignment = [rows][ld] with row i = window token i. */
+wk_status wk_add_word_timestamps(wk_segment* segs, int32_t n_segs, const int32_t* tokens, const float* token_logprobs,
+                                 const void* alignment, int32_t dtype, int32_t rows, int32_t cols, int64_t ld,
+                                 const wk_tokenizer_hooks* hooks, int64_t seek, float last_speech_timestamp, int32_t special_token_begin,
+                                 const char* prepended, const char* appended, wk_words** out);
 
 /* ---- instrumentation ---- */
 /* Number of kernels launched by this library on the calling process since the last reset. */

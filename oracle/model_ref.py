@@ -220,9 +220,13 @@ class WhisperOracle:
     def new_cache(self, batch: int):
         return {"k": [None] * self.dims.dec_layers, "v": [None] * self.dims.dec_layers, "len": 0}
 
-    def decode_step(self, tokens: torch.Tensor, pos: int, cache: dict, cross) -> torch.Tensor:
+    def decode_step(self, tokens: torch.Tensor, pos: int, cache: dict, cross, align_heads=None):
         """One decoder step (mirrors TextDecoder.predictLogits, TextDecoder.swift:361-418):
-        tokens [B] int64 at position `pos` -> logits [B, V] fp32.  Appends to cache."""
+        tokens [B] int64 at position `pos` -> logits [B, V] fp32.  Appends to cache.
+        align_heads = [(layer, head), ...] additionally returns the decoder model's `alignment_heads_weights` output
+        (TextDecoder.swift:310,414): the mean over those heads of the cross-attention softmax row, [B, T] rounded to Float16
+        (FloatType) - openai-whisper's alignment heads (whisper/timing.py find_alignment, model.set_alignment_heads)."""
+        align_acc = None
         w, d = self.w, self.dims
         scale = (d.d_model // d.n_heads) ** -0.5
         x = w["model.decoder.embed_tokens.weight"][tokens] + w["model.decoder.embed_positions.weight"][pos][None]
@@ -246,7 +250,12 @@ class WhisperOracle:
             q = self._heads(self._lin(xn, p + "encoder_attn.q_proj"))
             ck, cv = cross[i]
             s = (q @ ck.transpose(-1, -2)) * scale
-            a = torch.softmax(s, dim=-1) @ cv
+            pr = torch.softmax(s, dim=-1)
+            if align_heads is not None:
+                for (li, hi) in align_heads:
+                    if li == i:
+                        align_acc = pr[:, hi, 0] if align_acc is None else align_acc + pr[:, hi, 0]
+            a = pr @ cv
             a = self.r(a.transpose(1, 2).reshape(x.shape))
             x = x + self._lin(a, p + "encoder_attn.out_proj")
             xn = self.r(self._ln(x, p + "final_layer_norm"))
@@ -254,7 +263,10 @@ class WhisperOracle:
             x = x + self._lin(h, p + "fc2")
         xn = self.r(self._ln(x, "model.decoder.layer_norm"))
         cache["len"] = pos + 1
-        return F.linear(xn[:, 0], w["model.decoder.embed_tokens.weight"])
+        logits = F.linear(xn[:, 0], w["model.decoder.embed_tokens.weight"])
+        if align_heads is not None:
+            return logits, (align_acc / float(len(align_heads))).to(torch.float16).to(torch.float32)
+        return logits
 
 
 def to_hf_state_dict(weights: dict) -> dict:

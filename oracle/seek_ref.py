@@ -36,6 +36,7 @@ class TranscriptionSegment:
     avgLogprob: float = 0.0
     compressionRatio: float = 0.0
     noSpeechProb: float = 0.0
+    words: Optional[list] = None
 
 
 def find_seek_point_and_segments(tokens: Sequence[int], tokenLogProbs: Sequence[float], noSpeechProb: float, avgLogProb: float,
@@ -212,9 +213,12 @@ def vad_chunk_all(audio, maxChunkLength: int, clipTimestamps: Sequence[float] = 
 
 def seek_loop(contentFrames: int, decode_window, clipTimestamps: Sequence[float] = (), windowClipTime: float = 1.0,
               windowSamples: int = 480000, timeToken: int = 50364, noSpeechThreshold: Optional[float] = 0.6,
-              logProbThreshold: Optional[float] = -1.0, maxWindowSeek: Optional[int] = None):
-    """The windowing loop of TranscribeTask.run (TranscribeTask.swift:98-279) without word timestamps.
-    decode_window(seek, segmentSize) -> object with tokens, tokenLogProbs, avgLogProb, compressionRatio, temperature."""
+              logProbThreshold: Optional[float] = -1.0, maxWindowSeek: Optional[int] = None, wordTimestamps=None):
+    """The windowing loop of TranscribeTask.run (TranscribeTask.swift:98-279).
+    decode_window(seek, segmentSize) -> object with tokens, tokenLogProbs, avgLogProb, compressionRatio, temperature.
+    wordTimestamps = dict(alignment=fn(r) -> [rows, 1500] matrix of that window, split=fn(tokens) -> (words, wordTokens),
+    decode=fn(tokens) -> str, specialTokenBegin=int) switches on the addWordTimestamps block (TranscribeTask.swift:197-239)."""
+    from . import words_ref as WR
     allSegments: List[TranscriptionSegment] = []
     windows = []
     for clipStart, clipEnd in prepare_seek_clips(clipTimestamps, contentFrames):
@@ -229,6 +233,23 @@ def seek_loop(contentFrames: int, decode_window, clipTimestamps: Sequence[float]
                                                          noSpeechThreshold, logProbThreshold, len(allSegments), seek, segmentSize,
                                                          SAMPLE_RATE, timeToken)
             seek = max(seek, newSeek)
+            if wordTimestamps is not None:
+                a = np.asarray(wordTimestamps["alignment"](r), dtype=np.float32)
+                n_tok = len(r.tokens)
+                if a.shape[0] < n_tok:                                # rows past the 224-row tensor read as zeros (see csrc/longform.cu)
+                    a = np.concatenate([a, np.zeros((n_tok - a.shape[0], a.shape[1]), np.float32)])
+                upd = WR.add_word_timestamps([WR.Segment(g.start, g.end, g.tokens, g.tokenLogProbs, id=g.id, seek=g.seek) for g in (segs or [])],
+                                             a, wordTimestamps["split"], previousSeek, float(np.float64(previousSeek) / np.float64(SAMPLE_RATE)),
+                                             wordTimestamps["specialTokenBegin"], decode=wordTimestamps.get("decode"))
+                kept = []
+                for g, u in zip(segs or [], upd):
+                    g.start, g.end, g.words = u.start, u.end, u.words
+                    if F(g.end) > F(g.start):                         # filter out zero length segments (:214)
+                        kept.append(g)
+                if segs is not None:
+                    segs = kept
+                if kept:
+                    seek = max(seek, int(F(kept[-1].end) * F(SAMPLE_RATE)))
             if maxWindowSeek is not None:
                 seek = min(seek, previousSeek + maxWindowSeek)
             if seek <= previousSeek:

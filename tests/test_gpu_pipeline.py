@@ -392,3 +392,101 @@ def test_transcribe_streams_seek_loop_matches_oracle_loop():
     assert [g.seek for g in got[0]] == [r.seek for r in ref_all]
     np.testing.assert_allclose([g.start for g in got[0]], [r.start for r in ref_all], atol=1e-4)
     np.testing.assert_allclose([g.end for g in got[0]], [r.end for r in ref_all], atol=1e-4)
+
+
+def _toy_split(tokens, special_begin):
+    """Stand-in for the host tokenizer's splitToWordTokens on the toy vocabulary (same rule as tests/test_word_timestamps_host.py)."""
+    words, groups = [], []
+    for t in tokens:
+        if t >= special_begin:
+            words.append(f"<|{t}|>"); groups.append([t])
+        elif t % 17 == 0:
+            words.append(","); groups.append([t])
+        elif t % 3 == 0 or not words or groups[-1][0] >= special_begin:
+            words.append(" " + chr(97 + t % 26)); groups.append([t])
+        else:
+            words[-1] += chr(97 + t % 26); groups[-1].append(t)
+    return words, groups
+
+
+@pytest.mark.parametrize("policy", ["f16", "bf16"])
+def test_alignment_heads_weights_parity(policy):
+    """wordTimestamps: the decode loop's alignmentWeights tensor (mean cross-attention softmax row of the alignment heads, Float16, row
+    tokenIndex + 1; TextDecoder.swift:272-296,709-717) against the oracle decoder teacher-forced on the GPU's tokens."""
+    B = 3
+    dims, orc, model = build("toy128", policy, B, seed=21)
+    st_o = D.SpecialTokens.toy(dims.vocab)
+    st = wk.SpecialTokens.from_any(st_o)
+    pcm = np.stack([mel_ref.synthetic_pcm(300 + i) for i in range(B)])
+    fe, enc, dec = wk.FeatureExtractor(model), wk.AudioEncoder(model), wk.TextDecoder(model, B)
+    enc_t = enc.encodeFeatures(fe.logMelSpectrogram(pcm))
+    enc_gpu = enc_t.numpy()
+    for heads in ([], [(0, 1), (1, 0), (1, 3)]):
+        model.setAlignmentHeads(heads)
+        ref_heads = heads or [(l, h) for l in range(dims.dec_layers // 2, dims.dec_layers) for h in range(dims.n_heads)]
+        o = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=12, wordTimestamps=True)
+        prompt = dec.prefillDecoderInputs(o, st)
+        res = dec.decodeText(enc_t, prompt, o, st)
+        with torch.no_grad():
+            for b in range(B):
+                toks = res[b].tokens
+                steps = res[b].steps
+                a = dec.alignmentWeights(b, 224)
+                assert np.all(a[0] == 0) and np.all(a[steps + 1:] == 0)       # row 0 and unreached rows stay zero
+                written = steps if a[steps].any() else steps - 1                # the completing step writes no row (TextDecoder.swift:668-674)
+                cross = orc.cross_kv(torch.from_numpy(enc_gpu[b:b + 1]).transpose(1, 2).contiguous())
+                cache = orc.new_cache(1)
+                worst = 0.0
+                assert written >= 3
+                for i in range(written):
+                    _, al = orc.decode_step(torch.tensor([toks[i]]), i, cache, cross, align_heads=ref_heads)
+                    worst = max(worst, rel_err(a[i + 1], al[0].numpy()))
+                    assert abs(float(a[i + 1].sum()) - 1.0) < 5e-3               # a mean of softmax rows
+                print(f"[{policy}] alignment rows rel err {worst:.2e}")
+                assert worst <= (2e-2 if policy == "bf16" else 4e-3), worst
+    o0 = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=12)
+    dec.decodeText(enc_t, prompt, o0, st)
+    with pytest.raises(wk.WhisperError):
+        dec.alignmentWeights(0, 4)                                              # last decode did not ask for word timestamps
+    dec.close()
+    model.close()
+
+
+def test_transcribe_streams_word_timestamps_match_oracle_loop():
+    """wk_transcribe_streams with wordTimestamps (device alignment export -> DTW -> word timings -> segment/seek update) against the
+    oracle's seek loop + oracle word timing (oracle/words_ref.py) fed the same GPU decode results and alignment tensors."""
+    from oracle import seek_ref as S
+    from whisperkit_b200 import longform as L
+    st_o = D.SpecialTokens.toy(1024)
+    kit = wk.WhisperKit(wk.WhisperKitConfig(model="toy", maxBatch=4, seed=9, specialTokens=wk.SpecialTokens.from_any(st_o)))
+    o = wk.DecodingOptions(firstTokenLogProbThreshold=None, logProbThreshold=None, compressionRatioThreshold=None, sampleLength=24,
+                           temperatureFallbackCount=0, wordTimestamps=True)
+    SB = st_o.specialTokenBegin
+    split = lambda t: _toy_split(t, SB)                                          # noqa: E731
+    dec_fn = lambda t: "".join(chr(97 + v % 26) for v in t)                       # noqa: E731
+    lens = [480000 + 200000, 250000, 900000]
+    streams = [np.concatenate([mel_ref.synthetic_pcm(400 + 10 * i + k) for k in range(2)])[:n].astype(np.float32) for i, n in enumerate(lens)]
+    got, windows = L.transcribe_streams(kit, streams, o, split_to_word_tokens=split, decode=dec_fn)
+    n_words = 0
+    for i, x in enumerate(streams):
+        def decode_window(seek, size):
+            w = np.zeros(480000, np.float32)
+            w[:size] = x[seek:seek + size]
+            r = kit.transcribe(w[None], o, samplesPerWindow=[size])[0]
+            r.alignment = kit.textDecoder.alignmentWeights(0, min(len(r.tokens), 224))
+            return r
+        ref, wins = S.seek_loop(len(x), decode_window, timeToken=st_o.timeTokenBegin, noSpeechThreshold=o.noSpeechThreshold,
+                                logProbThreshold=o.logProbThreshold,
+                                wordTimestamps=dict(alignment=lambda r: r.alignment, split=split, decode=dec_fn, specialTokenBegin=SB))
+        assert [g.tokens for g in got[i]] == [r.tokens for r in ref], i
+        assert [g.seek for g in got[i]] == [r.seek for r in ref]
+        np.testing.assert_array_equal(np.float32([g.start for g in got[i]]), np.float32([r.start for r in ref]))
+        np.testing.assert_array_equal(np.float32([g.end for g in got[i]]), np.float32([r.end for r in ref]))
+        for g, r in zip(got[i], ref):
+            assert [w.word for w in g.words] == [w.word for w in r.words]
+            assert [w.tokens for w in g.words] == [w.tokens for w in r.words]
+            np.testing.assert_array_equal(np.float32([w.start for w in g.words]), np.float32([w.start for w in r.words]))
+            np.testing.assert_array_equal(np.float32([w.end for w in g.words]), np.float32([w.end for w in r.words]))
+            np.testing.assert_allclose([w.probability for w in g.words], [w.probability for w in r.words], atol=1e-6)
+            n_words += len(g.words)
+    assert n_words > 10

@@ -61,6 +61,7 @@ class wk_decode_opts(C.Structure):
         ("has_no_speech_threshold", C.c_int32), ("no_speech_threshold", C.c_float),
         ("seed", C.c_uint64),
         ("temperature_fallback_count", C.c_int32), ("temperature_increment_on_fallback", C.c_float),
+        ("word_timestamps", C.c_int32),
     ]
 
 
@@ -77,6 +78,19 @@ class wk_segment(C.Structure):
     _fields_ = [("stream", C.c_int32), ("id", C.c_int32), ("seek", C.c_int64), ("start", C.c_float), ("end", C.c_float),
                 ("token_offset", C.c_int64), ("n_tokens", C.c_int32), ("temperature", C.c_float), ("avg_logprob", C.c_float),
                 ("compression_ratio", C.c_float), ("no_speech_prob", C.c_float)]
+
+
+class wk_word(C.Structure):
+    _fields_ = [("word", C.c_char_p), ("tokens", C.POINTER(C.c_int32)), ("n_tokens", C.c_int32), ("start", C.c_float), ("end", C.c_float),
+                ("probability", C.c_float), ("segment", C.c_int32)]
+
+
+SPLIT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_char), C.c_int32, C.POINTER(C.c_int32), C.c_int32)
+DECODE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_char), C.c_int32)
+
+
+class wk_tokenizer_hooks(C.Structure):
+    _fields_ = [("split_to_word_tokens", SPLIT_FN), ("decode", DECODE_FN), ("user", C.c_void_p)]
 
 
 # every symbol include/wkb200.h declares: (name, restype, argtypes)
@@ -123,13 +137,29 @@ SYMBOLS = [
     ("wk_vad_active_chunks", I32, [P, I64, I32, I32, F32, PI64, I32, PI32]),
     ("wk_vad_chunk_all", I32, [P, I64, I64, PF32, I32, I64, I32, I32, F32, PI64, I32, PI32]),
     ("wk_transcribe_streams", I32, [P, P, C.POINTER(P), PI64, I32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), PI32, I32,
-                                    PF32, I32, F32, I64, I32, C.POINTER(P)]),
+                                    PF32, I32, F32, I64, I32, C.POINTER(wk_tokenizer_hooks), C.POINTER(P)]),
     ("wk_transcription_segment_count", I32, [P]),
     ("wk_transcription_window_count", I32, [P]),
     ("wk_transcription_token_count", I64, [P]),
     ("wk_transcription_segments", I32, [P, C.POINTER(wk_segment), I32]),
     ("wk_transcription_tokens", I32, [P, PI32, PF32, I64]),
+    ("wk_transcription_word_count", I32, [P]),
+    ("wk_transcription_word", I32, [P, I32, C.POINTER(wk_word)]),
     ("wk_transcription_free", None, [P]),
+    ("wk_model_set_alignment_heads", I32, [P, PI32, I32]),
+    ("wk_session_alignment_weights", I32, [P, I32, I32, PF32]),
+    ("wk_words_count", I32, [P]),
+    ("wk_words_get", I32, [P, I32, C.POINTER(wk_word)]),
+    ("wk_words_free", None, [P]),
+    ("wk_dtw", I32, [P, I32, I32, I32, I64, PI32, PI32, I32, PI32]),
+    ("wk_find_alignment", I32, [C.POINTER(wk_word), I32, P, I32, I32, I32, I64, PF32, I32, C.POINTER(P)]),
+    ("wk_merge_punctuations", I32, [C.POINTER(wk_word), I32, C.c_char_p, C.c_char_p, C.POINTER(P)]),
+    ("wk_word_duration_constraints", I32, [C.POINTER(wk_word), I32, PF32, PF32]),
+    ("wk_truncate_long_words", I32, [C.POINTER(wk_word), I32, F32, C.POINTER(P)]),
+    ("wk_update_segments_with_word_timings", I32, [C.POINTER(wk_segment), I32, PI32, C.POINTER(wk_word), I32, I64, F32, F32, F32, I32,
+                                                   C.POINTER(wk_tokenizer_hooks), C.POINTER(P)]),
+    ("wk_add_word_timestamps", I32, [C.POINTER(wk_segment), I32, PI32, PF32, P, I32, I32, I32, I64, C.POINTER(wk_tokenizer_hooks), I64, F32, I32,
+                                     C.c_char_p, C.c_char_p, C.POINTER(P)]),
     ("wk_kernel_launch_count", I64, [I32]),
     ("wk_last_timings", I32, [P, PF32]),
     ("wk_model_stream", P, [P]),

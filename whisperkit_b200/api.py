@@ -87,6 +87,7 @@ class DecodingOptions:
     firstTokenLogProbThreshold: Optional[float] = -1.5
     noSpeechThreshold: Optional[float] = 0.6
     concurrentWorkerCount: int = 16
+    wordTimestamps: bool = False
     seed: int = 0
 
     def to_c(self):
@@ -126,6 +127,7 @@ class DecodingOptions:
         o.seed = int(self.seed)
         o.temperature_fallback_count = int(self.temperatureFallbackCount)
         o.temperature_increment_on_fallback = float(self.temperatureIncrementOnFallback)
+        o.word_timestamps = int(self.wordTimestamps)
         return o, keep
 
 
@@ -211,6 +213,12 @@ class Model:
         for k, v in weights.items():
             self.set_tensor(k, v)
         check(self.lib.wk_model_finalize(self.handle))
+
+    def setAlignmentHeads(self, pairs: Sequence[Sequence[int]]) -> None:
+        """(layer, head) pairs averaged into `alignment_heads_weights`; [] restores the default (all heads of the last half of the layers)."""
+        flat = [int(v) for p in pairs for v in p]
+        arr = (C.c_int32 * max(1, len(flat)))(*flat)
+        check(self.lib.wk_model_set_alignment_heads(self.handle, arr, len(flat) // 2))
 
     def init_random(self, seed: int = 0, std: float = 0.02) -> None:
         check(self.lib.wk_model_init_random(self.handle, seed, std))
@@ -391,6 +399,12 @@ class TextDecoder:
         lp = (C.c_float * self.batch)()
         check(self.lib.wk_detect_language(self.handle, C.byref(st), lang, len(allLanguageTokens), float(temperature), tok, lp))
         return list(tok), list(lp)
+
+    def alignmentWeights(self, window: int, rows: int = MAX_TOKEN_CONTEXT) -> np.ndarray:
+        """DecodingResult.cache.alignmentWeights of one window of the last decodeText(wordTimestamps: true): [rows, 1500] (Float16 values)."""
+        out = np.empty((rows, self.model.info.n_audio_ctx), dtype=np.float32)
+        check(self.lib.wk_session_alignment_weights(self.handle, window, rows, _ptr(out)))
+        return out
 
     def lastLogits(self) -> np.ndarray:
         out = np.empty((self.batch, self.logitsSize), dtype=np.float32)

@@ -419,7 +419,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
                                const T* __restrict__ kcross, const T* __restrict__ vcross, T* __restrict__ out, int B, int H,
-                               int Tlen) {
+                               int Tlen, float* __restrict__ align_scratch, uint32_t align_mask) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                                   // kCrossStages * 16000
     float* scores = reinterpret_cast<float*>(smem + kCrossStages * kCrossStageBytes);  // [Tlen]
@@ -510,6 +510,12 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
     if (lane == 0) red[warp] = sm;
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    if (align_scratch != nullptr && ((align_mask >> h) & 1u)) {
+        // alignment head: export the normalised softmax row (word timestamps); slot = rank of h among the layer's alignment heads
+        const int slot = __popc(align_mask & ((1u << h) - 1u));
+        float* dst = align_scratch + ((long long)slot * B + b) * Tlen;
+        for (int t = tid; t < Tlen; t += 128) dst[t] = scores[t] * inv;
+    }
 
     // V phase: out[d] = sum_t p[t] V[t][d]
     float acc[8];
@@ -555,8 +561,31 @@ static size_t cross_smem_bytes(int T) {
     return (size_t)kCrossStages * kCrossStageBytes + (size_t)((T + 3) & ~3) * 4 + 64 * 4 + (4 * 64 + 32) * 4 + 2 * kCrossStages * 8 + 64;
 }
 
+__global__ void decoder_align_mean_kernel(const float* __restrict__ scratch, int n_slots, const int32_t* __restrict__ step,
+                                          const int32_t* __restrict__ done, __half* __restrict__ out, int B, int Tlen, int max_rows) {
+    const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    // launched after the sampler advanced the step: *step = tokenIndex + 1 = the row of this step's slice; a window whose segment just
+    // completed (or completed earlier) gets no row - the reference breaks out of its loop before updateAlignmentWeights
+    // (TextDecoder.swift:668-674,709-717)
+    const int row = *step;
+    if (t >= Tlen || row >= max_rows || done[b]) return;
+    float a = 0.f;
+    for (int s = 0; s < n_slots; ++s) a += scratch[((long long)s * B + b) * Tlen + t];   // fixed order: deterministic
+    out[((long long)b * max_rows + row) * Tlen + t] = __float2half(a / (float)n_slots);
+}
+
+wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* step, const int32_t* done, void* out_f16, int B, int T,
+                             int max_rows, cudaStream_t stream) {
+    launch_k(decoder_align_mean_kernel, dim3((T + 255) / 256, B), dim3(256), 0, stream, false, scratch, n_slots, step, done, (__half*)out_f16, B, T, max_rows);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decoder_align_mean launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
+}
+
 wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
-                                  const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream) {
+                                  const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
+                                  float* align_scratch, uint32_t align_mask) {
     if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
     const size_t smem = cross_smem_bytes(T);
     static bool attr_set[2] = {false, false};
@@ -569,9 +598,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
         attr_set[ti] = true;
     }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T);
+        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, align_scratch, align_mask);
     else
-        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T);
+        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, align_scratch, align_mask);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_cross_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }

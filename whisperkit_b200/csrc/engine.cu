@@ -118,6 +118,8 @@ struct wk_model {
     void* h1 = nullptr;        // f16 [Bm][3002][d]
     float* x = nullptr;        // f32 [Bm*1500][d]
     void* xn = nullptr; void* qkv = nullptr; void* attn = nullptr; void* ffn = nullptr; void* enc_out = nullptr;
+    // alignment heads (word timestamps): per decoder layer a head bit mask and the first scratch slot of the layer
+    std::vector<uint32_t> align_mask; std::vector<int> align_base; int n_align_slots = 0;
     float timings[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8];
     wk_tensor mel_tensor, enc_tensor;
@@ -141,6 +143,9 @@ struct Lane {
     cudaGraphExec_t graph_exec = nullptr;
     long long launches_per_step = 0;
     int gemm_max_stages = 0;
+    // word timestamps: per-head softmax rows of the current step, and the [Bs][224][T] Float16 alignmentWeights tensor
+    float* align_scratch = nullptr; void* align_w = nullptr; int align_slots = 0; bool align_on = false;
+    void* align_keep = nullptr;   // alignment of windows already final while the fallback ladder re-decodes the chunk
 };
 
 struct wk_session {
@@ -419,8 +424,10 @@ static wk_status decoder_forward(Lane* s, int prompt_len, int ts_begin, const in
         WK_CHECK(dec_gemm(s, l.wo, d, d, s->attn, &sp));
         WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.bo, l.lnx.g, l.lnx.b, s->x, s->xn, B, d, dt, st));
         WK_CHECK(dec_gemm(s, l.wcq, d, d, s->xn, &sp));
+        const bool align = s->align_on && !explicit_pos && m->align_mask[li] != 0;
         WK_CHECK(decoder_cross_attention(s->partial, sp, Bp, l.bcq, (char*)s->cross_kv + (size_t)(2 * li) * cross_block,
-                                         (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st));
+                                         (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st,
+                                         align ? s->align_scratch + (size_t)m->align_base[li] * B * T : nullptr, align ? m->align_mask[li] : 0u));
         WK_CHECK(dec_gemm(s, l.wco, d, d, s->attn, &sp));
         WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.bco, l.ln3.g, l.ln3.b, s->x, s->xn, B, d, dt, st));
         WK_CHECK(dec_gemm(s, l.w1, 4 * d, d, s->xn, &sp));
@@ -536,6 +543,7 @@ wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model**
     WK_CUDA_CHECK(cudaSetDevice(device));
     wk_model* m = new wk_model();
     m->cfg = *cfg;
+    wk_model_set_alignment_heads(m, nullptr, 0);
     m->device = device;
     cudaDeviceProp prop;
     WK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -981,7 +989,7 @@ static void lane_free(Lane* s) {
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
                     s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.step, s->st.n_done, s->st.input_ids,
-                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev};
+                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev, s->align_scratch, s->align_w, s->align_keep};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -1301,11 +1309,26 @@ wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_de
         WK_CHECK(upload_suppress(ln, st, o, &sp[li].n_suppress));
         if (ln->graph_exec) { cudaGraphExecDestroy(ln->graph_exec); ln->graph_exec = nullptr; }
         ln->launches_per_step = 0;
+        ln->align_on = o->word_timestamps != 0;
+        if (ln->align_on) {
+            const size_t T = m->cfg.n_audio_ctx;
+            if (!ln->align_w || ln->align_slots != m->n_align_slots) {
+                if (ln->align_scratch) { cudaFree(ln->align_scratch); ln->align_scratch = nullptr; }
+                if (!ln->align_w) WK_CUDA_CHECK(cudaMalloc(&ln->align_w, (size_t)ln->max_batch * kKvMaxLen * T * 2));
+                WK_CUDA_CHECK(cudaMalloc((void**)&ln->align_scratch, (size_t)m->n_align_slots * ln->max_batch * T * 4));
+                ln->align_slots = m->n_align_slots;
+            }
+            WK_CUDA_CHECK(cudaMemsetAsync(ln->align_w, 0, (size_t)ln->batch * kKvMaxLen * T * 2, ln->stream));   // row 0 and unreached rows stay 0
+        }
     }
     auto one_step = [&](int li) -> wk_status {
         Lane* ln = s->lane[li];
         WK_CHECK(decoder_forward(ln, n_prompt, st->time_token_begin, nullptr));
-        return sampler_filter_sample(ln->logits, m->cfg.vocab, sp[li], ln->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, ln->batch, ln->stream);
+        WK_CHECK(sampler_filter_sample(ln->logits, m->cfg.vocab, sp[li], ln->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, ln->batch, ln->stream));
+        if (ln->align_on)
+            WK_CHECK(decoder_align_mean(ln->align_scratch, m->n_align_slots, ln->st.step, ln->st.done, ln->align_w, ln->batch, m->cfg.n_audio_ctx,
+                                        kKvMaxLen, ln->stream));
+        return WK_OK;
     };
     for (int step = 0; step < loop_count; ++step) {
         bool redo = false;
@@ -1376,6 +1399,26 @@ wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_de
     return WK_OK;
 }
 
+// word timestamps across the fallback ladder: align_w belongs to the LAST decode; align_keep collects, per window, the alignment of
+// the decode whose result was kept.  window < 0 = every bound window; to_keep = align_w -> align_keep, else back.
+static wk_status align_keep_copy(wk_session* s, int window, bool to_keep) {
+    const size_t T = s->m->cfg.n_audio_ctx, block = (size_t)kKvMaxLen * T * 2;
+    for (int li = 0; li < s->n_lanes; ++li) {
+        Lane* ln = s->lane[li];
+        if (ln->batch == 0 || !ln->align_w) continue;
+        if (!ln->align_keep) WK_CUDA_CHECK(cudaMalloc(&ln->align_keep, (size_t)ln->max_batch * block));
+        int b0 = 0, nb = ln->batch;
+        if (window >= 0) {
+            if (window < ln->b0 || window >= ln->b0 + ln->batch) continue;
+            b0 = window - ln->b0; nb = 1;
+        }
+        char* w = (char*)ln->align_w + (size_t)b0 * block;
+        char* k = (char*)ln->align_keep + (size_t)b0 * block;
+        WK_CUDA_CHECK(cudaMemcpyAsync(to_keep ? k : w, to_keep ? w : k, (size_t)nb * block, cudaMemcpyDeviceToDevice, ln->stream));
+    }
+    return WK_OK;
+}
+
 wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_host, int64_t n_windows, int64_t stride,
                                 const int32_t* samples_per_window, const wk_special_tokens* st, const wk_decode_opts* opts,
                                 const int32_t* prompt, int32_t n_prompt, wk_decode_result* results) {
@@ -1411,10 +1454,13 @@ wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_hos
         WK_CHECK(wk_decode_text(s, st, opts, prompt, n_prompt, results + w0));   // returns with both lanes drained
         // decodeWithFallback (TranscribeTask.swift:316-411): the encoder output and cross-attention K/V of the chunk stay bound;
         // only the token loop reruns, at Float16(temperature) + Float16(i) * Float16(increment) (:327), for windows that ask.
+        bool retried = false;
         for (int i = 1; i <= opts->temperature_fallback_count; ++i) {
             bool any = false;
             for (int64_t b = 0; b < nb; ++b) any |= results[w0 + b].needs_fallback != 0;
             if (!any) break;
+            if (opts->word_timestamps && !retried) WK_CHECK(align_keep_copy(s, -1, true));   // alignment of every window of the first pass
+            retried = true;
             wk_decode_opts o2 = *opts;
             const float f16_t = __half2float(__float2half(opts->temperature));
             const float f16_step = __half2float(__float2half(__half2float(__float2half((float)i)) * __half2float(__float2half(opts->temperature_increment_on_fallback))));
@@ -1423,8 +1469,12 @@ wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_hos
             std::vector<wk_decode_result> retry((size_t)nb);
             WK_CHECK(wk_decode_text(s, st, &o2, prompt, n_prompt, retry.data()));
             for (int64_t b = 0; b < nb; ++b)
-                if (results[w0 + b].needs_fallback) results[w0 + b] = retry[b];
+                if (results[w0 + b].needs_fallback) {
+                    results[w0 + b] = retry[b];
+                    if (opts->word_timestamps) WK_CHECK(align_keep_copy(s, (int)b, true));   // this window's alignment now comes from the retry
+                }
         }
+        if (opts->word_timestamps && retried) WK_CHECK(align_keep_copy(s, -1, false));
         WK_CUDA_CHECK(cudaEventRecord(m->ev[5], m->stream));
         WK_CUDA_CHECK(cudaEventSynchronize(m->ev[5]));
         float t;
@@ -1435,6 +1485,52 @@ wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_hos
         cudaEventElapsedTime(&t, m->ev[4], m->ev[5]); acc[3] += t;
     }
     memcpy(m->timings, acc, sizeof(acc));
+    return WK_OK;
+}
+
+static void default_alignment_heads(wk_model* m) {
+    // openai-whisper's default when a checkpoint names no alignment heads: every head of the last half of the decoder layers
+    const int L = m->cfg.dec_layers, H = m->cfg.n_heads;
+    m->align_mask.assign(L, 0u);
+    m->align_base.assign(L, 0);
+    int slots = 0;
+    for (int l = 0; l < L; ++l) {
+        m->align_base[l] = slots;
+        if (l >= L / 2) { m->align_mask[l] = H >= 32 ? 0xffffffffu : ((1u << H) - 1u); slots += H; }
+    }
+    m->n_align_slots = slots;
+}
+
+wk_status wk_model_set_alignment_heads(wk_model* m, const int32_t* layer_head_pairs, int32_t n_pairs) {
+    if (!m || n_pairs < 0 || (n_pairs > 0 && !layer_head_pairs)) { set_error("wk_model_set_alignment_heads: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    if (n_pairs == 0) { default_alignment_heads(m); return WK_OK; }
+    const int L = m->cfg.dec_layers, H = m->cfg.n_heads;
+    std::vector<uint32_t> mask(L, 0u);
+    for (int i = 0; i < n_pairs; ++i) {
+        const int l = layer_head_pairs[2 * i], h = layer_head_pairs[2 * i + 1];
+        if (l < 0 || l >= L || h < 0 || h >= H || h >= 32) { set_error("wk_model_set_alignment_heads: (layer %d, head %d) out of range", l, h); return WK_ERR_INVALID_ARGUMENT; }
+        mask[l] |= 1u << h;
+    }
+    m->align_mask = mask;
+    m->align_base.assign(L, 0);
+    int slots = 0;
+    for (int l = 0; l < L; ++l) { m->align_base[l] = slots; slots += __builtin_popcount(mask[l]); }
+    m->n_align_slots = slots;
+    return WK_OK;
+}
+
+wk_status wk_session_alignment_weights(wk_session* s, int32_t window, int32_t rows, float* out) {
+    if (!s || !out || window < 0 || window >= s->batch || rows < 0 || rows > kKvMaxLen) { set_error("wk_session_alignment_weights: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    Lane* ln = s->lane[0];
+    for (int li = 0; li < s->n_lanes; ++li)
+        if (s->lane[li]->batch > 0 && window >= s->lane[li]->b0 && window < s->lane[li]->b0 + s->lane[li]->batch) ln = s->lane[li];
+    if (!ln->align_on || !ln->align_w) { set_error("wk_session_alignment_weights: the last decode did not ask for word timestamps"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
+    const size_t T = s->m->cfg.n_audio_ctx;
+    std::vector<__half> h((size_t)rows * T);
+    WK_CUDA_CHECK(cudaMemcpyAsync(h.data(), (const __half*)ln->align_w + (size_t)(window - ln->b0) * kKvMaxLen * T, h.size() * 2, cudaMemcpyDeviceToHost, ln->stream));
+    WK_CUDA_CHECK(cudaStreamSynchronize(ln->stream));
+    for (size_t i = 0; i < h.size(); ++i) out[i] = __half2float(h[i]);
     return WK_OK;
 }
 

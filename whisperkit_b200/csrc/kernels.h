@@ -134,8 +134,16 @@ wk_status decoder_self_attention(const float* partial, int splits, int Bp, const
                                  void* vcache, const int32_t* step, const int32_t* explicit_pos, void* out, int B, int H,
                                  int max_len, int dtype, cudaStream_t stream);
 // cross attention over T encoder positions; reduces q partials [S][Bp][d]; K/V [B][H][T][64]
+// align_scratch != nullptr: heads h with bit h of align_mask set also write their softmax row (f32, [slot][B][T], slot = rank of h in
+// the mask) - the alignment heads behind the reference decoder's `alignment_heads_weights` output (TextDecoder.swift:310,414)
 wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
-                                  const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream);
+                                  const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
+                                  float* align_scratch = nullptr, uint32_t align_mask = 0);
+// alignment row of the step just sampled (run AFTER the sampler advanced *step to tokenIndex + 1): out[b][*step][t] =
+// Float16(mean over n_slots of scratch[slot][b][t]) unless done[b] (TextDecoder.updateAlignmentWeights, TextDecoder.swift:272-296:
+// the slice of step tokenIndex lands in row tokenIndex + 1; a completed segment breaks out before the update, :668-674)
+wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* step, const int32_t* done, void* out_f16, int B, int T,
+                             int max_rows, cudaStream_t stream);
 wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
                                 int ld_tokens, const int32_t* n_tokens, int32_t* token_out, float* logprob_out,
                                 float* filtered_out, int B, cudaStream_t stream);

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -221,8 +222,16 @@ wk_status wk_vad_chunk_all(const float* wav, int64_t n, int64_t max_chunk_len, c
 // =====================================================================================================
 // batched seek loop
 // =====================================================================================================
+struct OutWord {
+    std::string word;
+    std::vector<int32_t> tokens;
+    float start, end, probability;
+    int segment;
+};
+
 struct wk_transcription {
     std::vector<wk_segment> segments;
+    std::vector<OutWord> words;   // .segment indexes `segments`
     std::vector<int32_t> tokens;
     std::vector<float> logprobs;
     int windows = 0;
@@ -239,6 +248,7 @@ struct Unit {                 // one independently advancing cursor: a stream, o
     int64_t seek = 0;
     bool done = false;
     std::vector<wk_segment> segs;
+    std::vector<OutWord> words;   // word timings; .segment indexes `segs`
 };
 }  // namespace
 
@@ -247,8 +257,9 @@ extern "C" {
 wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* audio, const int64_t* n_samples, int32_t n_streams,
                                 const wk_special_tokens* st, const wk_decode_opts* o, const int32_t* prompt, int32_t n_prompt,
                                 const float* cts, int32_t n_cts, float window_clip_time, int64_t max_window_seek, int32_t chunking_vad,
-                                wk_transcription** out) {
+                                const wk_tokenizer_hooks* hooks, wk_transcription** out) {
     if (!m || !s || !audio || !n_samples || n_streams < 1 || !st || !o || !prompt || !out) { set_error("wk_transcribe_streams: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    if (o->word_timestamps && (!hooks || !hooks->split_to_word_tokens)) { set_error("wk_transcribe_streams: wordTimestamps needs the tokenizer's split_to_word_tokens hook"); return WK_ERR_INVALID_ARGUMENT; }
     wk_model_info info;
     wk_status rc = wk_model_info_get(m, &info);
     if (rc != WK_OK) return rc;
@@ -317,8 +328,40 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
             const int64_t prev = u.seek;
             u.seek = std::max(u.seek, new_seek);
             if (max_window_seek >= 0) u.seek = std::min(u.seek, prev + max_window_seek);
+            std::vector<OutWord> new_words;
+            if (o->word_timestamps) {
+                // addWordTimestamps on this window (TranscribeTask.swift:197-239): rows = window tokens, zero rows past the tensor's 224
+                const int cols = info.n_audio_ctx, n_tok = r.n_tokens, have = std::min(n_tok, info.kv_max_len);
+                std::vector<float> align((size_t)std::max(n_tok, 1) * cols, 0.f);
+                rc = wk_session_alignment_weights(s, (int32_t)k, have, align.data());
+                if (rc != WK_OK) { delete T; return rc; }
+                wk_words* wh = nullptr;
+                const int n_in = std::max(nseg, 0);
+                rc = wk_add_word_timestamps(segs, n_in, r.tokens, r.token_logprobs, align.data(), WK_DTYPE_F32, std::max(n_tok, 1), cols, cols, hooks, prev,
+                                            (float)((double)prev / (double)kSampleRate), st->special_token_begin, nullptr, nullptr, &wh);
+                if (rc != WK_OK) { delete T; return rc; }
+                // drop zero-length segments (:214), remap the words' segment index, and let the last word end pull the seek forward (:217-219)
+                std::vector<int> remap((size_t)n_in, -1);
+                int kept = 0;
+                for (int g = 0; g < n_in; ++g)
+                    if (segs[g].end > segs[g].start) { remap[g] = kept; segs[kept++] = segs[g]; }
+                for (int i = 0; i < wk_words_count(wh); ++i) {
+                    wk_word w;
+                    wk_words_get(wh, i, &w);
+                    if (w.segment < 0 || remap[w.segment] < 0) continue;
+                    OutWord ow;
+                    ow.word = w.word; ow.tokens.assign(w.tokens, w.tokens + w.n_tokens);
+                    ow.start = w.start; ow.end = w.end; ow.probability = w.probability; ow.segment = remap[w.segment];
+                    new_words.push_back(std::move(ow));
+                }
+                wk_words_free(wh);
+                if (nseg >= 0) nseg = kept;
+                if (kept > 0) u.seek = std::max(u.seek, (int64_t)(segs[kept - 1].end * (float)kSampleRate));
+                if (max_window_seek >= 0) u.seek = std::min(u.seek, prev + max_window_seek);
+            }
             // termination guard (not in the reference, which can spin when a window decodes to <|0.00|><|0.00|>): always move on
             if (u.seek <= prev) u.seek = prev + seg_size[k];
+            for (OutWord& w : new_words) { w.segment += (int)u.segs.size(); u.words.push_back(std::move(w)); }
             for (int g = 0; g < nseg; ++g) {
                 wk_segment sg = segs[g];
                 const int64_t base = (int64_t)unit_tokens[active[k]].size();
@@ -346,6 +389,11 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
         const int64_t base = (int64_t)T->tokens.size();
         T->tokens.insert(T->tokens.end(), unit_tokens[i].begin(), unit_tokens[i].end());
         T->logprobs.insert(T->logprobs.end(), unit_lps[i].begin(), unit_lps[i].end());
+        const int seg_base = (int)T->segments.size();
+        for (OutWord w : u.words) {
+            w.start += seek_time; w.end += seek_time; w.segment += seg_base;
+            T->words.push_back(std::move(w));
+        }
         for (wk_segment sg : u.segs) {
             sg.id = next_id[u.stream]++;
             sg.seek += u.offset;
@@ -371,6 +419,14 @@ wk_status wk_transcription_tokens(const wk_transcription* t, int32_t* tokens, fl
     if (!t || cap < (int64_t)t->tokens.size()) { set_error("wk_transcription_tokens: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
     if (tokens && !t->tokens.empty()) memcpy(tokens, t->tokens.data(), t->tokens.size() * 4);
     if (logprobs && !t->logprobs.empty()) memcpy(logprobs, t->logprobs.data(), t->logprobs.size() * 4);
+    return WK_OK;
+}
+int32_t wk_transcription_word_count(const wk_transcription* t) { return t ? (int32_t)t->words.size() : 0; }
+wk_status wk_transcription_word(const wk_transcription* t, int32_t i, wk_word* out) {
+    if (!t || !out || i < 0 || i >= (int32_t)t->words.size()) { set_error("wk_transcription_word: index out of range"); return WK_ERR_INVALID_ARGUMENT; }
+    const OutWord& w = t->words[i];
+    out->word = w.word.c_str(); out->tokens = w.tokens.data(); out->n_tokens = (int32_t)w.tokens.size();
+    out->start = w.start; out->end = w.end; out->probability = w.probability; out->segment = w.segment;
     return WK_OK;
 }
 void wk_transcription_free(wk_transcription* t) { delete t; }

@@ -28,6 +28,7 @@ class TranscriptionSegment:
     avgLogprob: float
     compressionRatio: float
     noSpeechProb: float
+    words: Optional[list] = None
 
 
 def _segs(raw, n, tokens, lps, rel=0) -> List[TranscriptionSegment]:
@@ -139,7 +140,7 @@ class VADAudioChunker:
 
 def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional[DecodingOptions] = None,
                        clipTimestamps: Sequence[float] = (), windowClipTime: float = 1.0, maxWindowSeek: Optional[int] = None,
-                       chunkingStrategy: Optional[str] = None):
+                       chunkingStrategy: Optional[str] = None, split_to_word_tokens=None, decode=None):
     """TranscribeTask.run's seek loop for many audio arrays at once (TranscribeTask.swift:98-279; `chunkingStrategy="vad"`
     = WhisperKit.swift:878-911).  Returns (segments per stream, number of 30 s windows decoded)."""
     opts = options or DecodingOptions()
@@ -154,9 +155,12 @@ def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional
     n = len(clipTimestamps)
     ts = (C.c_float * max(1, n))(*[float(v) for v in clipTimestamps])
     h = C.c_void_p()
+    from .wordtiming import WordTiming, make_hooks
+    hooks, keep_hooks = make_hooks(split_to_word_tokens, decode)
     check(lib.wk_transcribe_streams(kit.model.handle, kit.textDecoder.handle, ptrs, lens, len(arrs), C.byref(st), C.byref(o), p, len(prompt),
                                     ts, n, windowClipTime, -1 if maxWindowSeek is None else maxWindowSeek,
-                                    1 if chunkingStrategy == "vad" else 0, C.byref(h)))
+                                    1 if chunkingStrategy == "vad" else 0, C.byref(hooks) if split_to_word_tokens is not None else None,
+                                    C.byref(h)))
     try:
         ns, nt = lib.wk_transcription_segment_count(h), lib.wk_transcription_token_count(h)
         raw = (wk_segment * max(1, ns))()
@@ -165,6 +169,14 @@ def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional
         lp = (C.c_float * max(1, nt))()
         check(lib.wk_transcription_tokens(h, tk, lp, max(1, nt)))
         segs = _segs(raw, ns, tk, lp)
+        if opts.wordTimestamps:
+            for g in segs:
+                g.words = []
+            w = _lib.wk_word()
+            for i in range(lib.wk_transcription_word_count(h)):
+                check(lib.wk_transcription_word(h, i, C.byref(w)))
+                segs[w.segment].words.append(WordTiming(w.word.decode("utf-8"), [int(w.tokens[k]) for k in range(w.n_tokens)], float(w.start),
+                                                        float(w.end), float(w.probability), int(w.segment)))
         windows = lib.wk_transcription_window_count(h)
     finally:
         lib.wk_transcription_free(h)
