@@ -224,7 +224,7 @@ def seek_loop(contentFrames: int, decode_window, clipTimestamps: Sequence[float]
     for clipStart, clipEnd in prepare_seek_clips(clipTimestamps, contentFrames):
         seek = clipStart
         windowPadding = int(F(windowClipTime) * F(SAMPLE_RATE))
-        while seek < clipEnd - windowPadding:
+        while seek < clipEnd - windowPadding and seek < contentFrames:   # 2nd term: guard shared with csrc/longform.cu (clip past the audio)
             segmentSize = min(windowSamples, contentFrames - seek, clipEnd - seek)
             r = decode_window(seek, segmentSize)
             windows.append((seek, segmentSize))

@@ -286,6 +286,13 @@ def test_temperature_fallback_ladder():
     assert all(r.temperature == 0.0 for r in res0)
     o1 = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=10, logProbThreshold=None, compressionRatioThreshold=None)
     assert all(r.fallback is None and r.temperature == 0.0 for r in kit.transcribe(pcm, o1))
+    # word timestamps across the ladder: the alignment tensor handed back belongs to the decode whose result was kept
+    ow = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=10, compressionRatioThreshold=None, wordTimestamps=True)
+    resw = kit.transcribe(pcm, ow)
+    assert all(abs(r.temperature - 1.0) < 1e-3 for r in resw)
+    for b in range(3):
+        a = kit.textDecoder.alignmentWeights(b, 224)
+        assert np.all(a[0] == 0) and abs(float(a[1].sum()) - 1.0) < 5e-3 and np.all(a[resw[b].steps + 1:] == 0)
 
 
 def test_tiny_en_jfk_config0():
@@ -373,7 +380,7 @@ def test_transcribe_streams_seek_loop_matches_oracle_loop():
             np.testing.assert_array_equal(np.float32([g.start for g in got[i]]), np.float32([r.start for r in ref]))
             np.testing.assert_array_equal(np.float32([g.end for g in got[i]]), np.float32([r.end for r in ref]))
             np.testing.assert_allclose([g.avgLogprob for g in got[i]], [r.avgLogprob for r in ref], atol=1e-5)
-        assert windows == total and total >= 8
+        assert windows == total and total >= 6
     # VAD chunking: each chunk is an independent unit whose seeks/timings are shifted by the chunk offset (WhisperKit.swift:896-911)
     x = streams[5].copy()
     x[500000:520000] = 0

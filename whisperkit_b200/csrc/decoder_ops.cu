@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include <algorithm>
 #include "kernels.h"
 
 namespace wk {
@@ -587,7 +588,10 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
                                   const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
                                   float* align_scratch, uint32_t align_mask) {
     if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
-    const size_t smem = cross_smem_bytes(T);
+    size_t smem = cross_smem_bytes(T);
+    // WKB200_CROSS_SMEM_KB pads the request so that fewer CTAs fit per SM, leaving shared memory for another lane's GEMM CTAs
+    static const int pad_kb = getenv("WKB200_CROSS_SMEM_KB") ? atoi(getenv("WKB200_CROSS_SMEM_KB")) : 0;
+    if (pad_kb > 0 && pad_kb <= 100) smem = std::max(smem, (size_t)pad_kb * 1024);
     static bool attr_set[2] = {false, false};
     const int ti = dtype == WK_DTYPE_F16 ? 1 : 0;
     if (!attr_set[ti]) {

@@ -285,9 +285,11 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
             rc = wk_prepare_seek_clips(chunking_vad ? nullptr : cts, chunking_vad ? 0 : n_cts, u.n, u.clips.data(), (int)u.clips.size() / 2, &nc);
             if (rc != WK_OK) return rc;
             u.clips.resize(2 * nc);
+            // a clip is live while seek < clipEnd - windowPadding (TranscribeTask.swift:118) and, as a guard the reference lacks (it would
+            // pad a negative-length window), while the seek is still inside the audio
             u.seek = u.clips[0];
-            u.done = !(u.seek < u.clips[1] - window_padding);
-            while (u.done && u.clip + 1 < nc) { ++u.clip; u.seek = u.clips[2 * u.clip]; u.done = !(u.seek < u.clips[2 * u.clip + 1] - window_padding); }
+            u.done = !(u.seek < u.clips[1] - window_padding && u.seek < u.n);
+            while (u.done && u.clip + 1 < nc) { ++u.clip; u.seek = u.clips[2 * u.clip]; u.done = !(u.seek < u.clips[2 * u.clip + 1] - window_padding && u.seek < u.n); }
             units.push_back(std::move(u));
         }
     }
@@ -374,7 +376,7 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
                 u.segs.push_back(sg);
             }
             const int nclips = (int)u.clips.size() / 2;
-            while (!(u.seek < u.clips[2 * u.clip + 1] - window_padding)) {
+            while (!(u.seek < u.clips[2 * u.clip + 1] - window_padding && u.seek < u.n)) {
                 if (u.clip + 1 >= nclips) { u.done = true; break; }
                 ++u.clip;
                 u.seek = u.clips[2 * u.clip];
