@@ -147,7 +147,7 @@ SYMBOLS = [
     ("wk_transcription_word", I32, [P, I32, C.POINTER(wk_word)]),
     ("wk_transcription_free", None, [P]),
     ("wk_model_set_alignment_heads", I32, [P, PI32, I32]),
-    ("wk_session_alignment_weights", I32, [P, I32, I32, PF32]),
+    ("wk_session_alignment_weights", I32, [P, I32, I32, P]),
     ("wk_words_count", I32, [P]),
     ("wk_words_get", I32, [P, I32, C.POINTER(wk_word)]),
     ("wk_words_free", None, [P]),
