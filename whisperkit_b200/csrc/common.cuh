@@ -203,10 +203,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 
 // Host-side launcher: cudaLaunchKernelEx with the PDL attribute when enabled (WKB200_NO_PDL=1 disables it).
 bool pdl_enabled();
+int pdl_mode();   // WKB200_PDL: 0 off (default), 1 every kernel of the decode step, 2 GEMM + split-K reduce kernels only, 3 reduce kernels only
 void pdl_disable();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
-                            Args&&... args) {
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int pdl,
+                            Args&&... args) {   // pdl: 0 never, 1 attention/sampler/embed class, 2 GEMM, 3 split-K reduce
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -217,7 +218,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    const int mode = pdl_mode();
+    cfg.numAttrs = (pdl > 0 && mode > 0 && (mode == 1 || pdl >= mode)) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -212,9 +212,9 @@ wk_status decoder_reduce_resid_ln(const float* partial, int splits, int Bp, cons
         return WK_ERR_INVALID_ARGUMENT;
     }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_reduce_resid_ln_kernel<__half>, dim3(B), dim3(kReduceThreads), 0, stream, true, partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
+        launch_k(decoder_reduce_resid_ln_kernel<__half>, dim3(B), dim3(kReduceThreads), 0, stream, 3, partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
     else
-        launch_k(decoder_reduce_resid_ln_kernel<__nv_bfloat16>, dim3(B), dim3(kReduceThreads), 0, stream, true, partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
+        launch_k(decoder_reduce_resid_ln_kernel<__nv_bfloat16>, dim3(B), dim3(kReduceThreads), 0, stream, 3, partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_reduce_resid_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -253,9 +253,9 @@ wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, con
     const long long threads = (long long)B * n / 4;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_reduce_bias_gelu_kernel<__half>, dim3(grid), dim3(256), 0, stream, true, partial, splits, Bp, bias, (__half*)out, B, n);
+        launch_k(decoder_reduce_bias_gelu_kernel<__half>, dim3(grid), dim3(256), 0, stream, 3, partial, splits, Bp, bias, (__half*)out, B, n);
     else
-        launch_k(decoder_reduce_bias_gelu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, true, partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
+        launch_k(decoder_reduce_bias_gelu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 3, partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_reduce_bias_gelu launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }

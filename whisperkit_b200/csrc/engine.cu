@@ -31,10 +31,14 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 static int g_pdl = -1;
-bool pdl_enabled() {
-    if (g_pdl < 0) g_pdl = getenv("WKB200_PDL") ? 1 : 0;   // measured slower on B200 (1491 vs 1388 ms/step): opt-in only
-    return g_pdl == 1;
+int pdl_mode() {
+    // Programmatic dependent launch along the decode step.  Measured on B200 (64 windows, 63 steps): off 495 ms/step, every kernel (1) 489,
+    // GEMM + split-K reduce kernels only (2) 480, reduce kernels only (3) 488 -> default 2: those kernels have a real prologue (TMEM
+    // alloc, barrier init, tensor-map prefetch, first weight tiles) to hide under the upstream kernel's tail; attention kernels do not.
+    if (g_pdl < 0) g_pdl = getenv("WKB200_PDL") ? std::max(0, atoi(getenv("WKB200_PDL"))) : 2;
+    return g_pdl;
 }
+bool pdl_enabled() { return pdl_mode() > 0; }
 void pdl_disable() { g_pdl = 0; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -159,11 +163,16 @@ struct wk_session {
 namespace wk {
 
 static int choose_splits(int tiles, int total_kb, int num_sms) {
+    // Split-K depth of a decoder swap-AB GEMM: the deepest split that still fits ONE wave of CTAs (tiles * s <= SMs), so every SM that
+    // takes part streams its share of the weights exactly once.  Measured with HBM-cold weights on B200 (tools/microbench_cold.py,
+    // 64 windows): one SM sustains only ~40 GB/s, so too few CTAs starve (d x d: s=1 11.0 us, s=10 6.1 us) while a second wave costs
+    // more than it saves (FC1: s=2 8.5 us, s=4 9.6 us; QKV: s=4 7.3 us, s=5 9.1 us; FC2: s=10 8.1 us, s=20 9.4 us).
+    static const int force = getenv("WKB200_FORCE_SPLITS") ? atoi(getenv("WKB200_FORCE_SPLITS")) : 0;  // microbenchmarks only
+    if (force > 0 && force <= 20 && total_kb % force == 0) return force;
     int best = 1;
     for (int s = 1; s <= total_kb && s <= 20; ++s) {   // 20 = kMaxSplits of the fused reduce kernels
         if (total_kb % s) continue;
-        best = s;
-        if (tiles * s >= (num_sms * 13) / 20) break;  // >= 0.65 * SMs pulling weights; fewer partials to reduce
+        if (tiles * s <= num_sms) best = s;
     }
     return best;
 }
@@ -396,7 +405,7 @@ static wk_status dec_gemm(Lane* s, const void* w, int N, int K, const void* act,
     const int tiles = (N + 127) / 128;
     g.splits = choose_splits(tiles, K / 64, m->num_sms);
     g.mode = GEMM_OUT_PARTIAL_T; g.out = s->partial; g.ld_out = N; g.out_rows_per_batch = N; g.partial_cols = s->bp;
-    g.pdl = 1;
+    g.pdl = 1; g.a_static = 1;
     if ((size_t)g.splits * s->bp * N > s->partial_elems) { set_error("partial workspace too small"); return WK_ERR_DECODING_FAILED; }
     *splits_out = g.splits;
     g.max_stages = s->gemm_max_stages;
@@ -444,7 +453,7 @@ static wk_status decoder_forward(Lane* s, int prompt_len, int ts_begin, const in
         g.b = s->xn; g.b_rows = Bp; g.b_ld = d; g.in_dtype = dt;
         g.m_rows_per_batch = c.vocab; g.n = Bp; g.k = d; g.taps = 1; g.bn = Bp; g.splits = 1;
         g.mode = GEMM_OUT_PARTIAL_T; g.out = s->logits; g.ld_out = c.vocab; g.out_rows_per_batch = c.vocab; g.partial_cols = B;
-        g.pdl = 1;
+        g.pdl = 1; g.a_static = 1;
         g.max_stages = s->gemm_max_stages;
         WK_CHECK(gemm_tcgen05(g, m->num_sms, st));
     }
@@ -1627,6 +1636,19 @@ wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t bat
                       if (!pos100) { std::vector<int32_t> h(256, 100); cudaMalloc(&pos100, 256 * 4); cudaMemcpy(pos100, h.data(), 256 * 4, cudaMemcpyHostToDevice); }
                       return decoder_self_attention(ln->partial, 1, round_up(B, 16), m->dec[0].bq, m->dec[0].bv, ln->self_k, ln->self_v, ln->st.step, pos100,
                                                     ln->attn, B, H, kKvMaxLen, dt, st); }
+            // 14-17: the decoder GEMMs with the weights rotating over all layers, so they stream from HBM as in a real step
+            case 14: case 15: case 16: case 17: {
+                if (!ln) return WK_ERR_INVALID_ARGUMENT;
+                static int rot = 0;
+                const int r = rot++;
+                const DecLayer& l = m->dec[r % c.dec_layers];
+                ln->bp = round_up(B, 16);
+                int sp;
+                if (which == 14) { const void* w3[3] = {l.wo, l.wcq, l.wco}; return dec_gemm(ln, w3[(r / c.dec_layers) % 3], d, d, ln->attn, &sp); }
+                if (which == 15) return dec_gemm(ln, l.w1, 4 * d, d, ln->xn, &sp);
+                if (which == 16) return dec_gemm(ln, l.w2, d, 4 * d, ln->ffn, &sp);
+                return dec_gemm(ln, l.wqkv, 3 * d, d, ln->xn, &sp);
+            }
             default: set_error("wk_bench_kernel: unknown kernel %d", which); return WK_ERR_INVALID_ARGUMENT;
         }
     };

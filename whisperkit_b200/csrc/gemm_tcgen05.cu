@@ -54,6 +54,7 @@ struct GemmKParams {
     int heads_T, heads_B, heads_H, heads_dmodel;
     int debug_mode;   // 0 normal; 1 exit after setup; 2 skip the epilogue stores (latency decomposition, WKB200_GEMM_DEBUG)
     int tmem_cols;
+    int a_static;     // see GemmDesc::a_static
 };
 
 template <typename T>
@@ -96,7 +97,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                // upstream results visible from here on (barrier init / TMEM alloc overlapped its tail)
+    // upstream results visible from here on (barrier init / TMEM alloc overlapped its tail).  With a static A operand the producer warp
+    // waits later, after it has put the first weight tiles in flight; every other warp only sees data that arrived after that wait.
+    const bool early_a = p.a_static != 0 && p.debug_mode == 0;
+    if (!(early_a && warp == 0)) pdl_wait();
 
     if (p.debug_mode == 1) {
         __syncthreads();
@@ -108,6 +112,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            bool need_wait = early_a;
+            auto issue = [&](int kb, int st, int row0, int batch, int n_tile, bool do_a, bool do_b) {
+                const int tap = kb / p.kb_per_tap;
+                const int kk = kb - tap * p.kb_per_tap;
+                uint8_t* sa = smem + (size_t)st * stage_bytes;
+                uint8_t* sb = sa + kStageA;
+                if (do_a) {
+                    mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+                    const int ac0 = p.tap_col_off[tap] + kk * kBlockK;
+                    const int ar = row0 + p.tap_row_shift[tap];
+                    if (p.a_is_3d) tma_load_3d(sa, &tmA, &full_bar[st], ac0, ar, batch);
+                    else tma_load_2d(sa, &tmA, &full_bar[st], ac0, ar);
+                }
+                if (do_b) tma_load_2d(sb, &tmB, &full_bar[st], kb * kBlockK, n_tile * p.bn);
+            };
             for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
                 const int split = w % p.splits;
                 const int t = w / p.splits;
@@ -116,21 +135,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int batch = m_tile / p.tiles_per_batch;
                 const int row0 = (m_tile % p.tiles_per_batch) * kBlockM;
                 const int kb0 = split * p.kb_per_split;
-                for (int kb = kb0; kb < kb0 + p.kb_per_split; ++kb) {
-                    const int tap = kb / p.kb_per_tap;
-                    const int kk = kb - tap * p.kb_per_tap;
+                int kb = kb0;
+                if (need_wait) {
+                    // first work item, fresh ring: weight tiles go out before griddepcontrol.wait, activation tiles after it
+                    const int n_pre = p.kb_per_split < p.stages ? p.kb_per_split : p.stages;
+                    for (int i = 0; i < n_pre; ++i) issue(kb0 + i, i, row0, batch, n_tile, true, false);
+                    pdl_wait();
+                    for (int i = 0; i < n_pre; ++i) issue(kb0 + i, i, row0, batch, n_tile, false, true);
+                    kb = kb0 + n_pre;
+                    if (n_pre == p.stages) { stage = 0; phase ^= 1; } else stage = n_pre;
+                    need_wait = false;
+                }
+                for (; kb < kb0 + p.kb_per_split; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + kStageA;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                    const int ac0 = p.tap_col_off[tap] + kk * kBlockK;
-                    const int ar = row0 + p.tap_row_shift[tap];
-                    if (p.a_is_3d) tma_load_3d(sa, &tmA, &full_bar[stage], ac0, ar, batch);
-                    else tma_load_2d(sa, &tmA, &full_bar[stage], ac0, ar);
-                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_tile * p.bn);
+                    issue(kb, stage, row0, batch, n_tile, true, true);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
+            if (need_wait) pdl_wait();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -380,6 +402,8 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
     p.tmem_cols = kTmemCols;
     if (p.work <= num_sms) { int c = 32; while (c < d.bn) c <<= 1; p.tmem_cols = c; }
     if (const char* e = getenv("WKB200_GEMM_TMEM")) p.tmem_cols = atoi(e);
+    static const bool early_a_off = getenv("WKB200_EARLY_A") && atoi(getenv("WKB200_EARLY_A")) == 0;   // A/B knob
+    p.a_static = early_a_off ? 0 : d.a_static;
     p.mode = d.mode;
     p.gelu = d.gelu;
     p.out = d.out;
@@ -423,7 +447,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             attr_set = true;
         }
-        e = launch_k(gemm_tcgen05_kernel<__half>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0, tmA, tmB, p);
+        e = launch_k(gemm_tcgen05_kernel<__half>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0 ? 2 : 0, tmA, tmB, p);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
@@ -431,7 +455,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             attr_set = true;
         }
-        e = launch_k(gemm_tcgen05_kernel<__nv_bfloat16>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0, tmA, tmB, p);
+        e = launch_k(gemm_tcgen05_kernel<__nv_bfloat16>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0 ? 2 : 0, tmA, tmB, p);
     }
     count_launch();
     e = cudaGetLastError();
