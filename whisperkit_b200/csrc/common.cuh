@@ -203,11 +203,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 
 // Host-side launcher: cudaLaunchKernelEx with the PDL attribute when enabled (WKB200_NO_PDL=1 disables it).
 bool pdl_enabled();
-int pdl_mode();   // WKB200_PDL: 0 off (default), 1 every kernel of the decode step, 2 GEMM + split-K reduce kernels only, 3 reduce kernels only
+// Bit mask of the kernel classes launched as programmatic dependents: 1 embed, 2 self-attention, 4 cross-attention, 8 sampler/advance,
+// 16 GEMM, 32 split-K reduce.  Default 53; WKB200_PDL = 0 off, 1 all (63), 2 GEMM + reduce (48), 3 reduce only; WKB200_PDL_MASK overrides.
+int pdl_mode();
 void pdl_disable();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int pdl,
-                            Args&&... args) {   // pdl: 0 never, 1 attention/sampler/embed class, 2 GEMM, 3 split-K reduce
+                            Args&&... args) {   // pdl: 0 never, else the class bit (see pdl_mode)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -218,8 +220,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    const int mode = pdl_mode();
-    cfg.numAttrs = (pdl > 0 && mode > 0 && (mode == 1 || pdl >= mode)) ? 1 : 0;
+    cfg.numAttrs = (pdl & pdl_mode()) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -130,9 +130,9 @@ wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gam
                            const int32_t* explicit_pos, cudaStream_t stream) {
     if (d > 2048) { set_error("decoder_embed_ln: d_model %d > 2048", d); return WK_ERR_INVALID_ARGUMENT; }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_embed_ln_kernel<__half>, dim3(B), dim3(256), 0, stream, true, (const __half*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__half*)xn, d, explicit_inputs, explicit_pos);
+        launch_k(decoder_embed_ln_kernel<__half>, dim3(B), dim3(256), 0, stream, 1, (const __half*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__half*)xn, d, explicit_inputs, explicit_pos);
     else
-        launch_k(decoder_embed_ln_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, stream, true, (const __nv_bfloat16*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_inputs, explicit_pos);
+        launch_k(decoder_embed_ln_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, stream, 1, (const __nv_bfloat16*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_inputs, explicit_pos);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_embed_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -212,9 +212,9 @@ wk_status decoder_reduce_resid_ln(const float* partial, int splits, int Bp, cons
         return WK_ERR_INVALID_ARGUMENT;
     }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_reduce_resid_ln_kernel<__half>, dim3(B), dim3(kReduceThreads), 0, stream, 3, partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
+        launch_k(decoder_reduce_resid_ln_kernel<__half>, dim3(B), dim3(kReduceThreads), 0, stream, 32, partial, splits, Bp, bias, gamma, beta, x, (__half*)xn, d);
     else
-        launch_k(decoder_reduce_resid_ln_kernel<__nv_bfloat16>, dim3(B), dim3(kReduceThreads), 0, stream, 3, partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
+        launch_k(decoder_reduce_resid_ln_kernel<__nv_bfloat16>, dim3(B), dim3(kReduceThreads), 0, stream, 32, partial, splits, Bp, bias, gamma, beta, x, (__nv_bfloat16*)xn, d);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_reduce_resid_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -253,9 +253,9 @@ wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, con
     const long long threads = (long long)B * n / 4;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_reduce_bias_gelu_kernel<__half>, dim3(grid), dim3(256), 0, stream, 3, partial, splits, Bp, bias, (__half*)out, B, n);
+        launch_k(decoder_reduce_bias_gelu_kernel<__half>, dim3(grid), dim3(256), 0, stream, 32, partial, splits, Bp, bias, (__half*)out, B, n);
     else
-        launch_k(decoder_reduce_bias_gelu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 3, partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
+        launch_k(decoder_reduce_bias_gelu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 32, partial, splits, Bp, bias, (__nv_bfloat16*)out, B, n);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_reduce_bias_gelu launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -396,9 +396,9 @@ wk_status decoder_self_attention(const float* partial, int splits, int Bp, const
     if (max_len > kMaxCtx) { set_error("decoder_self_attention: max_len %d > %d", max_len, kMaxCtx); return WK_ERR_INVALID_ARGUMENT; }
     const unsigned grid = (unsigned)((B * H + 3) / 4);
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, true, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, step, explicit_pos, (__half*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, step, explicit_pos, (__half*)out, B, H, max_len);
     else
-        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, true, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, step, explicit_pos, (__nv_bfloat16*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, step, explicit_pos, (__nv_bfloat16*)out, B, H, max_len);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_self_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -438,16 +438,12 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
         for (int i = 0; i < kCrossStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
         fence_barrier_init();
     }
-    pdl_wait();
-    if (tid < 64) {
-        float q = bq[h * 64 + tid];
-        for (int s = 0; s < splits; ++s) q += partial[((long long)s * Bp + b) * dm + h * 64 + tid];
-        sq[tid] = q * 0.125f;
-    }
     __syncthreads();
 
     if (warp == 4) {
         // ---------------- producer ----------------
+        // no griddepcontrol.wait here: the cross K/V cache is written once before the decode loop starts, so when this kernel is
+        // launched as a programmatic dependent the first K chunks are already in flight while the upstream GEMM drains
         if (lane == 0) {
             const uint8_t* kb = reinterpret_cast<const uint8_t*>(kcross + (long long)bh * Tlen * 64);
             const uint8_t* vb = reinterpret_cast<const uint8_t*>(vcross + (long long)bh * Tlen * 64);
@@ -463,6 +459,13 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
         return;
     }
     // ---------------- consumers (128 threads) ----------------
+    pdl_wait();                      // the q partials come from the upstream GEMM
+    if (tid < 64) {
+        float q = bq[h * 64 + tid];
+        for (int s = 0; s < splits; ++s) q += partial[((long long)s * Bp + b) * dm + h * 64 + tid];
+        sq[tid] = q * 0.125f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int sub = lane & 7;        // 16-byte piece of the 128-byte row: dims sub*8 .. sub*8+7
     const int rsel = lane >> 3;      // row within a group of 4
     float qv[8];
@@ -577,7 +580,7 @@ __global__ void decoder_align_mean_kernel(const float* __restrict__ scratch, int
 
 wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* step, const int32_t* done, void* out_f16, int B, int T,
                              int max_rows, cudaStream_t stream) {
-    launch_k(decoder_align_mean_kernel, dim3((T + 255) / 256, B), dim3(256), 0, stream, false, scratch, n_slots, step, done, (__half*)out_f16, B, T, max_rows);
+    launch_k(decoder_align_mean_kernel, dim3((T + 255) / 256, B), dim3(256), 0, stream, 0, scratch, n_slots, step, done, (__half*)out_f16, B, T, max_rows);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_align_mean launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -602,9 +605,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
         attr_set[ti] = true;
     }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, align_scratch, align_mask);
+        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, align_scratch, align_mask);
     else
-        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, true, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, align_scratch, align_mask);
+        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, align_scratch, align_mask);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_cross_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -866,11 +869,11 @@ wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerP
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(sampler): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
         attr_set = true;
     }
-    launch_k(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, stream, true, logits, (long long)ld_logits, p, st, tokens, ld_tokens,
+    launch_k(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, stream, 8, logits, (long long)ld_logits, p, st, tokens, ld_tokens,
              n_tokens, token_out, logprob_out, filtered_out);
     count_launch();
     if (p.prompt_len >= 0) {
-        launch_k(advance_step_kernel, dim3(1), dim3(1), 0, stream, true, st);
+        launch_k(advance_step_kernel, dim3(1), dim3(1), 0, stream, 8, st);
         count_launch();
     }
     cudaError_t e = cudaGetLastError();

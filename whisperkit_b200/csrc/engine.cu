@@ -32,10 +32,15 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static int g_pdl = -1;
 int pdl_mode() {
-    // Programmatic dependent launch along the decode step.  Measured on B200 (64 windows, 63 steps): off 495 ms/step, every kernel (1) 489,
-    // GEMM + split-K reduce kernels only (2) 480, reduce kernels only (3) 488 -> default 2: those kernels have a real prologue (TMEM
-    // alloc, barrier init, tensor-map prefetch, first weight tiles) to hide under the upstream kernel's tail; attention kernels do not.
-    if (g_pdl < 0) g_pdl = getenv("WKB200_PDL") ? std::max(0, atoi(getenv("WKB200_PDL"))) : 2;
+    // Programmatic dependent launch along the decode step.  Measured on B200 (64 windows, 63 steps, ms per hot-path pass): off 495-498,
+    // every kernel (63) 480-489, GEMM + split-K reduce (48) 480-481, reduce only (32) 488; on top of 48: + cross-attention (its K chunks
+    // are static and prefetched before griddepcontrol.wait) 473, + embed 478, + self-attention 486 (worse), + sampler 481 (neutral).
+    // Default 53 = embed | cross-attention | GEMM | reduce: the kernels with a real prologue to hide under the upstream kernel's tail.
+    if (g_pdl < 0) {
+        static const int by_mode[4] = {0, 63, 48, 32};
+        g_pdl = getenv("WKB200_PDL") ? by_mode[std::min(3, std::max(0, atoi(getenv("WKB200_PDL"))))] : 53;
+        if (const char* e = getenv("WKB200_PDL_MASK")) g_pdl = (int)strtol(e, nullptr, 0) & 63;
+    }
     return g_pdl;
 }
 bool pdl_enabled() { return pdl_mode() > 0; }

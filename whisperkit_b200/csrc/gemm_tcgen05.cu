@@ -447,7 +447,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             attr_set = true;
         }
-        e = launch_k(gemm_tcgen05_kernel<__half>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0 ? 2 : 0, tmA, tmB, p);
+        e = launch_k(gemm_tcgen05_kernel<__half>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0 ? 16 : 0, tmA, tmB, p);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
@@ -455,7 +455,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
             attr_set = true;
         }
-        e = launch_k(gemm_tcgen05_kernel<__nv_bfloat16>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0 ? 2 : 0, tmA, tmB, p);
+        e = launch_k(gemm_tcgen05_kernel<__nv_bfloat16>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, d.pdl != 0 ? 16 : 0, tmA, tmB, p);
     }
     count_launch();
     e = cudaGetLastError();
