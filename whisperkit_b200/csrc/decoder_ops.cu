@@ -307,12 +307,33 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     skc[warp][e] = kr.x; skc[warp][e + 1] = kr.y;
     svc[warp][e] = vr.x; svc[warp][e + 1] = vr.y;
     __syncwarp();
-    // scores: lane handles keys lane, lane+32, ...
+    // scores: lane handles keys lane, lane+32, ...; the cache row of key i+1 is fetched while key i is reduced (double-buffered
+    // registers), and the first V tile is put in flight before any of it: the kernel is latency-bound, not bandwidth-bound
+    const int sub = lane & 7, rsel = lane >> 3;
+    const T* vb = vcache + (long long)bh * max_len * 64 + sub * 8;
+    uint4 u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = 4 * j + rsel;
+        u[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + (long long)t * 64) : make_uint4(0u, 0u, 0u, 0u);
+    }
     float smax = -INFINITY;
     float sc[7];
+    uint4 kbuf[2][8];
+    {
+        const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)bh * max_len + lane) * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) kbuf[0][c] = (lane < pos) ? kp[c] : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const int t = lane + 32 * i;
+        if (i + 1 < 7) {
+            const int tn = t + 32;
+            const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)bh * max_len + tn) * 64);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) kbuf[(i + 1) & 1][c] = (tn < pos) ? kp[c] : make_uint4(0u, 0u, 0u, 0u);
+        }
         sc[i] = -INFINITY;
         if (t <= pos) {
             float acc = 0.f;
@@ -320,11 +341,10 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
 #pragma unroll 16
                 for (int j = 0; j < 64; ++j) acc += sq[warp][j] * skc[warp][j];
             } else {
-                const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)bh * max_len + t) * 64);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 u = kp[c];
-                    const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+                    const uint4 kv = kbuf[i & 1][c];
+                    const float2 a0 = T16<T>::unpack2(kv.x), a1 = T16<T>::unpack2(kv.y), a2 = T16<T>::unpack2(kv.z), a3 = T16<T>::unpack2(kv.w);
                     const float* qq = &sq[warp][c * 8];
                     acc += qq[0] * a0.x + qq[1] * a0.y + qq[2] * a1.x + qq[3] * a1.y + qq[4] * a2.x + qq[5] * a2.y + qq[6] * a3.x + qq[7] * a3.y;
                 }
@@ -346,18 +366,17 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     }
     ssum = warp_sum(ssum);
     __syncwarp();
-    // output: 16-byte loads, 4 cache rows per warp instruction, 8 instructions in flight: lane = (row % 4, 8-dim chunk)
-    const int sub = lane & 7, rsel = lane >> 3;
+    // output: 16-byte loads, 4 cache rows per warp instruction, 8 instructions in flight: lane = (row % 4, 8-dim chunk); the next
+    // tile of 32 rows is fetched while the current one is accumulated
     float o8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o8[j] = 0.f;
-    const T* vb = vcache + (long long)bh * max_len * 64 + sub * 8;
     for (int t0 = 0; t0 < pos; t0 += 32) {
-        uint4 u[8];
+        uint4 un[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int t = t0 + 4 * j + rsel;
-            u[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + (long long)t * 64) : make_uint4(0u, 0u, 0u, 0u);
+            const int t = t0 + 32 + 4 * j + rsel;
+            un[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + (long long)t * 64) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -367,6 +386,8 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
             o8[0] += p * a0.x; o8[1] += p * a0.y; o8[2] += p * a1.x; o8[3] += p * a1.y;
             o8[4] += p * a2.x; o8[5] += p * a2.y; o8[6] += p * a3.x; o8[7] += p * a3.y;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = un[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
