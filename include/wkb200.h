@@ -305,6 +305,30 @@ wk_status wk_add_word_timestamps(wk_segment* segs, int32_t n_segs, const int32_t
                                  const wk_tokenizer_hooks* hooks, int64_t seek, float last_speech_timestamp, int32_t special_token_begin,
                                  const char* prepended, const char* appended, wk_words** out);
 
+/* ---- tokenizer, decode side: ids -> text without a Swift host ----
+ * Byte-level BPE decode as swift-transformers does it (Tokenizer.swift:510-530, Decoder.swift:126-170): added tokens verbatim, the rest
+ * through the GPT-2 byte alphabet into lossy UTF-8, then cleanUp; WhisperTokenizerWrapper's special-token lookups and word splitting
+ * (Models.swift:1201-1306).  Text -> ids (merges, pre-tokenizer) is NOT built: prompts arrive as token ids. */
+typedef struct wk_tokenizer wk_tokenizer;
+/* path: a checkpoint directory (tokenizer.json, else vocab.json + added_tokens.json), or one of those files. */
+wk_status wk_tokenizer_load(const char* path, wk_tokenizer** out);
+/* From memory: flags bit 0 = added token (emitted verbatim), bit 1 = special (dropped by skip_special_tokens). */
+wk_status wk_tokenizer_create(const char* const* tokens, const int32_t* ids, const uint8_t* flags, int32_t n, int32_t clean_up_tokenization_spaces,
+                              wk_tokenizer** out);
+void wk_tokenizer_free(wk_tokenizer* t);
+int32_t wk_tokenizer_vocab_size(const wk_tokenizer* t);
+int32_t wk_tokenizer_token_to_id(const wk_tokenizer* t, const char* token);   /* convertTokenToId; -1 = nil */
+/* decode(tokens:skipSpecialTokens:): NUL-terminated UTF-8 into text; returns bytes written (without NUL), or -(bytes needed) if cap is short. */
+int32_t wk_tokenizer_decode(const wk_tokenizer* t, const int32_t* tokens, int32_t n, int32_t skip_special_tokens, char* text, int32_t cap);
+/* SpecialTokens as WhisperTokenizerWrapper.init derives them, with its defaults for absent tokens. */
+wk_status wk_tokenizer_special_tokens(const wk_tokenizer* t, wk_special_tokens* out);
+/* splitToWordTokens in the wk_tokenizer_hooks layout (words as consecutive NUL-terminated strings, one token count per word; a NUL
+ * byte inside a decoded word is dropped). */
+int32_t wk_tokenizer_split_to_word_tokens(const wk_tokenizer* t, const int32_t* tokens, int32_t n, char* text, int32_t text_cap, int32_t* counts,
+                                          int32_t counts_cap);
+/* Fills `hooks` with this tokenizer's split / decode so wk_transcribe_streams and wk_add_word_timestamps run without host callbacks. */
+wk_status wk_tokenizer_hooks_init(wk_tokenizer* t, wk_tokenizer_hooks* hooks);
+
 /* ---- instrumentation ---- */
 /* Number of kernels launched by this library on the calling process since the last reset. */
 int64_t wk_kernel_launch_count(int32_t reset);

@@ -160,6 +160,15 @@ SYMBOLS = [
                                                    C.POINTER(wk_tokenizer_hooks), C.POINTER(P)]),
     ("wk_add_word_timestamps", I32, [C.POINTER(wk_segment), I32, PI32, PF32, P, I32, I32, I32, I64, C.POINTER(wk_tokenizer_hooks), I64, F32, I32,
                                      C.c_char_p, C.c_char_p, C.POINTER(P)]),
+    ("wk_tokenizer_load", I32, [C.c_char_p, C.POINTER(P)]),
+    ("wk_tokenizer_create", I32, [C.POINTER(C.c_char_p), PI32, C.POINTER(C.c_uint8), I32, I32, C.POINTER(P)]),
+    ("wk_tokenizer_free", None, [P]),
+    ("wk_tokenizer_vocab_size", I32, [P]),
+    ("wk_tokenizer_token_to_id", I32, [P, C.c_char_p]),
+    ("wk_tokenizer_decode", I32, [P, PI32, I32, I32, C.POINTER(C.c_char), I32]),
+    ("wk_tokenizer_special_tokens", I32, [P, C.POINTER(wk_special_tokens)]),
+    ("wk_tokenizer_split_to_word_tokens", I32, [P, PI32, I32, C.POINTER(C.c_char), I32, PI32, I32]),
+    ("wk_tokenizer_hooks_init", I32, [P, C.POINTER(wk_tokenizer_hooks)]),
     ("wk_kernel_launch_count", I64, [I32]),
     ("wk_last_timings", I32, [P, PF32]),
     ("wk_model_stream", P, [P]),
