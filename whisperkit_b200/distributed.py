@@ -74,3 +74,77 @@ def transcribe_sharded(all_pcm: Optional[torch.Tensor], n_windows: int, stride: 
     shard = scatter_windows(all_pcm, n_windows, stride, device)
     res = transcribe_local(shard)
     return gather_tokens(pack_tokens(res, device), n_windows)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Long-form streams: whole audio streams are the independent units (each advances by its own seek
+# loop), so ranks take whole streams - no collective inside the path, only the edges move data.
+# ---------------------------------------------------------------------------------------------------------------------------------
+def assign_streams(n_samples: List[int], world: int) -> List[List[int]]:
+    """Longest-processing-time-first: streams sorted by length (ties by index) go to the currently lightest rank (ties by rank).
+    Deterministic, so every rank derives the same assignment without communication.  Returns stream indices per rank, ascending."""
+    loads = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in sorted(range(len(n_samples)), key=lambda k: (-int(n_samples[k]), k)):
+        r = min(range(world), key=lambda k: (loads[k], k))
+        out[r].append(i)
+        loads[r] += max(int(n_samples[i]), 1)
+    return [sorted(v) for v in out]
+
+
+SEG_HEAD = 8  # [stream, id, seek_lo, seek_hi, start(f32 bits), end(f32 bits), n_tokens, temperature(f32 bits)]
+
+
+def pack_segments(per_stream: dict, device) -> torch.Tensor:
+    """per_stream {stream index: [segment objects with .id .seek .start .end .tokens .temperature]} -> one int32 row list:
+    every segment is SEG_HEAD header words followed by its tokens; row 0 holds the total length."""
+    words: List[int] = [0]
+    f2i = lambda v: int(torch.tensor(float(v), dtype=torch.float32).view(torch.int32).item())  # noqa: E731
+    for s in sorted(per_stream):
+        for g in per_stream[s]:
+            seek = int(g.seek)
+            words += [int(s), int(g.id), seek & 0x7FFFFFFF, seek >> 31, f2i(g.start), f2i(g.end), len(g.tokens), f2i(getattr(g, "temperature", 0.0))]
+            words += [int(t) for t in g.tokens]
+    words[0] = len(words)
+    return torch.tensor(words, dtype=torch.int32, device=device)
+
+
+def unpack_segments(buf: torch.Tensor) -> dict:
+    from types import SimpleNamespace
+    w = buf.cpu()
+    n = int(w[0])
+    i2f = lambda v: float(torch.tensor(int(v), dtype=torch.int32).view(torch.float32).item())  # noqa: E731
+    out: dict = {}
+    i = 1
+    while i < n:
+        s, sid, lo, hi, st, en, nt, tp = (int(v) for v in w[i:i + SEG_HEAD])
+        toks = [int(v) for v in w[i + SEG_HEAD:i + SEG_HEAD + nt]]
+        out.setdefault(s, []).append(SimpleNamespace(stream=s, id=sid, seek=(hi << 31) | lo, start=i2f(st), end=i2f(en), tokens=toks, temperature=i2f(tp)))
+        i += SEG_HEAD + nt
+    return out
+
+
+def transcribe_streams_sharded(audio_arrays: list, device, transcribe_local: Callable[[list, List[int]], list], dst: int = 0) -> Optional[list]:
+    """Every rank holds (or can load) the audio of its own streams: `audio_arrays[i]` may be None on ranks that do not own stream i, but
+    the LENGTHS must be known everywhere (they decide the assignment).  `transcribe_local(arrays, stream_ids)` -> one segment list per
+    local stream (e.g. whisperkit_b200.longform.transcribe_streams).  Rank `dst` returns the segment lists in global stream order."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lengths = torch.tensor([0 if a is None else len(a) for a in audio_arrays], dtype=torch.int64, device=device)
+    dist.all_reduce(lengths, op=dist.ReduceOp.MAX)          # the only collective before the work: 8 bytes per stream
+    mine = assign_streams([int(v) for v in lengths.cpu()], world)[rank]
+    local = transcribe_local([audio_arrays[i] for i in mine], mine) if mine else []
+    packed = pack_segments({i: segs for i, segs in zip(mine, local)}, device)
+    size = torch.tensor([packed.numel()], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    cap = max(int(s.item()) for s in sizes)
+    pad = torch.zeros(cap, dtype=torch.int32, device=device)
+    pad[: packed.numel()] = packed
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    merged: dict = {}
+    for b in bufs:
+        merged.update(unpack_segments(b))
+    return [merged.get(i, []) for i in range(len(audio_arrays))]
