@@ -497,3 +497,36 @@ def test_transcribe_streams_word_timestamps_match_oracle_loop():
             np.testing.assert_allclose([w.probability for w in g.words], [w.probability for w in r.words], atol=1e-6)
             n_words += len(g.words)
     assert n_words > 10
+    # VAD chunking + word timestamps + maxWindowSeek: every chunk is an independent unit; segment AND word times carry the chunk offset
+    x = streams[2].copy()
+    x[430000:452000] = 0
+    chunks = S.vad_chunk_all(x, 480000)
+    assert len(chunks) >= 2
+    got, _ = L.transcribe_streams(kit, [x], o, chunkingStrategy="vad", split_to_word_tokens=split, decode=dec_fn, maxWindowSeek=400000)
+    ref_all = []
+    for (a, b) in chunks:
+        xc = x[a:b]
+
+        def decode_chunk(seek, size, xc=xc):
+            w = np.zeros(480000, np.float32)
+            w[:size] = xc[seek:seek + size]
+            r = kit.transcribe(w[None], o, samplesPerWindow=[size])[0]
+            r.alignment = kit.textDecoder.alignmentWeights(0, min(len(r.tokens), 224))
+            return r
+        ref, _ = S.seek_loop(len(xc), decode_chunk, timeToken=st_o.timeTokenBegin, noSpeechThreshold=o.noSpeechThreshold,
+                             logProbThreshold=o.logProbThreshold, maxWindowSeek=400000,
+                             wordTimestamps=dict(alignment=lambda r: r.alignment, split=split, decode=dec_fn, specialTokenBegin=SB))
+        off = np.float32(a) / np.float32(16000)
+        for r in ref:
+            r.seek += a
+            r.start, r.end = float(np.float32(r.start) + off), float(np.float32(r.end) + off)
+            for w in r.words:
+                w.start, w.end = float(np.float32(w.start) + off), float(np.float32(w.end) + off)
+        ref_all += ref
+    assert [g.tokens for g in got[0]] == [r.tokens for r in ref_all] and [g.seek for g in got[0]] == [r.seek for r in ref_all]
+    np.testing.assert_allclose([g.start for g in got[0]], [r.start for r in ref_all], atol=1e-4)
+    assert sum(len(g.words) for g in got[0]) > 5
+    for g, r in zip(got[0], ref_all):
+        assert [w.word for w in g.words] == [w.word for w in r.words]
+        np.testing.assert_allclose([w.start for w in g.words], [w.start for w in r.words], atol=1e-4)
+        np.testing.assert_allclose([w.end for w in g.words], [w.end for w in r.words], atol=1e-4)
