@@ -137,7 +137,10 @@ const char* wk_version(void);
 int32_t wk_device_available(void);
 
 /* ---- model ---- */
-void wk_default_config(const char* variant /* "tiny.en","large-v3","large-v3-turbo","distil-large-v3" */, wk_model_config* out);
+void wk_default_config(const char* variant /* tiny[.en] base[.en] small[.en] medium[.en] large large-v2 large-v3 large-v3-turbo distil-large-v3 */,
+                       wk_model_config* out);
+/* ModelUtilities.detectVariant + tokenizerNameForVariant + isModelMultilingual (ModelUtilities.swift:124-205): static strings out. */
+wk_status wk_detect_variant(int32_t logits_dim, int32_t encoder_dim, const char** variant, const char** tokenizer_repo, int32_t* is_multilingual);
 wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model** out);
 /* HuggingFace parameter names ("model.encoder.layers.0.self_attn.q_proj.weight", ...); data host or device. */
 wk_status wk_model_set_tensor(wk_model* m, const char* name, const void* data, int32_t dtype, const int64_t* shape, int32_t ndim);

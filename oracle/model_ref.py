@@ -60,6 +60,8 @@ VARIANTS = {
     # toy shapes for fast CPU tests (not real checkpoints)
     "toy": WhisperDims(80, 128, 2, 2, 2, 1024),
     "toy128": WhisperDims(128, 256, 4, 2, 2, 2048),
+    "toy512": WhisperDims(80, 512, 8, 2, 2, 2048),     # base-width (8 heads)
+    "toy768": WhisperDims(80, 768, 12, 2, 2, 2048),    # small-width (12 heads: a head count that is not a power of two)
 }
 
 

@@ -57,3 +57,23 @@ def test_no_cpu_fallback():
     with pytest.raises(wk.WhisperError) as e:
         wk.Model("toy")
     assert e.value.case == "modelsUnavailable"
+
+
+def test_variant_table_reference_kat():
+    """testTokenizerModelVariantDetection (UnitTests.swift:1101-1124) through wk_detect_variant, and wk_default_config for every variant."""
+    import ctypes as C
+    from whisperkit_b200 import _lib
+    lib = _lib.load()
+    kat = [(51865, 384, "tiny"), (51864, 384, "tiny.en"), (51865, 512, "base"), (51864, 512, "base.en"), (51865, 768, "small"), (51864, 768, "small.en"),
+           (51865, 1024, "medium"), (51864, 1024, "medium.en"), (51865, 1280, "large-v2"), (51866, 1280, "large-v3")]
+    for logits, enc, name in kat:
+        v, repo, ml = C.c_char_p(), C.c_char_p(), C.c_int32()
+        assert lib.wk_detect_variant(logits, enc, C.byref(v), C.byref(repo), C.byref(ml)) == 0
+        assert v.value.decode() == name and repo.value.decode() == "openai/whisper-" + name
+        assert bool(ml.value) == (not name.endswith(".en"))
+        cfg = _lib.wk_model_config()
+        lib.wk_default_config(name.encode(), C.byref(cfg))
+        assert (cfg.vocab, cfg.d_model) == (logits, enc) and cfg.d_model == cfg.n_heads * 64 and cfg.n_mels == (128 if name == "large-v3" else 80)
+    v = C.c_char_p()
+    lib.wk_detect_variant(12345, 999, C.byref(v), None, None)
+    assert v.value.decode() == "base"                                   # unrecognised vocabulary size -> base

@@ -33,7 +33,7 @@ def build(variant, policy, B, seed=5):
     return dims, orc, model
 
 
-@pytest.mark.parametrize("variant,policy", [("toy", "bf16"), ("toy128", "f16"), ("toy128", "bf16")])
+@pytest.mark.parametrize("variant,policy", [("toy", "bf16"), ("toy128", "f16"), ("toy128", "bf16"), ("toy512", "f16"), ("toy768", "f16")])
 def test_encoder_and_logits_parity(variant, policy):
     B = 3
     dims, orc, model = build(variant, policy, B)

@@ -160,6 +160,7 @@ SYMBOLS = [
                                                    C.POINTER(wk_tokenizer_hooks), C.POINTER(P)]),
     ("wk_add_word_timestamps", I32, [C.POINTER(wk_segment), I32, PI32, PF32, P, I32, I32, I32, I64, C.POINTER(wk_tokenizer_hooks), I64, F32, I32,
                                      C.c_char_p, C.c_char_p, C.POINTER(P)]),
+    ("wk_detect_variant", I32, [I32, I32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), PI32]),
     ("wk_tokenizer_load", I32, [C.c_char_p, C.POINTER(P)]),
     ("wk_tokenizer_create", I32, [C.POINTER(C.c_char_p), PI32, C.POINTER(C.c_uint8), I32, I32, C.POINTER(P)]),
     ("wk_tokenizer_free", None, [P]),

@@ -532,13 +532,42 @@ int32_t wk_device_available(void) {
 void wk_default_config(const char* variant, wk_model_config* c) {
     memset(c, 0, sizeof(*c));
     c->n_audio_ctx = 1500; c->n_text_ctx = 448; c->dtype = WK_DTYPE_BF16; c->max_batch = 16;
-    const std::string v = variant ? variant : "large-v3";
-    if (v == "tiny.en" || v == "tiny") { c->n_mels = 80; c->d_model = 384; c->n_heads = 6; c->enc_layers = 4; c->dec_layers = 4; c->vocab = v == "tiny" ? 51865 : 51864; }
-    else if (v == "large-v3-turbo") { c->n_mels = 128; c->d_model = 1280; c->n_heads = 20; c->enc_layers = 32; c->dec_layers = 4; c->vocab = 51866; }
-    else if (v == "distil-large-v3") { c->n_mels = 128; c->d_model = 1280; c->n_heads = 20; c->enc_layers = 32; c->dec_layers = 2; c->vocab = 51866; }
-    else if (v == "toy") { c->n_mels = 80; c->d_model = 128; c->n_heads = 2; c->enc_layers = 2; c->dec_layers = 2; c->vocab = 1024; }
-    else if (v == "toy128") { c->n_mels = 128; c->d_model = 256; c->n_heads = 4; c->enc_layers = 2; c->dec_layers = 2; c->vocab = 2048; }
-    else { c->n_mels = 128; c->d_model = 1280; c->n_heads = 20; c->enc_layers = 32; c->dec_layers = 32; c->vocab = 51866; }
+    std::string v = variant ? variant : "large-v3";
+    // OpenAI Whisper dimensions (external facts; the reference reads them off the CoreML model descriptions)
+    struct Dim { const char* name; int mels, d, heads, enc, dec, vocab; };
+    static const Dim dims[] = {
+        {"tiny", 80, 384, 6, 4, 4, 51865},       {"tiny.en", 80, 384, 6, 4, 4, 51864},       {"base", 80, 512, 8, 6, 6, 51865},
+        {"base.en", 80, 512, 8, 6, 6, 51864},    {"small", 80, 768, 12, 12, 12, 51865},      {"small.en", 80, 768, 12, 12, 12, 51864},
+        {"medium", 80, 1024, 16, 24, 24, 51865}, {"medium.en", 80, 1024, 16, 24, 24, 51864}, {"large", 80, 1280, 20, 32, 32, 51865},
+        {"large-v2", 80, 1280, 20, 32, 32, 51865}, {"large-v3", 128, 1280, 20, 32, 32, 51866}, {"large-v3-turbo", 128, 1280, 20, 32, 4, 51866},
+        {"distil-large-v3", 128, 1280, 20, 32, 2, 51866}, {"toy", 80, 128, 2, 2, 2, 1024},   {"toy128", 128, 256, 4, 2, 2, 2048},
+        {"toy512", 80, 512, 8, 2, 2, 2048}, {"toy768", 80, 768, 12, 2, 2, 2048},
+    };
+    const Dim* d = &dims[10];
+    for (const Dim& e : dims) if (v == e.name) d = &e;
+    c->n_mels = d->mels; c->d_model = d->d; c->n_heads = d->heads; c->enc_layers = d->enc; c->dec_layers = d->dec; c->vocab = d->vocab;
+}
+
+// ModelUtilities.detectVariant (ModelUtilities.swift:128-173) and tokenizerNameForVariant (:175-205)
+wk_status wk_detect_variant(int32_t logits_dim, int32_t encoder_dim, const char** variant, const char** tokenizer_repo, int32_t* is_multilingual) {
+    const char* v = "base";
+    if (logits_dim == 51865) {
+        switch (encoder_dim) { case 384: v = "tiny"; break; case 512: v = "base"; break; case 768: v = "small"; break; case 1024: v = "medium"; break;
+                               case 1280: v = "large-v2"; break; default: v = "base"; }
+    } else if (logits_dim == 51864) {
+        switch (encoder_dim) { case 384: v = "tiny.en"; break; case 512: v = "base.en"; break; case 768: v = "small.en"; break; case 1024: v = "medium.en"; break;
+                               default: v = "base.en"; }
+    } else if (logits_dim == 51866) {
+        v = "large-v3";
+    }
+    static const char* names[][2] = {{"tiny", "openai/whisper-tiny"}, {"tiny.en", "openai/whisper-tiny.en"}, {"base", "openai/whisper-base"},
+                                     {"base.en", "openai/whisper-base.en"}, {"small", "openai/whisper-small"}, {"small.en", "openai/whisper-small.en"},
+                                     {"medium", "openai/whisper-medium"}, {"medium.en", "openai/whisper-medium.en"},
+                                     {"large-v2", "openai/whisper-large-v2"}, {"large-v3", "openai/whisper-large-v3"}};
+    if (variant) *variant = v;
+    if (tokenizer_repo) for (auto& n : names) if (!strcmp(n[0], v)) *tokenizer_repo = n[1];
+    if (is_multilingual) *is_multilingual = logits_dim != 51864;   // ModelUtilities.isModelMultilingual (:124-126)
+    return WK_OK;
 }
 
 wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model** out) {
