@@ -255,7 +255,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ own arm
@@ -448,14 +448,29 @@ def run_own_arm(args):
                                           f"batch 1; encoder on {used[0]} threads, token loop on {used[1]} threads) - the Swift/CoreML reference "
                                           "cannot run on Linux"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    global _JSON_OUT
     args = parse_args()
+    # Libraries may write to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG asks for it): keep the original
+    # stdout for the JSON line only and send everything else written to fd 1 to stderr.
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
