@@ -90,3 +90,34 @@ def test_oracle_model_matches_hf_live():
         cross, cache = orc.cross_kv(enc), orc.new_cache(2)
         for t in range(5):
             assert (orc.decode_step(toks[:, t], t, cache, cross) - out_hf[:, t]).abs().max() < 2e-5
+
+
+def test_oracle_alignment_heads_match_hf_cross_attentions():
+    """The oracle's `alignment_heads_weights` (mean over the alignment heads of the cross-attention softmax row, what the GPU path exports
+    for word timestamps) against the cross-attention probabilities HuggingFace Whisper returns with output_attentions - the tensors
+    openai-whisper's timing.py reads through its alignment-head hooks."""
+    torch = pytest.importorskip("torch")
+    tr = pytest.importorskip("transformers")
+    dims = M.VARIANTS["toy128"]
+    w = M.random_weights(dims, seed=4, policy="fp32", std=0.08)        # larger weights: attention rows far from uniform
+    cfg = tr.WhisperConfig(vocab_size=dims.vocab, num_mel_bins=dims.n_mels, d_model=dims.d_model, encoder_layers=dims.enc_layers,
+                           decoder_layers=dims.dec_layers, encoder_attention_heads=dims.n_heads, decoder_attention_heads=dims.n_heads,
+                           encoder_ffn_dim=dims.ffn, decoder_ffn_dim=dims.ffn, max_source_positions=1500, max_target_positions=448,
+                           activation_function="gelu", pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=1,
+                           suppress_tokens=None, begin_suppress_tokens=None, attn_implementation="eager")
+    hf = tr.WhisperForConditionalGeneration(cfg).eval()
+    hf.load_state_dict(M.to_hf_state_dict(w), strict=False)
+    orc = M.WhisperOracle(dims, w, "fp32")
+    mel = torch.randn(2, dims.n_mels, 3000)
+    toks = torch.randint(0, dims.vocab, (2, 6))
+    heads = [(0, 1), (1, 0), (1, 3)]
+    with torch.no_grad():
+        enc = orc.encode(mel)
+        out = hf(encoder_outputs=(enc,), decoder_input_ids=toks, output_attentions=True)
+        cross, cache = orc.cross_kv(enc), orc.new_cache(2)
+        for t in range(6):
+            _, al = orc.decode_step(toks[:, t], t, cache, cross, align_heads=heads)
+            ref = sum(out.cross_attentions[l][:, h, t] for l, h in heads) / len(heads)       # [B, 1500]
+            assert ref.max() > 5.0 / 1500                                                 # not a flat row
+            assert (al - ref.to(torch.float16).to(torch.float32)).abs().max() <= 2e-6 + 1e-3 * ref.max()
+            assert abs(float(al.sum(-1).mean()) - 1.0) < 2e-3
