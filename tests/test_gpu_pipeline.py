@@ -530,3 +530,62 @@ def test_transcribe_streams_word_timestamps_match_oracle_loop():
         assert [w.word for w in g.words] == [w.word for w in r.words]
         np.testing.assert_allclose([w.start for w in g.words], [w.start for w in r.words], atol=1e-4)
         np.testing.assert_allclose([w.end for w in g.words], [w.end for w in r.words], atol=1e-4)
+
+
+def _toy_tokenizer(vocab=1024):
+    """A byte-level vocabulary for the toy model: ids 0..255 are the GPT-2 byte alphabet, 256..sb-1 two-byte merges, then the Whisper
+    special tokens at the ids of D.SpecialTokens.toy(vocab) and <|t|> timestamps after them."""
+    from whisperkit_b200.tokenizer import WhisperTokenizer
+    bs = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b); cs.append(256 + n); n += 1
+    alphabet = {b: chr(c) for b, c in zip(bs, cs)}
+    sb = vocab // 2
+    toks, ids, flags = [], [], []
+    for b in range(256):
+        toks.append(alphabet[b]); ids.append(b); flags.append(0)
+    letters = " etaoinshrdlu"
+    for i in range(256, sb):
+        a, c = letters[(i * 7) % len(letters)], letters[(i * 3 + 1) % len(letters)]
+        toks.append(alphabet[ord(a)] + alphabet[ord(c)]); ids.append(i); flags.append(0)
+    names = {sb: "<|endoftext|>", sb + 1: "<|startoftranscript|>", sb + 2: "<|en|>", sb + 3: "<|translate|>", sb + 4: "<|transcribe|>",
+             sb + 5: "<|xx|>", sb + 6: "<|startofprev|>", sb + 7: "<|nospeech|>", sb + 8: "<|notimestamps|>"}
+    for i in range(sb, vocab):
+        toks.append(names.get(i, f"<|{(i - sb - 9) * 0.02:.2f}|>")); ids.append(i); flags.append(3)
+    return WhisperTokenizer(tokens=toks, ids=ids, flags=flags)
+
+
+def test_transcribe_audio_text_and_words_with_library_tokenizer():
+    """longform.transcribe_audio: the whole long-form path with the library's own tokenizer (no host callbacks) - segments and word timings
+    equal the callable-hook route (which is checked against the oracle above), texts are the tokenizer's decode of the segment tokens."""
+    from whisperkit_b200 import longform as L
+    tok = _toy_tokenizer(1024)
+    st_o = D.SpecialTokens.toy(1024)
+    st = tok.specialTokens
+    assert (st.endToken, st.startOfTranscriptToken, st.timeTokenBegin, st.transcribeToken, st.noTimestampsToken) == \
+        (st_o.endToken, st_o.startOfTranscriptToken, st_o.timeTokenBegin, st_o.transcribeToken, st_o.noTimestampsToken)
+    kit = wk.WhisperKit(wk.WhisperKitConfig(model="toy", maxBatch=4, seed=9, specialTokens=st))
+    o = wk.DecodingOptions(firstTokenLogProbThreshold=None, logProbThreshold=None, compressionRatioThreshold=None, sampleLength=24,
+                           temperatureFallbackCount=0, wordTimestamps=True)
+    streams = [np.concatenate([mel_ref.synthetic_pcm(500 + 10 * i + k) for k in range(2)])[:n].astype(np.float32)
+               for i, n in enumerate([700000, 200000])]
+    res = L.transcribe_audio(kit, streams, o, tokenizer=tok)
+    ref, _ = L.transcribe_streams(kit, streams, o, split_to_word_tokens=tok.splitToWordTokens, decode=tok.decode)
+    sb = st.specialTokenBegin
+    n_words = 0
+    for r, segs in zip(res, ref):
+        assert [g.tokens for g in r.segments] == [g.tokens for g in segs]
+        assert [(g.start, g.end) for g in r.segments] == [(g.start, g.end) for g in segs]
+        for g, h in zip(r.segments, segs):
+            assert [(w.word, w.tokens, w.start, w.end) for w in g.words] == [(w.word, w.tokens, w.start, w.end) for w in h.words]
+            assert g.text == tok.decode(g.tokens) and g.text.startswith("<|")
+            n_words += len(g.words)
+        assert r.text == tok.decode([t for g in r.segments for t in g.tokens if t < sb]).strip()
+    assert n_words > 5
+    o2 = wk.DecodingOptions(firstTokenLogProbThreshold=None, logProbThreshold=None, compressionRatioThreshold=None, sampleLength=24,
+                            temperatureFallbackCount=0, skipSpecialTokens=True)
+    r2 = L.transcribe_audio(kit, streams[:1], o2, tokenizer=tok)[0]
+    assert all("<|" not in g.text for g in r2.segments) and all(g.words is None for g in r2.segments)

@@ -463,6 +463,7 @@ class WhisperKitConfig:
     specialTokens: Optional[SpecialTokens] = None
     weights: Optional[Dict[str, object]] = None  # HF-named tensors; None -> seeded random weights
     seed: int = 0
+    modelFolder: Optional[str] = None            # HuggingFace checkpoint directory: config.json + *.safetensors (+ tokenizer.json / vocab.json)
 
 
 class WhisperKit:
@@ -471,17 +472,28 @@ class WhisperKit:
 
     def __init__(self, config: WhisperKitConfig):
         self.config = config
-        self.model = Model(config.model, config.device, config.maxBatch, config.dtype)
-        if config.weights is not None:
-            self.model.load_state_dict(config.weights)
+        self.tokenizer = None
+        if config.modelFolder is not None:
+            # loadModels + loadTokenizer from a local folder (WhisperKit.swift:358-470): weights through the safetensors loader, the
+            # decode-side tokenizer when the folder carries tokenizer.json or vocab.json
+            self.model = Model.from_pretrained(config.modelFolder, config.device, config.maxBatch, config.dtype)
+            if any(os.path.exists(os.path.join(config.modelFolder, f)) for f in ("tokenizer.json", "vocab.json")):
+                from .tokenizer import WhisperTokenizer
+                self.tokenizer = WhisperTokenizer(config.modelFolder)
         else:
-            self.model.init_random(config.seed)
+            self.model = Model(config.model, config.device, config.maxBatch, config.dtype)
+            if config.weights is not None:
+                self.model.load_state_dict(config.weights)
+            else:
+                self.model.init_random(config.seed)
         self.featureExtractor = FeatureExtractor(self.model)
         self.audioEncoder = AudioEncoder(self.model)
         self.textDecoder = TextDecoder(self.model, config.maxBatch)
         info = self.model.info
         if config.specialTokens is not None:
             self.specialTokens = config.specialTokens
+        elif self.tokenizer is not None:
+            self.specialTokens = self.tokenizer.specialTokens
         elif info.vocab == 51866:
             self.specialTokens = SpecialTokens(endToken=50257, englishToken=50259, noSpeechToken=50363,
                                                noTimestampsToken=50364, specialTokenBegin=50257,

@@ -29,6 +29,7 @@ class TranscriptionSegment:
     compressionRatio: float
     noSpeechProb: float
     words: Optional[list] = None
+    text: str = ""
 
 
 def _segs(raw, n, tokens, lps, rel=0) -> List[TranscriptionSegment]:
@@ -182,3 +183,37 @@ def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional
         lib.wk_transcription_free(h)
     per_stream = [[g for g in segs if g.stream == i] for i in range(len(arrs))]
     return per_stream, windows
+
+
+@dataclass
+class TranscriptionResult:
+    """Models.swift TranscriptionResult, the fields this backend produces."""
+    text: str
+    segments: List[TranscriptionSegment]
+    windows: int = 0
+
+
+def transcribe_audio(kit, audioArrays: Sequence[np.ndarray], options: Optional[DecodingOptions] = None, tokenizer=None,
+                     chunkingStrategy: Optional[str] = None, clipTimestamps: Sequence[float] = ()) -> List[TranscriptionResult]:
+    """WhisperKit.transcribe(audioArrays:) for audio of any length (WhisperKit.swift:667-812 over TranscribeTask.run): every array runs the
+    seek loop, all arrays share the GPU batches.  With a `whisperkit_b200.tokenizer.WhisperTokenizer` the segment and result texts are
+    filled the way the reference does it (segment text: SegmentSeeker.swift:118-121,160-165 - all tokens unless skipSpecialTokens;
+    result text: TranscribeTask.finalizeTranscriptionResult, :299-311 - text tokens only, trimmed) and word timestamps need no callbacks."""
+    opts = options or DecodingOptions()
+    split = decode = None
+    if tokenizer is not None:
+        split, decode = tokenizer.splitToWordTokens, tokenizer.decode
+    elif opts.wordTimestamps:
+        raise _lib.WhisperError(-1, "wordTimestamps needs a tokenizer")
+    per_stream, windows = transcribe_streams(kit, audioArrays, opts, clipTimestamps=clipTimestamps, chunkingStrategy=chunkingStrategy,
+                                             split_to_word_tokens=split if opts.wordTimestamps else None, decode=decode)
+    sb = kit.specialTokens.specialTokenBegin
+    out = []
+    for segs in per_stream:
+        text = ""
+        if tokenizer is not None:
+            for g in segs:
+                g.text = tokenizer.decode([t for t in g.tokens if t < sb] if opts.skipSpecialTokens else g.tokens)
+            text = tokenizer.decode([t for g in segs for t in g.tokens if t < sb]).strip(" \t               　")
+        out.append(TranscriptionResult(text, segs, windows))
+    return out
