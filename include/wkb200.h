@@ -311,7 +311,8 @@ wk_status wk_add_word_timestamps(wk_segment* segs, int32_t n_segs, const int32_t
 /* ---- tokenizer, decode side: ids -> text without a Swift host ----
  * Byte-level BPE decode as swift-transformers does it (Tokenizer.swift:510-530, Decoder.swift:126-170): added tokens verbatim, the rest
  * through the GPT-2 byte alphabet into lossy UTF-8, then cleanUp; WhisperTokenizerWrapper's special-token lookups and word splitting
- * (Models.swift:1201-1306).  Text -> ids (merges, pre-tokenizer) is NOT built: prompts arrive as token ids. */
+ * (Models.swift:1201-1306).  wk_tokenizer_encode is text -> ids WITHOUT the post-processor (no <|startoftranscript|> ... template): the
+ * reference filters special tokens out of encoded prompts anyway (TranscribeCLIUtils / promptTokens). */
 typedef struct wk_tokenizer wk_tokenizer;
 /* path: a checkpoint directory (tokenizer.json, else vocab.json + added_tokens.json), or one of those files. */
 wk_status wk_tokenizer_load(const char* path, wk_tokenizer** out);
@@ -323,6 +324,10 @@ int32_t wk_tokenizer_vocab_size(const wk_tokenizer* t);
 int32_t wk_tokenizer_token_to_id(const wk_tokenizer* t, const char* token);   /* convertTokenToId; -1 = nil */
 /* decode(tokens:skipSpecialTokens:): NUL-terminated UTF-8 into text; returns bytes written (without NUL), or -(bytes needed) if cap is short. */
 int32_t wk_tokenizer_decode(const wk_tokenizer* t, const int32_t* tokens, int32_t n, int32_t skip_special_tokens, char* text, int32_t cap);
+/* encode(text:) minus the post-processor: added tokens verbatim, then the GPT-2 pre-tokenizer pattern, byte alphabet and BPE merges
+ * (merges come from tokenizer.json / merges.txt, or wk_tokenizer_set_merges).  Returns the id count, or -(ids needed) if cap is short. */
+int32_t wk_tokenizer_encode(const wk_tokenizer* t, const char* text_utf8, int32_t* ids, int32_t cap);
+wk_status wk_tokenizer_set_merges(wk_tokenizer* t, const char* const* left, const char* const* right, int32_t n);
 /* SpecialTokens as WhisperTokenizerWrapper.init derives them, with its defaults for absent tokens. */
 wk_status wk_tokenizer_special_tokens(const wk_tokenizer* t, wk_special_tokens* out);
 /* splitToWordTokens in the wk_tokenizer_hooks layout (words as consecutive NUL-terminated strings, one token count per word; a NUL

@@ -146,3 +146,36 @@ def test_word_timestamps_with_builtin_tokenizer_hooks(toks):
     np.testing.assert_array_equal(np.float32([w.start for w in via_c]), np.float32([w.start for w in via_py[0][2]]))
     ref = W.add_word_timestamps([seg], m, lambda t: TR.split_to_word_tokens(wt.decode, t, sb), 0, 0.0, sb, decode=wt.decode)
     assert [w.word for w in ref[0].words] == [w.word for w in via_c]
+
+
+def test_encode_matches_huggingface_tokenizers(toks):
+    """text -> ids (pre-tokenizer pattern + byte alphabet + BPE merges + verbatim added tokens) against `tokenizers` on the tokenizer.json
+    it wrote, without the post-processor on either side."""
+    hf, wt, _ = toks
+    cases = CORPUS + ["", " ", "  ", "a", " a", "a ", "  leading and trailing  ", "tabs\t\tand\nnewlines\n\n x", "it's we're I'll they'd don't 'tis 'Twas",
+                      "num83r5 1234567 3.14159 ½ ²", "mixed-CASE_snake_case::path/to/file.txt", "<|startoftranscript|><|en|> hello<|0.00|> world<|endoftext|>",
+                      "x<|notimestamps|>y <|nospeech|>", "😀 emoji 👩‍👩‍👧‍👦 zwj", "한국어 Русский العربية עברית ไทย", " nbsp emspace　ideographic",
+                      "a  b   c    d", "trailing space after punctuation !  ?", "'", "''s", "' s", "x's'", "<|", "<|not a token|>"]
+    for text in cases:
+        assert wt.encode(text) == hf.encode(text, add_special_tokens=False).ids, repr(text)
+        assert wt.decode(wt.encode(text)) == hf_decode(hf, hf.encode(text, add_special_tokens=False).ids)
+    rng = np.random.default_rng(5)
+    alphabet = list(" \t\n'.,!?-_:;()[]{}<>|/\\\"0123456789") + list("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ") + \
+        list("áéíóúüñçßøåœ") + list("こんにちは世界テスト") + list("привет") + list("🙂👍") + ["'s", "'re", "'ll", " ", "  ", "<|en|>", "<|0.00|>"]
+    for _ in range(400):
+        text = "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), int(rng.integers(1, 40))))
+        assert wt.encode(text) == hf.encode(text, add_special_tokens=False).ids, repr(text)
+
+
+def test_encode_from_vocab_json_and_merges_txt(toks, tmp_path):
+    hf, wt, d = toks
+    data = json.load(open(os.path.join(d, "tokenizer.json"), encoding="utf-8"))
+    json.dump(data["model"]["vocab"], open(tmp_path / "vocab.json", "w", encoding="utf-8"))
+    json.dump({a["content"]: a["id"] for a in data["added_tokens"]}, open(tmp_path / "added_tokens.json", "w", encoding="utf-8"))
+    with open(tmp_path / "merges.txt", "w", encoding="utf-8") as f:
+        f.write("#version: 0.2\n")
+        for m in data["model"]["merges"]:
+            f.write((m if isinstance(m, str) else " ".join(m)) + "\n")
+    wt2 = WhisperTokenizer(str(tmp_path))
+    for text in CORPUS:
+        assert wt2.encode(" " + text) == hf.encode(" " + text, add_special_tokens=False).ids

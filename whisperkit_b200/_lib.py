@@ -167,6 +167,8 @@ SYMBOLS = [
     ("wk_tokenizer_vocab_size", I32, [P]),
     ("wk_tokenizer_token_to_id", I32, [P, C.c_char_p]),
     ("wk_tokenizer_decode", I32, [P, PI32, I32, I32, C.POINTER(C.c_char), I32]),
+    ("wk_tokenizer_encode", I32, [P, C.c_char_p, PI32, I32]),
+    ("wk_tokenizer_set_merges", I32, [P, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), I32]),
     ("wk_tokenizer_special_tokens", I32, [P, C.POINTER(wk_special_tokens)]),
     ("wk_tokenizer_split_to_word_tokens", I32, [P, PI32, I32, C.POINTER(C.c_char), I32, PI32, I32]),
     ("wk_tokenizer_hooks_init", I32, [P, C.POINTER(wk_tokenizer_hooks)]),

@@ -1,6 +1,7 @@
 // tokenizer.cu - token ids -> text for the host side of the path: the decode half of the reference's
 // byte-level BPE tokenizer and WhisperTokenizerWrapper's word splitting, so that word timestamps and segment text work without a
-// Swift host.  Pure host C++ (no GPU).  Encoding (text -> ids: merges + the pre-tokenizer regex) is not built.
+// Swift host, plus text -> ids (pre-tokenizer pattern, byte alphabet, BPE merges; no post-processor: special tokens are the caller's).
+// Pure host C++ (no GPU).
 //   PreTrainedTokenizer.decode(tokens:skipSpecialTokens:) + cleanUp      Sources/ArgmaxCore/External/Tokenizers/Tokenizer.swift:428-447,510-530
 //   ByteLevelDecoder (added tokens verbatim, the rest bytes -> UTF-8)     Sources/ArgmaxCore/External/Tokenizers/Decoder.swift:126-170
 //   byteEncoder / byteDecoder (GPT-2 bytes_to_unicode)                   Sources/ArgmaxCore/External/Tokenizers/ByteEncoder.swift
@@ -18,6 +19,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "unicode_letters.h"
 #include "unicode_punct.h"
 
 using namespace wk;
@@ -33,6 +35,9 @@ struct wk_tokenizer {
     std::vector<uint8_t> present, added, special;
     std::unordered_map<std::string, int> token_to_id;
     int byte_of_cp[512];                    // GPT-2 byte <-> code point bijection (code points < 0x144)
+    std::string cp_of_byte[256];            // the same bijection, byte -> UTF-8 of its alphabet character
+    std::unordered_map<std::string, int> merge_rank;   // "left\x01right" -> rank (text -> ids only)
+    std::vector<std::string> added_sorted;  // added-token contents, longest first (matched verbatim in the text)
     bool clean_up = true;
 };
 
@@ -99,6 +104,92 @@ void build_byte_map(wk_tokenizer* t) {
         if (self) t->byte_of_cp[b] = b;
         else t->byte_of_cp[256 + n++] = b;
     }
+    for (int cp = 0; cp < 512; ++cp)
+        if (t->byte_of_cp[cp] >= 0) { std::string u; append_utf8(u, (uint32_t)cp); t->cp_of_byte[t->byte_of_cp[cp]] = u; }
+}
+
+bool in_ranges(const uint32_t (*r)[2], int n, uint32_t cp) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (cp < r[mid][0]) hi = mid - 1;
+        else if (cp > r[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+bool is_letter(uint32_t cp) { return in_ranges(kLetterRanges, kLetterRangesCount, cp); }
+bool is_number(uint32_t cp) { return in_ranges(kNumberRanges, kNumberRangesCount, cp); }
+bool is_space(uint32_t cp) {   // \s of the pre-tokenizer pattern = Unicode White_Space
+    return (cp >= 0x9 && cp <= 0xD) || cp == 0x20 || cp == 0x85 || cp == 0xA0 || cp == 0x1680 || (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 ||
+           cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
+}
+
+// The GPT-2 / Whisper pre-tokenizer (ByteLevel use_regex; BPETokenizer.swift:165):
+//   's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+      leftmost, alternatives in order, each greedy
+void pre_tokenize(const std::vector<uint32_t>& cps, std::vector<std::pair<size_t, size_t>>& pieces) {
+    const size_t n = cps.size();
+    size_t i = 0;
+    auto other = [&](uint32_t c) { return !is_space(c) && !is_letter(c) && !is_number(c); };
+    while (i < n) {
+        size_t e = 0;
+        if (cps[i] == '\'' && i + 1 < n) {
+            const uint32_t a = cps[i + 1], b = i + 2 < n ? cps[i + 2] : 0;
+            if (a == 's' || a == 't') e = i + 2;
+            else if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e')) e = i + 3;
+            else if (a == 'm') e = i + 2;
+            else if (a == 'l' && b == 'l') e = i + 3;
+            else if (a == 'd') e = i + 2;
+        }
+        if (!e) {
+            const size_t k = (cps[i] == ' ' && i + 1 < n) ? i + 1 : i;
+            if (is_letter(cps[k])) { e = k; while (e < n && is_letter(cps[e])) ++e; }
+            else if (is_number(cps[k])) { e = k; while (e < n && is_number(cps[e])) ++e; }
+            else if (other(cps[k])) { e = k; while (e < n && other(cps[e])) ++e; }
+        }
+        if (!e && is_space(cps[i])) {
+            size_t r = i;
+            while (r < n && is_space(cps[r])) ++r;
+            if (r == n) e = r;                      // \s+(?!\S) at the end of the text
+            else if (r - i >= 2) e = r - 1;         // leave the last blank to the next piece (it becomes its leading space)
+            else e = r;                             // \s+
+        }
+        if (!e) e = i + 1;
+        pieces.push_back({i, e});
+        i = e;
+    }
+}
+
+// classic BPE: merge the lowest-rank adjacent pair (all its occurrences, left to right) until none is left
+void bpe(const wk_tokenizer* t, std::vector<std::string>& word) {
+    while (word.size() > 1) {
+        int best = -1;
+        size_t where = 0;
+        for (size_t k = 0; k + 1 < word.size(); ++k) {
+            auto it = t->merge_rank.find(word[k] + '\x01' + word[k + 1]);
+            if (it != t->merge_rank.end() && (best < 0 || it->second < best)) { best = it->second; where = k; }
+        }
+        if (best < 0) break;
+        const std::string a = word[where], b = word[where + 1];
+        std::vector<std::string> next;
+        for (size_t k = 0; k < word.size();) {
+            if (k + 1 < word.size() && word[k] == a && word[k + 1] == b) { next.push_back(a + b); k += 2; }
+            else { next.push_back(word[k]); ++k; }
+        }
+        word.swap(next);
+    }
+}
+
+void finish_added(wk_tokenizer* t) {
+    t->added_sorted.clear();
+    for (size_t id = 0; id < t->id_to_token.size(); ++id)
+        if (t->present[id] && t->added[id] && !t->id_to_token[id].empty()) t->added_sorted.push_back(t->id_to_token[id]);
+    std::sort(t->added_sorted.begin(), t->added_sorted.end(), [](const std::string& a, const std::string& b) { return a.size() != b.size() ? a.size() > b.size() : a < b; });
+}
+
+void add_merge(wk_tokenizer* t, const std::string& a, const std::string& b) {
+    const int rank = (int)t->merge_rank.size();
+    t->merge_rank.emplace(a + '\x01' + b, rank);
 }
 
 bool is_punct(uint32_t cp) {
@@ -335,6 +426,28 @@ bool parse_tokenizer_json(Json& j, wk_tokenizer* t) {
                 const std::string k = j.str();
                 if (!j.ok || !j.eat(':')) return false;
                 if (k == "vocab" && j.peek() == '{') { if (!parse_flat_vocab(j, t, false)) return false; }
+                else if (k == "merges" && j.peek() == '[') {
+                    // ["a b", ...] (older tokenizers) or [["a", "b"], ...]
+                    j.eat('[');
+                    if (!j.eat(']')) {
+                        do {
+                            if (j.peek() == '[') {
+                                j.eat('[');
+                                const std::string a = j.str();
+                                if (!j.eat(',')) return false;
+                                const std::string b = j.str();
+                                if (!j.ok || !j.eat(']')) return false;
+                                add_merge(t, a, b);
+                            } else {
+                                const std::string m = j.str();
+                                const size_t sp = m.find(' ');
+                                if (!j.ok || sp == std::string::npos) return false;
+                                add_merge(t, m.substr(0, sp), m.substr(sp + 1));
+                            }
+                        } while (j.eat(','));
+                        if (!j.eat(']')) return false;
+                    }
+                }
                 else j.skip();
             } while (j.ok && j.eat(','));
             if (!j.eat('}')) return false;
@@ -356,6 +469,7 @@ wk_status wk_tokenizer_create(const char* const* tokens, const int32_t* ids, con
     build_byte_map(t);
     t->clean_up = clean_up != 0;
     for (int i = 0; i < n; ++i) put(t, tokens[i] ? tokens[i] : "", ids[i], flags && (flags[i] & 1), flags && (flags[i] & 2));
+    finish_added(t);
     *out = t;
     return WK_OK;
 }
@@ -383,8 +497,22 @@ wk_status wk_tokenizer_load(const char* path, wk_tokenizer** out) {
             Json k{extra.data(), extra.data() + extra.size()};
             ok = parse_flat_vocab(k, t, true);
         }
+        std::string merges;
+        if (ok && read_file(p + "/merges.txt", merges)) {   // "#version" header line, then "left right" per line
+            size_t pos = 0;
+            while (pos < merges.size()) {
+                size_t eol = merges.find('\n', pos);
+                if (eol == std::string::npos) eol = merges.size();
+                std::string line = merges.substr(pos, eol - pos);
+                if (!line.empty() && line.back() == '\r') line.pop_back();
+                const size_t sp = line.find(' ');
+                if (!line.empty() && line[0] != '#' && sp != std::string::npos) add_merge(t, line.substr(0, sp), line.substr(sp + 1));
+                pos = eol + 1;
+            }
+        }
     }
     if (!ok || t->id_to_token.empty()) { delete t; set_error("wk_tokenizer_load: no readable tokenizer.json / vocab.json at %s", path); return WK_ERR_MODELS_UNAVAILABLE; }
+    finish_added(t);
     *out = t;
     return WK_OK;
 }
@@ -401,6 +529,54 @@ int32_t wk_tokenizer_decode(const wk_tokenizer* t, const int32_t* tokens, int32_
     if ((int64_t)s.size() + 1 > cap) return -(int32_t)(s.size() + 1);   // -(bytes needed)
     memcpy(text, s.c_str(), s.size() + 1);
     return (int32_t)s.size();
+}
+
+wk_status wk_tokenizer_set_merges(wk_tokenizer* t, const char* const* left, const char* const* right, int32_t n) {
+    if (!t || n < 0 || (n > 0 && (!left || !right))) { set_error("wk_tokenizer_set_merges: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    t->merge_rank.clear();
+    for (int i = 0; i < n; ++i) add_merge(t, left[i], right[i]);
+    return WK_OK;
+}
+
+int32_t wk_tokenizer_encode(const wk_tokenizer* t, const char* text_utf8, int32_t* ids, int32_t cap) {
+    if (!t || !text_utf8 || (cap > 0 && !ids)) return -1;
+    const std::string text = text_utf8;
+    std::vector<int32_t> out;
+    auto encode_plain = [&](const std::string& part) -> bool {
+        std::vector<uint32_t> cps;
+        std::vector<size_t> off;   // byte offset of every code point, plus the end
+        for (size_t i = 0; i < part.size();) { uint32_t cp; off.push_back(i); i += next_cp(part, i, &cp); cps.push_back(cp); }
+        off.push_back(part.size());
+        std::vector<std::pair<size_t, size_t>> pieces;
+        pre_tokenize(cps, pieces);
+        for (auto& pc : pieces) {
+            std::vector<std::string> word;
+            for (size_t b = off[pc.first]; b < off[pc.second]; ++b) word.push_back(t->cp_of_byte[(unsigned char)part[b]]);
+            bpe(t, word);
+            for (const std::string& w : word) {
+                auto it = t->token_to_id.find(w);
+                if (it == t->token_to_id.end()) return false;   // cannot happen with a byte-level vocabulary
+                out.push_back(it->second);
+            }
+        }
+        return true;
+    };
+    // added tokens are matched verbatim first (Tokenizer.swift:470-481), longest content first
+    size_t start = 0, i = 0;
+    while (i < text.size()) {
+        const std::string* hit = nullptr;
+        for (const std::string& a : t->added_sorted)
+            if (text.compare(i, a.size(), a) == 0) { hit = &a; break; }
+        if (!hit) { ++i; continue; }
+        if (i > start && !encode_plain(text.substr(start, i - start))) return -1;
+        out.push_back(t->token_to_id.at(*hit));
+        i += hit->size();
+        start = i;
+    }
+    if (start < text.size() && !encode_plain(text.substr(start))) return -1;
+    if ((int64_t)out.size() > cap) return -(int32_t)out.size();   // -(ids needed)
+    if (!out.empty()) memcpy(ids, out.data(), out.size() * 4);
+    return (int32_t)out.size();
 }
 
 wk_status wk_tokenizer_special_tokens(const wk_tokenizer* t, wk_special_tokens* out) {

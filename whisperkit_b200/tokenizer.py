@@ -45,6 +45,20 @@ class WhisperTokenizer:
             cap = -r + 1
         raise _lib.WhisperError(-1, "wk_tokenizer_decode failed")
 
+    def encode(self, text: str) -> List[int]:
+        """encode(text:) without the post-processor (no special-token template)."""
+        b = text.encode("utf-8")
+        cap = 4 * len(b) + 16
+        for _ in range(2):
+            ids = (C.c_int32 * cap)()
+            n = self.lib.wk_tokenizer_encode(self.handle, b, ids, cap)
+            if n >= 0:
+                return [int(v) for v in ids[:n]]
+            if n == -1:
+                break
+            cap = -n
+        raise _lib.WhisperError(-1, "wk_tokenizer_encode failed")
+
     @property
     def specialTokens(self) -> SpecialTokens:
         st = wk_special_tokens()
