@@ -6,6 +6,8 @@ scale) - against the oracle run under the same 16-bit storage policy (oracle/mod
 weights give near-uniform logits, token equality is asserted on every sequence whose smallest top-1 margin in
 the oracle exceeds 20x the measured logit error (the statistic is printed), and unconditionally on the logits
 themselves (teacher-forced on the oracle's tokens)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -589,3 +591,14 @@ def test_transcribe_audio_text_and_words_with_library_tokenizer():
                             temperatureFallbackCount=0, skipSpecialTokens=True)
     r2 = L.transcribe_audio(kit, streams[:1], o2, tokenizer=tok)[0]
     assert all("<|" not in g.text for g in r2.segments) and all(g.words is None for g in r2.segments)
+
+
+@pytest.mark.skipif(os.environ.get("WKB200_TEST_FUSED") != "1", reason="experimental fused decoder chains: opt-in bring-up test (WKB200_TEST_FUSED=1)")
+def test_fused_decoder_chains_match_the_launch_per_phase_path():
+    """csrc/fused_chain.cu (WKB200_FUSED=1) keeps the arithmetic and its order: tokens and logits must be bit-identical to the default path."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fused_check.py")], capture_output=True, text=True, timeout=240)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0

@@ -155,6 +155,7 @@ struct Lane {
     // word timestamps: per-head softmax rows of the current step, and the [Bs][224][T] Float16 alignmentWeights tensor
     float* align_scratch = nullptr; void* align_w = nullptr; int align_slots = 0; bool align_on = false;
     void* align_keep = nullptr;   // alignment of windows already final while the fallback ladder re-decodes the chunk
+    unsigned int* chain_counters = nullptr;   // WKB200_FUSED=1: grid-barrier words of the fused phase chains, zeroed once per step
 };
 
 struct wk_session {
@@ -430,6 +431,57 @@ static wk_status decoder_forward(Lane* s, int prompt_len, int ts_begin, const in
                               explicit_pos ? 1 : 0, explicit_pos, st));
     int n_layers = c.dec_layers;
     if (const char* e = getenv("WKB200_DEBUG_DEC_LAYERS")) n_layers = std::min(n_layers, atoi(e));  // stage debugging only
+    static const bool fused = getenv("WKB200_FUSED") && atoi(getenv("WKB200_FUSED")) == 1;
+    if (fused) {
+        // EXPERIMENTAL (fused_chain.cu, not validated on a GPU yet): per layer, self-attention -> chain B -> cross-attention -> chain C
+        const int kWords = 8;
+        if (!s->chain_counters) WK_CUDA_CHECK(cudaMalloc((void**)&s->chain_counters, (size_t)c.dec_layers * 2 * kWords * 4));
+        WK_CUDA_CHECK(cudaMemsetAsync(s->chain_counters, 0, (size_t)c.dec_layers * 2 * kWords * 4, st));
+        auto gemm_phase = [&](const void* w, int N, int K, const void* act) {
+            ChainPhaseDesc ph; memset(&ph, 0, sizeof(ph));
+            ph.kind = 0; ph.w = w; ph.n = N; ph.k = K; ph.act = act; ph.splits = choose_splits((N + 127) / 128, K / 64, m->num_sms);
+            return ph;
+        };
+        auto ln_phase = [&](const float* bias, const LayerNormW& ln) {
+            ChainPhaseDesc ph; memset(&ph, 0, sizeof(ph));
+            ph.kind = 1; ph.bias = bias; ph.gamma = ln.g; ph.beta = ln.b; ph.out16 = s->xn;
+            return ph;
+        };
+        auto chain_base = [&](int li, int which) {
+            ChainDesc cd; memset(&cd, 0, sizeof(cd));
+            cd.partial = s->partial; cd.x = s->x; cd.B = B; cd.Bp = Bp; cd.d = d; cd.dtype = dt; cd.pdl = 1;
+            cd.counters = s->chain_counters + ((size_t)li * 2 + which) * kWords;
+            return cd;
+        };
+        WK_CHECK(dec_gemm(s, m->dec[0].wqkv, 3 * d, d, s->xn, &sp));
+        for (int li = 0; li < n_layers; ++li) {
+            DecLayer& l = m->dec[li];
+            WK_CHECK(decoder_self_attention(s->partial, sp, Bp, l.bq, l.bv, (char*)s->self_k + li * self_layer, (char*)s->self_v + li * self_layer,
+                                            s->st.step, explicit_pos, s->attn, B, H, kKvMaxLen, dt, st));
+            ChainDesc cb = chain_base(li, 0);
+            cb.ph[0] = gemm_phase(l.wo, d, d, s->attn);
+            cb.ph[1] = ln_phase(l.bo, l.lnx);
+            cb.ph[2] = gemm_phase(l.wcq, d, d, s->xn);
+            cb.n_phases = 3;
+            WK_CHECK(decoder_chain(cb, m->num_sms, st));
+            sp = cb.ph[2].splits;
+            const bool align = s->align_on && !explicit_pos && m->align_mask[li] != 0;
+            WK_CHECK(decoder_cross_attention(s->partial, sp, Bp, l.bcq, (char*)s->cross_kv + (size_t)(2 * li) * cross_block,
+                                             (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st,
+                                             align ? s->align_scratch + (size_t)m->align_base[li] * B * T : nullptr, align ? m->align_mask[li] : 0u));
+            ChainDesc cc = chain_base(li, 1);
+            const LayerNormW& nxt = (li + 1 < n_layers) ? m->dec[li + 1].ln1 : m->dec_ln;
+            cc.ph[0] = gemm_phase(l.wco, d, d, s->attn);
+            cc.ph[1] = ln_phase(l.bco, l.ln3);
+            cc.ph[2] = gemm_phase(l.w1, 4 * d, d, s->xn);
+            cc.ph[3].kind = 2; cc.ph[3].bias = l.b1; cc.ph[3].out16 = s->ffn;
+            cc.ph[4] = gemm_phase(l.w2, d, 4 * d, s->ffn);
+            cc.ph[5] = ln_phase(l.b2, nxt);
+            cc.n_phases = 6;
+            if (li + 1 < n_layers) { cc.ph[6] = gemm_phase(m->dec[li + 1].wqkv, 3 * d, d, s->xn); cc.n_phases = 7; sp = cc.ph[6].splits; }
+            WK_CHECK(decoder_chain(cc, m->num_sms, st));
+        }
+    } else
     for (int li = 0; li < n_layers; ++li) {
         DecLayer& l = m->dec[li];
         WK_CHECK(dec_gemm(s, l.wqkv, 3 * d, d, s->xn, &sp));
@@ -1032,7 +1084,7 @@ static void lane_free(Lane* s) {
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
                     s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.step, s->st.n_done, s->st.input_ids,
-                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev, s->align_scratch, s->align_w, s->align_keep};
+                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev, s->align_scratch, s->align_w, s->align_keep, s->chain_counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;

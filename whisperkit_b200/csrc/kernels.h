@@ -150,4 +150,29 @@ wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerP
                                 float* filtered_out, int B, cudaStream_t stream);
 wk_status decode_state_init(DecodeState st, const int32_t* prompt_dev, int n_prompt, int B, cudaStream_t stream);
 
+// ---- experimental (WKB200_FUSED=1): a chain of decoder GEMM / split-K reduce phases in ONE persistent kernel with grid-wide barriers
+// between the phases instead of kernel boundaries.  fused_chain.cu
+wk_status make_tmap_2d(void* tm, const void* base, int dtype, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);
+constexpr int kChainMaxPhases = 7;
+constexpr int kChainMaxGemms = 4;
+struct ChainPhaseDesc {
+    int kind;                  // 0 swap-AB split-K GEMM -> partials; 1 reduce + bias + residual + LayerNorm; 2 reduce + bias + GELU
+    // kind 0
+    const void* w; int n, k;   // weights [n][k]
+    const void* act;           // activations [Bp][k], 16-bit
+    int splits;
+    // kind 1 / 2 (reduce the partials of the GEMM phase before it)
+    const float* bias; const float* gamma; const float* beta;
+    void* out16;               // LN output / GELU output, 16-bit [B][row length]
+};
+struct ChainDesc {
+    int n_phases;
+    ChainPhaseDesc ph[kChainMaxPhases];
+    float* partial; float* x;  // split-K workspace, f32 residual stream [Bp][d]
+    int B, Bp, d, dtype;
+    unsigned int* counters;    // n_phases - 1 words, zero before the launch
+    int pdl;
+};
+wk_status decoder_chain(const ChainDesc& c, int num_sms, cudaStream_t stream);
+
 }  // namespace wk
