@@ -179,3 +179,64 @@ def test_encode_from_vocab_json_and_merges_txt(toks, tmp_path):
     wt2 = WhisperTokenizer(str(tmp_path))
     for text in CORPUS:
         assert wt2.encode(" " + text) == hf.encode(" " + text, add_special_tokens=False).ids
+
+
+def _gpt2_alphabet():
+    bs = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b); cs.append(256 + n); n += 1
+    return bs, {b: chr(c) for b, c in zip(bs, cs)}
+
+
+def _reference_mini_vocab():
+    """The slice of the real Whisper (multilingual tiny) vocabulary that the reference's own tokenizer tests reveal
+    (UnitTests.swift:1326-1375, 2494-2652): ids 0..255 are the GPT-2 byte alphabet in its canonical order (so 0 = '!', 11 = ',',
+    30 = '?', 220 = ' ', and 171,120,223 = EF BC 81 = '！' exactly as the tests list them), plus the multi-byte tokens at their real ids."""
+    order, alpha = _gpt2_alphabet()
+    toks, ids, flags = [], [], []
+    for i, b in enumerate(order):
+        toks.append(alpha[b]); ids.append(i); flags.append(0)
+    known = {2425: " Hello", 1002: " world", 639: " This", 307: " is", 257: " a", 31636: "test", 1943: " isn", 380: "'t", 309: " it",
+             24364: "¡", 48529: "Hola", 376: " M", 6043: "undo", 20547: " Esta", 785: " es", 2002: " una", 48241: " prueba", 3841: " ¿", 1771: "no",
+             38088: "こんにちは", 1231: "、", 24486: "世界", 25212: "これは", 22985: "テ", 40498: "スト", 4767: "です", 30346: "よね"}
+    for i, text in known.items():
+        toks.append("".join(alpha[b] for b in text.encode("utf-8"))); ids.append(i); flags.append(0)
+    for i, name in {50257: "<|endoftext|>", 50258: "<|startoftranscript|>", 50363: "<|notimestamps|>", 50364: "<|0.00|>", 50414: "<|1.00|>"}.items():
+        toks.append(name); ids.append(i); flags.append(3)
+    return WhisperTokenizer(tokens=toks, ids=ids, flags=flags)
+
+
+def test_split_to_word_tokens_reference_kats():
+    """testSplitToWordTokens / ...Spanish / ...Japanese (UnitTests.swift:1326-1375) on the vocabulary slice those tests reveal."""
+    wt = _reference_mini_vocab()
+    assert wt.specialTokens.specialTokenBegin == 50257 and wt.specialTokens.whitespaceToken == 220   # " " is not a vocabulary string -> default 220
+    ids = [50364, 2425, 11, 1002, 0, 50414, 50414, 639, 307, 257, 220, 31636, 11, 1943, 380, 309, 30, 50257]
+    words, groups = wt.splitToWordTokens(ids)
+    assert words == ["<|0.00|>", " Hello", ",", " world", "!", "<|1.00|>", "<|1.00|>", " This", " is", " a", " test", ",", " isn't", " it", "?", "<|endoftext|>"]
+    assert groups == [[50364], [2425], [11], [1002], [0], [50414], [50414], [639], [307], [257], [220, 31636], [11], [1943, 380], [309], [30], [50257]]
+    ids = [50363, 24364, 48529, 376, 6043, 0, 20547, 785, 2002, 48241, 11, 3841, 1771, 30, 50257]
+    words, groups = wt.splitToWordTokens(ids)
+    assert words == ["<|notimestamps|>", "¡Hola", " Mundo", "!", " Esta", " es", " una", " prueba", ",", " ¿no", "?", "<|endoftext|>"]
+    assert groups == [[50363], [24364, 48529], [376, 6043], [0], [20547], [785], [2002], [48241], [11], [3841, 1771], [30], [50257]]
+    ids = [50364, 38088, 1231, 24486, 171, 120, 223, 25212, 22985, 40498, 4767, 30346, 171, 120, 253, 50257]
+    words, groups = wt.splitToWordTokens(ids)
+    assert words == ["<|0.00|>", "こんにちは", "、", "世界", "！", "これは", "テ", "スト", "です", "よね", "？", "<|endoftext|>"]
+    assert groups == [[50364], [38088], [1231], [24486], [171, 120, 223], [25212], [22985], [40498], [4767], [30346], [171, 120, 253], [50257]]
+    # the same vocabulary reproduces the inputs of the reference's mergePunctuations tests from token ids alone
+    assert wt.decode([2425, 11, 1002, 0]) == " Hello, world!" and wt.decode([3841, 1771, 30]) == " ¿no?"
+
+
+def test_tokenizer_output_reference_kat():
+    """testTokenizerOutput (UnitTests.swift:1288-1297): the large-v3 ids decode to the jfk sentence, special tokens verbatim.  The token
+    strings come from the reference's word-timestamp goldens (UnitTests.swift:2703-2725), ids 50364 / 50889 are the large-v3 specials."""
+    _, alpha = _gpt2_alphabet()
+    words = {400: " And", 370: " so", 452: " my", 7177: " fellow", 6280: " Americans", 1029: " ask", 406: " not", 437: " what", 428: " your", 1941: " country",
+             393: " can", 360: " do", 337: " for", 291: " you", 13: "."}
+    toks = ["".join(alpha[b] for b in w.encode("utf-8")) for w in words.values()] + ["<|notimestamps|>", "<|10.48|>"]
+    wt = WhisperTokenizer(tokens=toks, ids=list(words) + [50364, 50889], flags=[0] * len(words) + [3, 3])
+    ids = [50364, 400, 370, 452, 7177, 6280, 1029, 406, 437, 428, 1941, 393, 360, 337, 291, 1029, 437, 291, 393, 360, 337, 428, 1941, 13, 50889]
+    assert wt.decode(ids) == "<|notimestamps|> And so my fellow Americans ask not what your country can do for you ask what you can do for your country.<|10.48|>"
+    assert wt.decode(ids, skipSpecialTokens=True) == " And so my fellow Americans ask not what your country can do for you ask what you can do for your country."
