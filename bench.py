@@ -58,7 +58,23 @@ def parse_args():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-windows", type=int, default=1)
     ap.add_argument("--profile-pass", action="store_true", help="one untimed pass of the hot path and exit (for ncu)")
+    ap.add_argument("--windows", type=int, default=0, help="30 s windows per GPU per step (default: --batch, i.e. one window per decode slot)")
+    ap.add_argument("--eot-profile", action="store_true",
+                    help="windows end at their own length: per-window sampleLength drawn (seeded) from a speech-like distribution instead of "
+                         "the worst-case 223 steps for every window; with --windows > --batch the freed slots take the next windows")
+    ap.add_argument("--encoder-chunk", type=int, default=0, help="windows per mel+encoder pass (default: the model's max_batch)")
     return ap.parse_args()
+
+
+def eot_profile_lengths(n: int, seed: int = 4321) -> np.ndarray:
+    """Decoder steps per 30 s window for the --eot-profile mode.  No checkpoint is available offline, so the lengths come from a seeded
+    log-normal fit of what 30 s of speech turns into with Whisper's tokenizer (4 prompt tokens + ~2.5 words/s x ~1.3 tokens/word plus
+    timestamp pairs: median ~95 tokens), with 8 % near-silent windows, clipped to [6, 223]."""
+    rng = np.random.default_rng(seed)
+    x = np.exp(rng.normal(np.log(95.0), 0.45, size=n))
+    silent = rng.random(n) < 0.08
+    x[silent] = rng.integers(6, 20, size=n)[silent]
+    return np.clip(np.round(x), 6, 223).astype(np.int64)
 
 
 def measured_peaks():
@@ -263,6 +279,7 @@ def run_own_arm(args):
     import torch
     import whisperkit_b200 as wk
     from whisperkit_b200._lib import check, wk_decode_result
+    from whisperkit_b200.api import make_batch_opts
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,7 +288,8 @@ def run_own_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    B = args.batch
+    B = args.batch                       # decode slots per GPU
+    W = args.windows or B                # windows per GPU per step
     log(f"rank {rank}/{world}: creating model {args.variant} max_batch {B}")
     model = wk.Model(args.variant, device=local_rank, max_batch=B, dtype=args.dtype)
     model.init_random(seed=1234)
@@ -282,15 +300,20 @@ def run_own_arm(args):
     st = special_tokens_for(info.vocab)
     # one greedy pass per window: with random-init weights avgLogProb is always below logProbThreshold, so the temperature
     # fallback ladder (retries, not part of the metric) is switched off; the CPU arm decodes one pass as well
-    opts = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=args.sample_length, temperatureFallbackCount=0)
-    prompt = dec.prefillDecoderInputs(opts, st)
+    base = dict(firstTokenLogProbThreshold=None, temperatureFallbackCount=0)
+    if args.eot_profile:
+        lens = eot_profile_lengths(world * W)[rank * W:(rank + 1) * W]
+        opts = [wk.DecodingOptions(sampleLength=int(v), **base) for v in lens]
+        expected_steps = int(lens.sum())
+    else:
+        opts = wk.DecodingOptions(sampleLength=args.sample_length, **base)
+        expected_steps = W * min(args.sample_length, 223)
     st_c = st.to_c()
-    o_c, keep = opts.to_c()
-    p_c = (C.c_int32 * len(prompt))(*prompt)
-    res = (wk_decode_result * B)()
+    bo, keep = make_batch_opts(W, opts, None, encoderChunk=args.encoder_chunk)
+    res = (wk_decode_result * W)()
     ext = torch.cuda.ExternalStream(model.stream, device=torch.device("cuda", local_rank))
 
-    pcm_np = synthetic_windows(rank * B, B)
+    pcm_np = synthetic_windows(rank * W, W)
     pcm_host = torch.from_numpy(pcm_np).pin_memory()
     pcm_dev = pcm_host.cuda(non_blocking=False)
     torch.cuda.synchronize()
@@ -300,35 +323,34 @@ def run_own_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(pcm_dev.data_ptr()), B, 480000, None, C.byref(st_c),
-                                        C.byref(o_c), p_c, len(prompt), res))
+    def transcribe(ptr, n, result_array, batch_opts):
+        check(lib.wk_transcribe_windows_ex(model.handle, dec.handle, C.c_void_p(ptr), n, 480000, None, C.byref(st_c), C.byref(batch_opts), result_array))
 
-    # e2e: host PCM in, token IDs on the host out.  N > 1: rank 0 owns all N*B windows in pinned memory, copies them
+    def step_device():
+        transcribe(pcm_dev.data_ptr(), W, res, bo)
+
+    # e2e: host PCM in, token IDs on the host out.  N > 1: rank 0 owns all N*W windows in pinned memory, copies them
     # to its GPU, NCCL scatters shards over NVLink, every rank transcribes, NCCL gathers token IDs back to rank 0.
+    e2e_stages = {}
     if world > 1:
         from whisperkit_b200 import distributed as WD
-        from whisperkit_b200.api import DecodingResult
-        all_host = torch.from_numpy(synthetic_windows(0, world * B)).pin_memory() if rank == 0 else None
+        all_host = torch.from_numpy(synthetic_windows(0, world * W)).pin_memory() if rank == 0 else None
         dev = torch.device("cuda", local_rank)
-    d2h_bytes = B * (224 * 8 + 16)
+    d2h_bytes = W * (224 * 8 + 16)
 
     def step_e2e():
         if world == 1:
-            check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(pcm_host.data_ptr()), B, 480000, None,
-                                            C.byref(st_c), C.byref(o_c), p_c, len(prompt), res))
+            transcribe(pcm_host.data_ptr(), W, res, bo)
             return
 
         def local(shard):
             torch.cuda.synchronize()  # NCCL ran on torch's stream; the library has its own
-            check(lib.wk_transcribe_windows(model.handle, dec.handle, C.c_void_p(shard.data_ptr()), shard.shape[0], 480000, None,
-                                            C.byref(st_c), C.byref(o_c), p_c, len(prompt), res))
-            return [DecodingResult.from_c(res[b]) for b in range(shard.shape[0])]
+            transcribe(shard.data_ptr(), shard.shape[0], res, bo)
+            return res
 
-        staged = all_host.to(dev, non_blocking=True) if rank == 0 else None
-        toks = WD.transcribe_sharded(staged, world * B, 480000, dev, local)
+        toks = WD.transcribe_sharded(all_host, world * W, 480000, dev, local, stages=e2e_stages)
         if rank == 0:
-            assert len(toks) == world * B
+            assert len(toks) == world * W
 
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
@@ -340,22 +362,24 @@ def run_own_arm(args):
         if sampler:
             sampler.__enter__()
         e0.record(ext)
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
         e1.record(ext)
         barrier()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
         if sampler:
             sampler.__exit__()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e1), 0.0)
         launches = int(lib.wk_kernel_launch_count(0))
         if world > 1:
-            t = torch.tensor([ms], device="cuda")
+            t = torch.tensor([ms, wall_ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, wall_ms = float(t[0].item()), float(t[1].item())
             lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
             launches = int(lt.item())
-        return ms, launches, (sampler.summary() if sampler else None)
+        return ms, launches, (sampler.summary() if sampler else None), wall_ms
 
     log("PCM ready; first (untimed) pass")
     t_first = time.perf_counter()
@@ -365,36 +389,50 @@ def run_own_arm(args):
         step_device()
         log(f"profile pass done, launches {int(lib.wk_kernel_launch_count(0))}")
         return
-    ms, launches, clocks = timed(step_device, args.steps, max(args.warmup, 3), True)
+    ms, launches, clocks, _ = timed(step_device, args.steps, max(args.warmup, 3), True)
     log(f"device-resident arm: {ms / args.steps:.1f} ms/step")
     steps_run = [r.steps for r in res]
     timings = model.last_timings()
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 1, False)
+    # the e2e region ends when the token IDs are on the host: the library call returns with them, so the wall clock of the calls is the
+    # honest end (the event on the model stream cannot see the session's streams)
+    ms_e2e, _, _, wall_e2e = timed(step_e2e, args.steps, 1, False)
     log(f"e2e arm: {ms_e2e / args.steps:.1f} ms/step")
-    audio = world * B * AUDIO_SECONDS_PER_WINDOW * args.steps
+    audio = world * W * AUDIO_SECONDS_PER_WINDOW * args.steps
     value = audio / (ms / 1000.0)
     e2e_value = audio / (ms_e2e / 1000.0)
     ms_per_step = ms / args.steps
+    name = "whisper-large-v3" if args.variant == "large-v3" else f"whisper-{args.variant}"
+    cfg_name = {"large-v3": "BASELINE configs[1]", "large-v3-turbo": "BASELINE configs[3] shape, one GPU's share", "distil-large-v3": "distil decoder"}.get(args.variant, "")
+    workload = (f"{name} greedy {args.dtype}, {W} x 30 s windows per GPU through {B} decode slots ({cfg_name}), DecodingOptions defaults except "
+                f"firstTokenLogProbThreshold=nil and temperatureFallbackCount=0 (one greedy pass; random-init weights would otherwise always retry); ")
+    if args.eot_profile:
+        workload += (f"--eot-profile: per-window sampleLength from a seeded speech-like distribution (decode steps per window "
+                     f"{min(steps_run)}..{max(steps_run)}, mean {sum(steps_run) / len(steps_run):.0f}); ended windows retire, freed slots take the next windows; ")
+    else:
+        workload += f"sampleLength={args.sample_length} (decode steps per window: {min(steps_run)}..{max(steps_run)} - the worst case: real speech ends at EOT far earlier); "
+    workload += "timestamps on (TimestampRulesFilter active)"
 
     line = {
-        "metric": "RTFx (audio-sec/s) whisper-large-v3 greedy" if args.variant == "large-v3" else f"RTFx (audio-sec/s) whisper-{args.variant} greedy",
+        "metric": f"RTFx (audio-sec/s) {name} greedy",
         "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-        "data": "synthetic 16 kHz PCM (seeded noise + gated tones), seeded random weights of the large-v3 architecture",
-        "config": {"workload": f"whisper-{args.variant} greedy {args.dtype}, batch={B} x 30 s windows per GPU (BASELINE configs[1]), "
-                               f"DecodingOptions defaults except firstTokenLogProbThreshold=nil and temperatureFallbackCount=0 (one greedy pass; random-init "
-                               f"weights would otherwise always retry); sampleLength={args.sample_length} "
-                               f"(decode steps per window: {min(steps_run)}..{max(steps_run)}), timestamps on (TimestampRulesFilter active)",
-                   "windows_per_gpu": B, "sample_length": args.sample_length, "decode_steps": max(steps_run),
+        "data": f"synthetic 16 kHz PCM (seeded noise + gated tones), seeded random weights of the {args.variant} architecture",
+        "config": {"workload": workload,
+                   "windows_per_gpu": W, "decode_slots": B, "sample_length": args.sample_length, "decode_steps": max(steps_run),
+                   "decode_steps_total_per_gpu": int(sum(steps_run)), "eot_profile": bool(args.eot_profile),
                    "parallelism": f"dp{world} (windows sharded, weights replicated)",
-                   "l2": "inputs_larger_than_L2 (3.1 GB weights + 15.7 GB cross-KV streamed every step; no flush needed)",
-                   "stage_ms": timings},
-        "e2e": {"value": e2e_value, "unit": "audio-sec/s", "h2d_bytes_per_step": world * B * 480000 * 4,
+                   "l2": "inputs_larger_than_L2 (decoder weights + cross-KV of every live window streamed every step; no flush needed)",
+                   "stage_ms": timings, "scheduler": dec.stats()},
+        "e2e": {"value": e2e_value, "unit": "audio-sec/s", "h2d_bytes_per_step": world * W * 480000 * 4,
                 "d2h_bytes_per_step": world * d2h_bytes, "ms_per_step": ms_e2e / args.steps,
-                "path": "wk_transcribe_windows(host pinned PCM)" + (" + NCCL scatter/gather" if world > 1 else "")},
+                "wall_ms_per_step": wall_e2e / args.steps,
+                "path": "wk_transcribe_windows_ex(host pinned PCM)" + (" + NCCL scatter/gather" if world > 1 else "")},
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if world > 1 and rank == 0 and e2e_stages:
+        line["e2e"]["stage_ms_rank0"] = {k: round(v / max(1, e2e_stages.get("_calls", 1)), 2) for k, v in e2e_stages.items() if k != "_calls"}
+    assert sum(steps_run) <= expected_steps
 
     if rank == 0 and not args.no_roofline:
         peaks = measured_peaks()
@@ -402,40 +440,70 @@ def run_own_arm(args):
         wk_ = C.c_double()
         kernels = {}
         L, Ld = info.enc_layers, info.dec_layers
-        nsteps = max(steps_run)
-        nl, lb = C.c_int32(), (C.c_int32 * 2)()
-        check(lib.wk_session_lanes(dec.handle, C.byref(nl), lb))
-        n_lanes = int(nl.value)   # lane-local kernels (decoder) launch once per lane per layer-step, on lane_batch windows
-        per_step = {0: Ld * nsteps * n_lanes, 1: L, 2: 1, 3: L, 4: Ld * nsteps * n_lanes, 5: L}
-        line["config"]["decode_lanes"] = n_lanes
-        names = {0: "decoder_cross_attention_kernel", 1: "gemm_tcgen05_kernel[enc FC1 M=B*1500,N=5120,K=1280]", 2: "mel_pass1+pass2",
-                 3: "encoder_attention_kernel", 4: "gemm_tcgen05_kernel[dec QKV swap-AB N=3840,K=1280,split-K]",
-                 5: "gemm_tcgen05_kernel[enc QKV M=B*1500,N=3840,K=1280]"}
-        bound = {0: "hbm", 1: "tensor", 2: "hbm", 3: "tensor", 4: "hbm", 5: "tensor"}
-        for which in range(6):
+        d, H = info.d_model, info.n_heads
+        sched = dec.stats()                       # of the last step: decode steps launched, admissions ...
+        nsteps = max(1, sched["steps"])
+        live_frac = min(1.0, int(sum(steps_run)) / (nsteps * B))   # share of the slot-steps that carried a live window
+        # kernel id -> (name, bound, launches per step of the workload)
+        table = {
+            0: ("decoder_cross_attention_kernel", "hbm", Ld * nsteps),
+            1: (f"gemm_tcgen05_kernel[enc FC1+GELU M=B*1500,N={4 * d},K={d}]", "tensor", L * (W / B)),
+            2: ("mel_pass1+pass2", "hbm", W / B),
+            3: ("encoder_attention_tcgen05_kernel", "tensor", L * (W / B)),
+            4: (f"gemm_tcgen05_kernel[dec QKV swap-AB N={3 * d},K={d},split-K] (L2-warm)", "hbm", 0),
+            5: (f"gemm_tcgen05_kernel[enc QKV M=B*1500,N={3 * d},K={d}]", "tensor", L * (W / B)),
+            9: ("decoder_self_attention_kernel[pos 100]", "hbm", Ld * nsteps),
+            18: ("decoder_chain_kernel[B: out-proj > reduce+LN > cross-Q]", "hbm", Ld * nsteps),
+            19: ("decoder_chain_kernel[C: cross-out > LN > FC1 > GELU > FC2 > LN > QKV]", "hbm", Ld * nsteps),
+        }
+        for which, (kname, bound, per_step) in table.items():
             check(lib.wk_bench_kernel(model.handle, dec.handle, which, B, 20 if which != 2 else 5, C.byref(f), C.byref(wk_)))
             t_ms, work = float(f.value), float(wk_.value)
-            if bound[which] == "hbm":
+            if bound == "hbm":
                 ach, peak, unit = work / (t_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
             else:
                 ach, peak, unit = work / (t_ms * 1e-3) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
-            kernels[names[which]] = {"bound": bound[which], "ms": t_ms, "achieved": ach, "peak": peak, "unit": unit,
-                                     "frac": ach / peak, "launches_per_step": per_step[which],
-                                     "share_of_step": per_step[which] * t_ms / ms_per_step}
+            kernels[kname] = {"bound": bound, "ms": t_ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                              "algorithmic_work": work, "launches_per_step": per_step,
+                              "share_of_step": per_step * t_ms * (live_frac if which in (0, 9) else 1.0) / ms_per_step}
         log("per-kernel timings done")
-        dom = max(kernels.items(), key=lambda kv: kv[1]["share_of_step"])
-        traffic = None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel (same batch / model only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if args.variant == "large-v3" and B == 64 and dom[0] in tj:
-                traffic = tj[dom[0]]["bytes"]
+        traffic_file = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        tj = {}
+        try:
+            tj = json.load(open(traffic_file))
         except Exception:
             pass
+        for kname, k in kernels.items():   # DRAM bytes per launch from the committed ncu --set full captures (tools/ncu_traffic.py)
+            short = kname.split("[")[0]
+            ent = tj.get(kname) or tj.get(short)
+            k["traffic"] = ent["bytes"] if ent and args.variant == "large-v3" and B == 64 else None
+        dom = max(kernels.items(), key=lambda kv: kv[1]["share_of_step"])
         line["roofline"] = {"kernel": dom[0], "bound": dom[1]["bound"], "achieved": dom[1]["achieved"], "peak": dom[1]["peak"],
-                            "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": traffic,
+                            "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": dom[1]["traffic"],
                             "peak_source": peaks["source"] + " (MEASURED_PEAKS.json burst figures; kernel timed alone)",
                             "share_of_step": dom[1]["share_of_step"]}
         line["kernels"] = kernels
+        # whole decode step against HBM: what one step MUST stream = decoder weights (tied embedding included) once + the cross K/V of
+        # every live window + the self K/V read so far and the new rows written (SURVEY 8d "K6 decode step")
+        V = info.vocab
+        w_bytes = Ld * 12 * d * d * 2 + V * d * 2
+        cross_bytes = Ld * 2 * 1500 * d * 2
+        mean_pos = (max(steps_run) - 1) / 2.0
+        self_bytes = Ld * (2 * mean_pos * d * 2 + 2 * d * 2)
+        live = B * live_frac
+        step_bytes = w_bytes + live * (cross_bytes + self_bytes)
+        step_ms = timings["decodingLoop"] / max(1, nsteps)
+        line["roofline_step"] = {"bound": "hbm", "bytes_per_step": step_bytes, "ms_per_decode_step": step_ms,
+                                 "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs_sustained"] if "hbm_gbs_sustained" in peaks else peaks["hbm_gbs"],
+                                 "unit": "GB/s", "live_rows": live,
+                                 "what": "decoder weights once + cross K/V and self K/V of the live windows, divided by the measured decode-loop time per step"}
+        line["roofline_step"]["frac"] = line["roofline_step"]["achieved"] / line["roofline_step"]["peak"]
+        enc_flops = W * (2 * info.n_mels * 3 * d * 3000 + 2 * d * 3 * d * 1500 + L * (8 * 1500 * d * d + 4 * 1500 * 1500 * d + 16 * 1500 * d * d))
+        line["roofline_encoder"] = {"bound": "tensor", "flops": enc_flops, "ms": timings["encoding"],
+                                    "achieved": enc_flops / (timings["encoding"] * 1e-3) / 1e12 if timings["encoding"] else None,
+                                    "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s"}
+        if line["roofline_encoder"]["achieved"]:
+            line["roofline_encoder"]["frac"] = line["roofline_encoder"]["achieved"] / peaks["bf16_tflops_sustained"]
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

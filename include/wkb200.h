@@ -24,10 +24,14 @@
  * Conventions: plain C types only; every function returns a wk_status (0 = ok, negative = error, mapped
  * 1:1 onto WhisperError cases, Sources/WhisperKit/Utilities/WhisperError.swift:6-19); the message of the
  * last error on the calling thread is wk_last_error().  Host pointers may be pageable or pinned; pointers
- * documented as "host or device" are resolved with cudaPointerGetAttributes.  Handles are not thread-safe
- * individually; a wk_model may be shared by several wk_sessions (one per concurrent worker, mirroring
- * the per-task DecodingInputs of TranscribeTask.swift:83).  There is NO CPU fallback: every compute entry
- * point fails with WK_ERR_MODELS_UNAVAILABLE if no sm_100 device is present.
+ * documented as "host or device" are resolved with cudaPointerGetAttributes.
+ *
+ * Threading (the reference calls the same protocol objects from up to concurrentWorkerCount tasks, WhisperKit.swift:735-791):
+ * a finalized wk_model is immutable and may be used from any number of host threads - the model-level entry points
+ * (wk_mel, wk_encode, wk_filter_sample, wk_tensor_*) serialise internally; a wk_session (the per-task DecodingInputs of
+ * TranscribeTask.swift:83 plus its own mel/encoder workspace and CUDA streams) belongs to one thread at a time, and different
+ * sessions of one model run concurrently.  wk_tensor results own their device buffer until wk_tensor_free.
+ * There is NO CPU fallback: every compute entry point fails with WK_ERR_MODELS_UNAVAILABLE if no sm_100 device is present.
  */
 #ifndef WKB200_H
 #define WKB200_H
@@ -156,6 +160,10 @@ void wk_model_free(wk_model* m);
 wk_status wk_tensor_shape(const wk_tensor* t, int64_t* shape4, int32_t* ndim, int32_t* dtype);
 /* Copies to the host in the REFERENCE layout as f32: mel -> [B, nMels, 3000]; encoder output -> [B, d, 1500]. */
 wk_status wk_tensor_to_host(const wk_tensor* t, float* dst, int64_t dst_elems);
+/* Same, into a host MLMultiArray with explicit element strides (IOSurface-backed arrays pad their rows: every host access in the
+ * reference goes through `strides`, TextDecoder.swift:222-227, MLMultiArrayExtensions.swift:75-82): dst[b*stride_b + c*stride_c + t*stride_t]. */
+wk_status wk_tensor_to_host_strided(const wk_tensor* t, float* dst, int64_t stride_b, int64_t stride_c, int64_t stride_t, int64_t dst_elems);
+/* Releases the tensor and (stream-ordered, after its last reader) its device buffer. */
 void wk_tensor_free(wk_tensor* t);
 
 /* ---- FeatureExtracting ---- */
@@ -193,15 +201,47 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
  * results: array of `batch` wk_decode_result. */
 wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* opts,
                          const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
-/* Concurrent decode lanes of the session (2 once max_batch >= 32) and the windows bound to each. */
-wk_status wk_session_lanes(const wk_session* s, int32_t* n_lanes, int32_t* lane_batch2);
+/* Scheduler counters of the session's last batched call: [0] decode steps launched, [1] sum over those steps of the windows that were
+ * live when their burst started (an upper bound of the rows that actually streamed K/V), [2] windows admitted to a slot, [3] ladder
+ * re-admissions. */
+wk_status wk_session_stats(const wk_session* s, int64_t* out4);
 /* Device logits of the last step, copied to host (debug / parity). */
 wk_status wk_session_last_logits(wk_session* s, float* logits_out);
 
-/* ---- whole hot path: host PCM in, token IDs out (TranscribeTask.run body, batched) ---- */
+/* TranscriptionCallback (Models.swift TranscriptionProgress; TextDecoder.swift:724-762): called from the thread that runs the decode
+ * every `progress_every` decoder steps with each live window's current tokens.  Returning 0 is the reference's `callback -> false`:
+ * that window stops early (EarlyStopActor) and its result is built from the tokens it has. */
+typedef int32_t (*wk_progress_fn)(void* user, int32_t window, const int32_t* tokens, int32_t n_tokens, float avg_logprob);
+
+/* Per-item arguments of the batched entry points (transcribeWithOptions' decodeOptionsArray, WhisperKit.swift:716-735). */
+typedef struct wk_batch_opts {
+    const wk_decode_opts* opts;         /* n_opts == 1: shared by every window; else one per window */
+    int32_t n_opts;
+    const int32_t* const* prompts;      /* per-window initial prompts (prefillDecoderInputs output); NULL = one shared `prompt` */
+    const int32_t* prompt_lens;
+    const int32_t* prompt; int32_t n_prompt;   /* shared prompt when prompts == NULL; NULL too = built per window with wk_build_prompt */
+    wk_progress_fn progress; void* progress_user;
+    int32_t progress_every;             /* decoder steps between callbacks / completion polls; <= 0 = 16 */
+    wk_status* status;                  /* per-window Result<> (WhisperKit.swift:775-790): WK_OK or that window's error; may be NULL */
+    int32_t encoder_chunk;              /* windows per mel+encoder pass; <= 0 = the model's max_batch */
+} wk_batch_opts;
+
+/* ---- whole hot path: host PCM in, token IDs out (TranscribeTask.run body, batched) ----
+ * Windows are independent units.  The session's max_batch decode slots run as one device-resident loop; a window that ends (EOT,
+ * sampleLength, first-token threshold, early stop) retires from every kernel of the step at once and its slot is handed to the next
+ * encoded window, while the mel + encoder pass of the following chunk runs on a second stream (tensor-bound encoder under the
+ * HBM-bound decode).  The temperature ladder re-admits a window that asks for a fallback into its own slot (cross K/V kept). */
 wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_host /* host (pageable/pinned) or device */, int64_t n_windows, int64_t stride,
                                 const int32_t* samples_per_window, const wk_special_tokens* st, const wk_decode_opts* opts,
                                 const int32_t* prompt, int32_t n_prompt, wk_decode_result* results);
+/* decodeText on the bound windows with per-window options / prompts / status and the progress callback (no temperature ladder, like
+ * TextDecoding.decodeText itself). */
+wk_status wk_decode_text_ex(wk_session* s, const wk_special_tokens* st, const wk_batch_opts* bo, wk_decode_result* results);
+/* Same with per-window options / prompts / status and a progress callback.  Returns WK_OK when the call itself ran; per-window
+ * failures are reported through bo->status (and fail the call only when status is NULL). */
+wk_status wk_transcribe_windows_ex(wk_model* m, wk_session* s, const float* pcm_host, int64_t n_windows, int64_t stride,
+                                   const int32_t* samples_per_window, const wk_special_tokens* st, const wk_batch_opts* bo,
+                                   wk_decode_result* results);
 
 /* ---- long-form windowing: host logic, callable without a GPU ---- */
 typedef struct wk_tokenizer_hooks wk_tokenizer_hooks;   /* defined with the word-timestamp API below */
@@ -349,11 +389,19 @@ void* wk_model_stream(wk_model* m);
 /* ---- kernel-level test/bench hooks (used by tests/ and bench.py; device pointers) ---- */
 /* C[M,N] = A[M,K] * W[N,K]^T (+bias) with the tcgen05 GEMM; out_dtype WK_DTYPE_BF16/F16/F32. */
 wk_status wk_test_gemm(wk_model* m, const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
-                       int32_t in_dtype, int32_t out_dtype, int32_t gelu, int32_t simt_reference);
+                       int32_t in_dtype, int32_t out_dtype, int32_t gelu);
 /* Same product through the decoder's swap-AB split-K path: out f32 [rows_x, N]. */
 wk_status wk_test_gemm_splitk(wk_model* m, const void* w, const void* x, float* out, int32_t N, int32_t rows_x, int32_t K, int32_t in_dtype, int32_t splits);
 /* Encoder attention on packed qkv [B*T, 3*d] -> out [B*T, d]. */
 wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, int32_t T, int32_t n_heads, int32_t dtype);
+/* Decoder cross-attention kernel alone: q [B][H*64] f32, K/V [B][H][T][64] 16-bit -> out [B][H*64] 16-bit; done (device, may be NULL)
+ * marks rows to skip. */
+wk_status wk_test_cross_attention(wk_model* m, const float* q, const void* kcross, const void* vcross, void* out, int32_t B, int32_t H,
+                                  int32_t T, int32_t dtype, const int32_t* done);
+/* Decoder self-attention kernel alone: qkv [B][3*H*64] f32 of the new token, caches [B][H][224][64] 16-bit (positions < pos[b] valid;
+ * row pos[b] is appended), pos [B] device -> out [B][H*64] 16-bit. */
+wk_status wk_test_self_attention(wk_model* m, const float* qkv, void* kcache, void* vcache, const int32_t* pos, void* out, int32_t B,
+                                 int32_t H, int32_t dtype, const int32_t* done);
 
 /* Average device time (ms) of one launch of a named hot kernel on the live buffers, plus its algorithmic work
  * (bytes for HBM-bound kernels, FLOPs for tensor-bound ones): 0 decoder cross-attention, 1 encoder FC1 GEMM,

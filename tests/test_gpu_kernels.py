@@ -49,7 +49,7 @@ def test_gemm_tcgen05_vs_torch(toy, dt, M, N, K, gelu, out32):
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out32 else tdt)
     _sync()
     wk._lib.check(toy.lib.wk_test_gemm(toy.handle, p(a), p(w), p(bias), p(out), M, N, K, wdt,
-                                       _lib.WK_DTYPE_F32 if out32 else wdt, gelu, 0))
+                                       _lib.WK_DTYPE_F32 if out32 else wdt, gelu))
     torch.cuda.current_stream().synchronize()
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t() + bias
@@ -80,7 +80,73 @@ def test_gemm_swap_ab_splitk(toy, N, rows, Kd, splits):
 
 
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
-@pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (1, 200, 1), (3, 77, 2)])
+@pytest.mark.parametrize("B,H", [(64, 20), (3, 6), (1, 2)])
+def test_decoder_cross_attention_kernel_vs_torch(toy, dt, B, H):
+    """decoder_cross_attention_kernel alone at the benchmarked lane shape (B = 64 windows, H = 20 heads, T = 1500 encoder positions)
+    against torch fp32 on the same 16-bit K/V; rows flagged done must be left untouched (ended windows skip their K/V stream)."""
+    tdt, wdt = TD[dt]
+    T, dm = 1500, H * 64
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + H)
+    q = torch.randn(B, dm, device="cuda", generator=g)
+    k = (torch.randn(B, H, T, 64, device="cuda", generator=g) * 0.7).to(tdt)
+    v = torch.randn(B, H, T, 64, device="cuda", generator=g).to(tdt)
+    if B > 2:   # a peaked row: one key dominates (exercises the max subtraction)
+        k[1, 0, 777] = (q[1, :64] * 3).to(tdt)
+    out = torch.full((B, dm), 7.0, device="cuda", dtype=tdt)
+    done = torch.zeros(B, dtype=torch.int32, device="cuda")
+    if B > 2:
+        done[2] = 1
+    _sync()
+    wk._lib.check(toy.lib.wk_test_cross_attention(toy.handle, p(q), p(k), p(v), p(out), B, H, T, wdt, p(done)))
+    torch.cuda.synchronize()
+    qh = q.view(B, H, 1, 64)
+    ref = (torch.softmax(qh @ k.float().transpose(-1, -2) * 0.125, dim=-1) @ v.float()).reshape(B, dm)
+    got = out.float()
+    live = done == 0
+    err = (got[live] - ref[live]).abs().max().item()
+    tol = (8e-3 if dt == "bf16" else 1e-3) * max(1.0, ref.abs().max().item())   # f32 math, 16-bit output rounding
+    assert err <= tol, err
+    if B > 2:
+        assert torch.all(got[2] == 7.0)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("B,H", [(64, 20), (5, 6)])
+def test_decoder_self_attention_kernel_vs_torch(toy, dt, B, H):
+    """decoder_self_attention_kernel alone at B = 64, H = 20 with per-row positions 0 / 1 / 100 / 222 (and everything between): reduces
+    the q|k|v row, appends K/V at pos[b] in the cache, attends over positions <= pos[b]; against torch fp32."""
+    tdt, wdt = TD[dt]
+    dm, L = H * 64, 224
+    g = torch.Generator(device="cuda").manual_seed(B * 3 + H)
+    qkv = torch.randn(B, 3 * dm, device="cuda", generator=g)
+    kc = torch.randn(B, H, L, 64, device="cuda", generator=g).to(tdt)
+    vc = torch.randn(B, H, L, 64, device="cuda", generator=g).to(tdt)
+    pos_list = [0, 1, 100, 222] + [int(x) for x in torch.randint(0, 223, (max(0, B - 4),), generator=torch.Generator().manual_seed(B))]
+    pos = torch.tensor(pos_list[:B], dtype=torch.int32, device="cuda")
+    out = torch.full((B, dm), 7.0, device="cuda", dtype=tdt)
+    done = torch.zeros(B, dtype=torch.int32, device="cuda")
+    done[B - 1] = 1
+    kc0, vc0 = kc.clone(), vc.clone()
+    _sync()
+    wk._lib.check(toy.lib.wk_test_self_attention(toy.handle, p(qkv), p(kc), p(vc), p(pos), p(out), B, H, wdt, p(done)))
+    torch.cuda.synchronize()
+    q, kn, vn = [t.view(B, H, 64) for t in qkv.split(dm, dim=1)]
+    worst = 0.0
+    for b in range(B - 1):
+        t = int(pos[b])
+        kk = torch.cat([kc0[b, :, :t].float(), kn[b].to(tdt).float()[:, None]], dim=1)     # [H, t+1, 64]
+        vv = torch.cat([vc0[b, :, :t].float(), vn[b].to(tdt).float()[:, None]], dim=1)
+        ref = (torch.softmax(q[b][:, None] @ kk.transpose(-1, -2) * 0.125, dim=-1) @ vv).reshape(dm)
+        worst = max(worst, (out[b].float() - ref).abs().max().item() / max(1.0, ref.abs().max().item()))
+        # the new row landed in the cache, rounded to the storage type; older rows are untouched
+        assert torch.equal(kc[b, :, t], kn[b].to(tdt)) and torch.equal(vc[b, :, t], vn[b].to(tdt))
+        assert torch.equal(kc[b, :, :t], kc0[b, :, :t])
+    assert worst <= (8e-3 if dt == "bf16" else 1e-3), worst
+    assert torch.all(out[B - 1].float() == 7.0) and torch.equal(kc[B - 1], kc0[B - 1])   # done row: no cache traffic at all
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (1, 200, 1), (3, 77, 2), (2, 1500, 20)])
 def test_encoder_attention_vs_torch(toy, dt, B, T, H):
     tdt, wdt = TD[dt]
     dm = H * 64
@@ -216,3 +282,16 @@ def test_temperature_topk_sampling_vs_oracle(toy):
     assert len(set(np.round(counts))) > 1
     tok1, lp1, _ = wk.filter_and_sample(toy, logits[:4], [[1]] * 4, st, wk.DecodingOptions(temperature=T, topK=1, seed=9))
     assert all(t == int(np.argmax(base)) for t in tok1)
+
+
+def test_sampler_row_without_finite_logit_is_flagged(toy):
+    """A row whose every logit is -inf (or NaN) has no argmax: the kernel reports token -1 / logprob -inf instead of an out-of-range id
+    (in the decode loop the window ends there and the host reports WhisperError.decodingLogitsFailed)."""
+    st = wk.SpecialTokens()
+    logits = np.full((3, 64), -np.inf, np.float32)
+    logits[1, 5] = 1.0
+    logits[2, :] = np.nan
+    tok, lp, _ = wk.filter_and_sample(toy, logits, [[1], [1], [1]], st)
+    assert tok[0] == -1 and np.isneginf(lp[0])
+    assert tok[1] == 5 and abs(lp[1]) < 1e-6
+    assert tok[2] == -1

@@ -226,32 +226,6 @@ def test_model_load_from_safetensors_checkpoint(tmp_path):
     m2.close()
 
 
-def test_two_decode_lanes_match_single_lane(monkeypatch):
-    """Opt-in second decode lane (own stream / KV caches / state for half of the windows): results must be
-    bit-identical to the single-lane schedule and keep the window order."""
-    dims, orc, model = build("toy", "bf16", 35, seed=8)
-    st = wk.SpecialTokens.from_any(D.SpecialTokens.toy(dims.vocab))
-    fe, enc = wk.FeatureExtractor(model), wk.AudioEncoder(model)
-    pcm = np.stack([mel_ref.synthetic_pcm(40 + i) for i in range(35)]).astype(np.float32)
-    enc_t = enc.encodeFeatures(fe.logMelSpectrogram(pcm))
-    o = wk.DecodingOptions(firstTokenLogProbThreshold=None, sampleLength=14)
-    monkeypatch.setenv("WKB200_DECODE_LANES", "2")
-    dual = wk.TextDecoder(model, 35)
-    monkeypatch.delenv("WKB200_DECODE_LANES")
-    single = wk.TextDecoder(model, 35)
-    prompt = dual.prefillDecoderInputs(o, st)
-    r2 = dual.decodeText(enc_t, prompt, o, st)
-    lg2 = dual.lastLogits()
-    r1 = single.decodeText(enc_t, prompt, o, st)
-    lg1 = single.lastLogits()
-    assert [x.tokens for x in r1] == [x.tokens for x in r2]
-    np.testing.assert_array_equal(lg1, lg2)
-    assert np.abs(lg2[0] - lg2[34]).max() > 0  # rows belong to different windows (an order mix-up would show)
-    dual.close()
-    single.close()
-    model.close()
-
-
 def test_detect_language_matches_oracle():
     """detectLanguage: one step on [SOT], LanguageLogitsFilter, greedy (TextDecoder.swift:420-539)."""
     B = 3
@@ -593,12 +567,12 @@ def test_transcribe_audio_text_and_words_with_library_tokenizer():
     assert all("<|" not in g.text for g in r2.segments) and all(g.words is None for g in r2.segments)
 
 
-@pytest.mark.skipif(os.environ.get("WKB200_TEST_FUSED") != "1", reason="experimental fused decoder chains: opt-in bring-up test (WKB200_TEST_FUSED=1)")
 def test_fused_decoder_chains_match_the_launch_per_phase_path():
-    """csrc/fused_chain.cu (WKB200_FUSED=1) keeps the arithmetic and its order: tokens and logits must be bit-identical to the default path."""
+    """csrc/fused_chain.cu (the default decode schedule) keeps the arithmetic and its order: tokens and logits must be bit-identical to
+    the launch-per-phase schedule (WKB200_FUSED=0), at toy widths and at d = 1280 / H = 20 / V = 51866."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fused_check.py")], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fused_check.py")], capture_output=True, text=True, timeout=600)
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0

@@ -1,15 +1,22 @@
 #!/bin/bash
-# Runs each GPU test stage under its own timeout so one hang cannot take the others down.
-# usage: tools/gpu_stage.sh <logdir> ; results in <logdir>/*.log
-cd "$(dirname "$0")/.."
-OUT=${1:-gpurun_out/stage}
-mkdir -p "$OUT"
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > "$OUT/gpu.txt" 2>&1
-run() { name=$1; shift; echo "=== $name"; timeout 300 "$@" > "$OUT/$name.log" 2>&1; echo "exit $?" >> "$OUT/$name.log"; tail -5 "$OUT/$name.log"; }
-run gemm python -m pytest tests/test_gpu_kernels.py -x -q -k "gemm_tcgen05" -p no:cacheprovider
-run splitk python -m pytest tests/test_gpu_kernels.py -x -q -k "swap_ab" -p no:cacheprovider
-run attn python -m pytest tests/test_gpu_kernels.py -x -q -k "attention" -p no:cacheprovider
-run mel python -m pytest tests/test_gpu_kernels.py -x -q -k "log_mel" -p no:cacheprovider
-run filters python -m pytest tests/test_gpu_kernels.py -x -q -k "filter" -p no:cacheprovider
-run pipeline python -m pytest tests/test_gpu_pipeline.py -x -q -s -p no:cacheprovider
-run smoke python __graft_entry__.py smoke
+# One GPU-box visit: the parity suite under the launch-per-phase schedule, the fused-chain bit-identity check, the suite again on the
+# fused (default) schedule, then short bench runs of both.  Everything lands in gpurun_out/$1.
+out=gpurun_out/${1:-stage}
+mkdir -p $out
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $out/gpu.txt 2>&1
+(time WKB200_FUSED=0 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 -s) > $out/pytest_unfused.log 2>&1
+echo "unfused rc $?" >> $out/summary.txt
+(time timeout 600 python tools/fused_check.py) > $out/fused_check.log 2>&1
+rc=$?
+echo "fused_check rc $rc" >> $out/summary.txt
+if [ $rc -eq 0 ]; then
+  (time timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_scheduler.py -m gpu -q --timeout 600 -s) > $out/pytest_fused.log 2>&1
+  echo "fused suite rc $?" >> $out/summary.txt
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_fused.json 2> $out/bench_fused.err
+  echo "bench fused rc $?" >> $out/summary.txt
+fi
+WKB200_FUSED=0 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-roofline > $out/bench_unfused.json 2> $out/bench_unfused.err
+echo "bench unfused rc $?" >> $out/summary.txt
+cat $out/summary.txt
+tail -5 $out/pytest_unfused.log

@@ -74,6 +74,17 @@ class wk_decode_result(C.Structure):
     ]
 
 
+PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_float)
+
+
+class wk_batch_opts(C.Structure):
+    _fields_ = [("opts", C.POINTER(wk_decode_opts)), ("n_opts", C.c_int32),
+                ("prompts", C.POINTER(C.POINTER(C.c_int32))), ("prompt_lens", C.POINTER(C.c_int32)),
+                ("prompt", C.POINTER(C.c_int32)), ("n_prompt", C.c_int32),
+                ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("progress_every", C.c_int32),
+                ("status", C.POINTER(C.c_int32)), ("encoder_chunk", C.c_int32)]
+
+
 class wk_segment(C.Structure):
     _fields_ = [("stream", C.c_int32), ("id", C.c_int32), ("seek", C.c_int64), ("start", C.c_float), ("end", C.c_float),
                 ("token_offset", C.c_int64), ("n_tokens", C.c_int32), ("temperature", C.c_float), ("avg_logprob", C.c_float),
@@ -111,6 +122,7 @@ SYMBOLS = [
     ("wk_model_free", None, [P]),
     ("wk_tensor_shape", I32, [P, PI64, PI32, PI32]),
     ("wk_tensor_to_host", I32, [P, P, I64]),
+    ("wk_tensor_to_host_strided", I32, [P, P, I64, I64, I64, I64]),
     ("wk_tensor_free", None, [P]),
     ("wk_mel", I32, [P, P, I64, I64, PI32, C.POINTER(P)]),
     ("wk_encode", I32, [P, P, C.POINTER(P)]),
@@ -126,7 +138,10 @@ SYMBOLS = [
     ("wk_decode_text", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts), PI32, I32,
                              C.POINTER(wk_decode_result)]),
     ("wk_session_last_logits", I32, [P, P]),
-    ("wk_session_lanes", I32, [P, PI32, PI32]),
+    ("wk_session_stats", I32, [P, PI64]),
+    ("wk_decode_text_ex", I32, [P, C.POINTER(wk_special_tokens), C.POINTER(wk_batch_opts), C.POINTER(wk_decode_result)]),
+    ("wk_transcribe_windows_ex", I32, [P, P, P, I64, I64, PI32, C.POINTER(wk_special_tokens), C.POINTER(wk_batch_opts),
+                                       C.POINTER(wk_decode_result)]),
     ("wk_transcribe_windows", I32, [P, P, P, I64, I64, PI32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts),
                                     PI32, I32, C.POINTER(wk_decode_result)]),
     ("wk_find_seek_point_and_segments", I32, [PI32, PF32, I32, F32, F32, F32, F32, C.POINTER(wk_decode_opts), I32, I64, I64, I32, I32,
@@ -175,7 +190,9 @@ SYMBOLS = [
     ("wk_kernel_launch_count", I64, [I32]),
     ("wk_last_timings", I32, [P, PF32]),
     ("wk_model_stream", P, [P]),
-    ("wk_test_gemm", I32, [P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32]),
+    ("wk_test_gemm", I32, [P, P, P, P, P, I32, I32, I32, I32, I32, I32]),
+    ("wk_test_cross_attention", I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
+    ("wk_test_self_attention", I32, [P, P, P, P, P, P, I32, I32, I32, P]),
     ("wk_test_gemm_splitk", I32, [P, P, P, P, I32, I32, I32, I32, I32]),
     ("wk_test_attention", I32, [P, P, P, I32, I32, I32, I32]),
     ("wk_debug_read", I32, [P, P, I32, I64, P, I64]),

@@ -22,8 +22,8 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import (WK_DTYPE_BF16, WK_DTYPE_F16, WK_DTYPE_F32, WhisperError, check, wk_decode_opts, wk_decode_result,
-                   wk_model_config, wk_model_info, wk_special_tokens)
+from ._lib import (PROGRESS_FN, WK_DTYPE_BF16, WK_DTYPE_F16, WK_DTYPE_F32, WhisperError, check, wk_batch_opts, wk_decode_opts,
+                   wk_decode_result, wk_model_config, wk_model_info, wk_special_tokens)
 
 MAX_TOKEN_CONTEXT = 224  # Constants.maxTokenContext (Models.swift:1334)
 WINDOW_SAMPLES = 480000  # Constants.defaultWindowSamples (Models.swift:1457)
@@ -252,10 +252,22 @@ class Model:
 
 class DeviceTensor:
     """Opaque device buffer handed between mel -> encoder -> decoder (the reference's marker protocols
-    FeatureExtractorOutputType / AudioEncoderOutputType allow exactly this, FeatureExtractor.swift:10-11)."""
+    FeatureExtractorOutputType / AudioEncoderOutputType allow exactly this, FeatureExtractor.swift:10-11).  Owns its buffer, like the
+    MLMultiArray the reference returns: released with the object."""
 
     def __init__(self, model: Model, handle):
         self.model, self.handle = model, handle
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value and getattr(self.model, "handle", None) and self.model.handle.value:
+            self.model.lib.wk_tensor_free(self.handle)
+        self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @property
     def shape(self):
@@ -264,9 +276,14 @@ class DeviceTensor:
         check(self.model.lib.wk_tensor_shape(self.handle, shp, C.byref(nd), C.byref(dt)))
         return tuple(shp[: nd.value])
 
-    def numpy(self) -> np.ndarray:
-        """Reference layout, f32: mel [B, nMels, 3000]; encoder output [B, d, 1500]."""
+    def numpy(self, row_pad: int = 0) -> np.ndarray:
+        """Reference layout, f32: mel [B, nMels, 3000]; encoder output [B, d, 1500].  row_pad > 0 reads back through explicit element
+        strides into rows padded by that many elements (how an IOSurface-backed MLMultiArray lays its rows out)."""
         b, c, _, t = self.shape
+        if row_pad:
+            buf = np.zeros((b, c, t + row_pad), dtype=np.float32)
+            check(self.model.lib.wk_tensor_to_host_strided(self.handle, _ptr(buf), c * (t + row_pad), t + row_pad, 1, buf.size))
+            return buf[:, :, :t]
         out = np.empty((b, c, t), dtype=np.float32)
         check(self.model.lib.wk_tensor_to_host(self.handle, _ptr(out), out.size))
         return out
@@ -377,15 +394,17 @@ class TextDecoder:
         check(self.lib.wk_decode_step(self.handle, ids, cl, _ptr(out)))
         return out
 
-    def decodeText(self, encoderOutput: Optional[DeviceTensor], prompt: Sequence[int], options: DecodingOptions,
-                   specialTokens: SpecialTokens) -> List[DecodingResult]:
+    def decodeText(self, encoderOutput: Optional[DeviceTensor], prompt, options, specialTokens: SpecialTokens,
+                   callback=None, callbackEvery: int = 0) -> List[DecodingResult]:
+        """decodeText for every bound window.  `prompt` / `options` may be one shared value or one per window;
+        callback(window, tokens, avgLogprob) -> bool is the TranscriptionCallback (False = stop that window early)."""
         if encoderOutput is not None:
             self.bindEncoderOutput(encoderOutput)
         st = specialTokens.to_c()
-        o, keep = options.to_c()
-        p = (C.c_int32 * len(prompt))(*[int(v) for v in prompt])
-        res = (wk_decode_result * self.batch)()
-        check(self.lib.wk_decode_text(self.handle, C.byref(st), C.byref(o), p, len(prompt), res))
+        n = self.batch
+        bo, keep = make_batch_opts(n, options, prompt, callback, callbackEvery, None)
+        res = (wk_decode_result * n)()
+        check(self.lib.wk_decode_text_ex(self.handle, C.byref(st), C.byref(bo), res))
         return [DecodingResult.from_c(r) for r in res]
 
     def detectLanguage(self, encoderOutput: Optional[DeviceTensor], specialTokens: SpecialTokens, allLanguageTokens: Sequence[int],
@@ -406,6 +425,12 @@ class TextDecoder:
         check(self.lib.wk_session_alignment_weights(self.handle, window, rows, _ptr(out)))
         return out
 
+    def stats(self) -> dict:
+        """Scheduler counters of the last batched call (decode steps launched, live-row steps, admissions, ladder re-admissions)."""
+        a = (C.c_int64 * 4)()
+        check(self.lib.wk_session_stats(self.handle, a))
+        return dict(zip(("steps", "row_steps", "admissions", "ladder"), [int(v) for v in a]))
+
     def lastLogits(self) -> np.ndarray:
         out = np.empty((self.batch, self.logitsSize), dtype=np.float32)
         check(self.lib.wk_session_last_logits(self.handle, _ptr(out)))
@@ -421,6 +446,49 @@ class TextDecoder:
             self.close()
         except Exception:
             pass
+
+
+def make_batch_opts(n: int, options, prompt, callback=None, callbackEvery: int = 0, status=None, encoderChunk: int = 0):
+    """wk_batch_opts for n windows.  options: DecodingOptions or a list of n; prompt: None (built per window from the options), one token
+    list, or a list of n token lists.  Returns (struct, keepalive)."""
+    keep = []
+    bo = wk_batch_opts()
+    opt_list = list(options) if isinstance(options, (list, tuple)) else [options]
+    if len(opt_list) not in (1, n):
+        raise ValueError(f"{len(opt_list)} DecodingOptions for {n} windows")
+    arr = (wk_decode_opts * len(opt_list))()
+    for i, o in enumerate(opt_list):
+        c, k = o.to_c()
+        arr[i] = c
+        keep.append(k)
+    keep.append(arr)
+    bo.opts, bo.n_opts = arr, len(opt_list)
+    if prompt is not None and len(prompt) > 0 and isinstance(prompt[0], (list, tuple, np.ndarray)):
+        if len(prompt) != n:
+            raise ValueError(f"{len(prompt)} prompts for {n} windows")
+        rows = [(C.c_int32 * max(1, len(p)))(*[int(v) for v in p]) for p in prompt]
+        ptrs = (C.POINTER(C.c_int32) * n)(*[C.cast(r, C.POINTER(C.c_int32)) for r in rows])
+        lens = (C.c_int32 * n)(*[len(p) for p in prompt])
+        keep += [rows, ptrs, lens]
+        bo.prompts, bo.prompt_lens = ptrs, lens
+    elif prompt is not None:
+        p = (C.c_int32 * max(1, len(prompt)))(*[int(v) for v in prompt])
+        keep.append(p)
+        bo.prompt, bo.n_prompt = p, len(prompt)
+    if callback is not None:
+        def tramp(user, window, tokens, n_tokens, avg):
+            try:
+                return 1 if callback(int(window), [int(tokens[i]) for i in range(n_tokens)], float(avg)) is not False else 0
+            except Exception:
+                return 0
+        fn = PROGRESS_FN(tramp)
+        keep.append(fn)
+        bo.progress = fn
+    bo.progress_every = int(callbackEvery)
+    if status is not None:
+        bo.status = status
+    bo.encoder_chunk = int(encoderChunk)
+    return bo, keep
 
 
 def filter_and_sample(model: Model, logits: np.ndarray, tokens: Sequence[Sequence[int]], specialTokens: SpecialTokens,
@@ -507,29 +575,50 @@ class WhisperKit:
         else:
             self.specialTokens = SpecialTokens()
 
-    def transcribe(self, audioArrays, decodeOptions: Optional[DecodingOptions] = None,
-                   samplesPerWindow: Optional[Sequence[int]] = None) -> List[DecodingResult]:
-        """audioArrays: host float32 [N, stride<=480000-padded] (numpy, or pinned torch CPU tensor).  One
-        DecodingResult per window, in order."""
-        opts = decodeOptions or DecodingOptions()
+    def resolveLanguage(self, opts: DecodingOptions) -> DecodingOptions:
+        """DecodingOptions.language -> the "<|xx|>" token id through the tokenizer, as prefillDecoderInputs does with
+        tokenizer.convertTokenToId (TextDecoder.swift:181-186).  No tokenizer = an error, never a silent <|en|>."""
+        if opts.language is None or opts.languageToken is not None or not self.textDecoder.isModelMultilingual:
+            return opts
+        if self.tokenizer is None:
+            raise WhisperError(-4, f"DecodingOptions.language={opts.language!r} needs a tokenizer to resolve <|{opts.language}|> (or set languageToken)")
+        tok = self.tokenizer.convertTokenToId(f"<|{opts.language}|>")
+        if tok is None or tok < 0:
+            raise WhisperError(-4, f"the tokenizer has no <|{opts.language}|> token")
+        import dataclasses
+        return dataclasses.replace(opts, languageToken=int(tok))
+
+    def transcribe(self, audioArrays, decodeOptions=None, samplesPerWindow: Optional[Sequence[int]] = None, callback=None,
+                   callbackEvery: int = 0, returnErrors: bool = False, encoderChunk: int = 0):
+        """audioArrays: host float32 [N, stride<=480000-padded] (numpy, or pinned torch CPU tensor).  decodeOptions: one DecodingOptions
+        or one per window (transcribeWithOptions' decodeOptionsArray, WhisperKit.swift:716-735).  One DecodingResult per window, in order;
+        with returnErrors a window that failed yields its WhisperError instead of failing the call (the reference's Result<>, :775-790)."""
         a = audioArrays
         if not hasattr(a, "data_ptr"):
             a = np.ascontiguousarray(a, dtype=np.float32)
         if a.ndim == 1:
             a = a[None]
         n, stride = int(a.shape[0]), int(a.shape[1])
-        prompt = self.textDecoder.prefillDecoderInputs(opts if opts.usePrefillPrompt else None, self.specialTokens)
+        if isinstance(decodeOptions, (list, tuple)):
+            opts = [self.resolveLanguage(o or DecodingOptions()) for o in decodeOptions]
+        else:
+            opts = self.resolveLanguage(decodeOptions or DecodingOptions())
         st = self.specialTokens.to_c()
-        o, keep = opts.to_c()
-        p = (C.c_int32 * len(prompt))(*prompt)
+        status = (C.c_int32 * n)() if returnErrors else None
+        bo, keep = make_batch_opts(n, opts, None, callback, callbackEvery, status, encoderChunk)
         spw = None
         if samplesPerWindow is not None:
             spw = (C.c_int32 * n)(*[int(v) for v in samplesPerWindow])
         res = (wk_decode_result * n)()
-        check(self.model.lib.wk_transcribe_windows(self.model.handle, self.textDecoder.handle, _ptr(a), n, stride, spw,
-                                                   C.byref(st), C.byref(o), p, len(prompt), res))
+        # the prompt of every window is built inside the library from that window's options (prefillDecoderInputs); decodeWithFallback
+        # (TranscribeTask.swift:316-411) runs there too: a window whose DecodingFallback asks for it is decoded again at the next temperature
+        check(self.model.lib.wk_transcribe_windows_ex(self.model.handle, self.textDecoder.handle, _ptr(a), n, stride, spw, C.byref(st),
+                                                      C.byref(bo), res))
         self.textDecoder.batch = min(n, self.config.maxBatch)
-        # decodeWithFallback (TranscribeTask.swift:316-411) runs inside wk_transcribe_windows: windows whose
-        # DecodingFallback.needsFallback is set are decoded again from the same encoder output at the next ladder temperature.
-        out = [DecodingResult.from_c(r) for r in res]
+        out = []
+        for i, r in enumerate(res):
+            if returnErrors and status[i] != 0:
+                out.append(WhisperError(int(status[i]), f"window {i} failed"))
+            else:
+                out.append(DecodingResult.from_c(r))
         return out

@@ -336,9 +336,6 @@ wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, in
     p.idesc_pv = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(kFaD >> 3) << 17) |
                  ((uint32_t)(kFaBM >> 4) << 24);
     p.v_lbo = 1; p.v_sbo = 64; p.v_kstep = 2048;
-    if (const char* e = getenv("WKB200_FA_VLBO")) p.v_lbo = (uint32_t)atoi(e);
-    if (const char* e = getenv("WKB200_FA_VSBO")) p.v_sbo = (uint32_t)atoi(e);
-    if (const char* e = getenv("WKB200_FA_VKSTEP")) p.v_kstep = (uint32_t)atoi(e);
     dim3 grid((T + kFaBM - 1) / kFaBM, B * n_heads);
     cudaError_t e;
     if (dtype == WK_DTYPE_F16) {

@@ -40,28 +40,34 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 // =====================================================================================================
 // decode state
 // =====================================================================================================
-__global__ void decode_state_init_kernel(DecodeState st, const int32_t* __restrict__ prompt, int n_prompt, int B) {
-    const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < kMaxCtx; i += blockDim.x) {
-        st.tokens[b * kMaxCtx + i] = i < n_prompt ? prompt[i] : 0;
-        st.logprobs[b * kMaxCtx + i] = 0.f;
+__global__ void decode_slots_init_kernel(DecodeState st, RowParams* __restrict__ rp_dev, const int32_t* __restrict__ slot_ids,
+                                         const int32_t* __restrict__ prompts, const RowParams* __restrict__ rp_new) {
+    const int i = blockIdx.x, b = slot_ids[i];
+    const RowParams R = rp_new[i];
+    const int n_prompt = R.prompt_len;
+    for (int t = threadIdx.x; t < kMaxCtx; t += blockDim.x) {
+        st.tokens[b * kMaxCtx + t] = t < n_prompt ? prompts[i * kMaxCtx + t] : 0;
+        st.logprobs[b * kMaxCtx + t] = 0.f;
     }
     if (threadIdx.x == 0) {
+        rp_dev[b] = R;
         st.n_tokens[b] = n_prompt;
-        st.next_token[b] = n_prompt > 0 ? prompt[n_prompt - 1] : 0;
+        st.next_token[b] = n_prompt > 0 ? prompts[i * kMaxCtx + n_prompt - 1] : 0;
         st.done[b] = 0;
         st.first_low[b] = 0;
         st.steps[b] = 0;
         st.input_ids[b] = 0;
-        if (b == 0) { *st.step = 0; *st.n_done = 0; }
+        st.error[b] = 0;
     }
 }
 
-wk_status decode_state_init(DecodeState st, const int32_t* prompt_dev, int n_prompt, int B, cudaStream_t stream) {
-    decode_state_init_kernel<<<B, 64, 0, stream>>>(st, prompt_dev, n_prompt, B);
+wk_status decode_slots_init(DecodeState st, RowParams* rp_dev, const int32_t* slot_ids, const int32_t* prompts, const RowParams* rp_new,
+                            int n, cudaStream_t stream) {
+    if (n < 1) return WK_OK;
+    decode_slots_init_kernel<<<n, 64, 0, stream>>>(st, rp_dev, slot_ids, prompts, rp_new);
     count_launch();
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("decode_state_init launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    if (e != cudaSuccess) { set_error("decode_slots_init launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     return WK_OK;
 }
 
@@ -71,22 +77,24 @@ wk_status decode_state_init(DecodeState st, const int32_t* prompt_dev, int n_pro
 template <typename T>
 __global__ void __launch_bounds__(256)
 decoder_embed_ln_kernel(const T* __restrict__ emb, const float* __restrict__ pos_emb, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, DecodeState st, int prompt_len, int ts_begin, float* __restrict__ x,
-                        T* __restrict__ xn, int d, int explicit_inputs, const int32_t* __restrict__ explicit_pos) {
+                        const float* __restrict__ beta, DecodeState st, int vocab, int ts_begin, float* __restrict__ x,
+                        T* __restrict__ xn, int d, const int32_t* __restrict__ explicit_pos) {
     __shared__ float scratch[32];
     const int b = blockIdx.x, tid = threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
     int tok, pos;
-    if (explicit_inputs) {
+    if (explicit_pos) {
         tok = st.input_ids[b];
         pos = explicit_pos[b];
     } else {
-        const int step = *st.step;
+        if (st.done[b]) return;          // the window has ended: its row of the step is dead (x / xn keep their last values)
+        const int step = st.steps[b];
+        const int prompt_len = st.rp[b].prompt_len;
         pos = step;
         tok = st.next_token[b];
         bool overwrite = false;
-        if (!st.done[b] && step < prompt_len) {
+        if (step < prompt_len) {
             const int cur = st.tokens[b * kMaxCtx + step];
             const bool is_ts = cur >= ts_begin, pred_ts = tok >= ts_begin;
             if (!(step == prompt_len - 1 && is_ts && pred_ts)) tok = cur;
@@ -98,6 +106,7 @@ decoder_embed_ln_kernel(const T* __restrict__ emb, const float* __restrict__ pos
             st.input_ids[b] = tok;
         }
     }
+    tok = min(max(tok, 0), vocab - 1);   // never index the embedding table out of bounds
     float v[8];
     float s = 0.f;
 #pragma unroll
@@ -125,14 +134,13 @@ decoder_embed_ln_kernel(const T* __restrict__ emb, const float* __restrict__ pos
     }
 }
 
-wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gamma, const float* beta, DecodeState st,
-                           int prompt_len, int ts_begin, float* x, void* xn, int B, int d, int dtype, int explicit_inputs,
-                           const int32_t* explicit_pos, cudaStream_t stream) {
+wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gamma, const float* beta, DecodeState st, int vocab,
+                           int ts_begin, float* x, void* xn, int B, int d, int dtype, const int32_t* explicit_pos, cudaStream_t stream) {
     if (d > 2048) { set_error("decoder_embed_ln: d_model %d > 2048", d); return WK_ERR_INVALID_ARGUMENT; }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_embed_ln_kernel<__half>, dim3(B), dim3(256), 0, stream, 1, (const __half*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__half*)xn, d, explicit_inputs, explicit_pos);
+        launch_k(decoder_embed_ln_kernel<__half>, dim3(B), dim3(256), 0, stream, 1, (const __half*)emb16, pos, gamma, beta, st, vocab, ts_begin, x, (__half*)xn, d, explicit_pos);
     else
-        launch_k(decoder_embed_ln_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, stream, 1, (const __nv_bfloat16*)emb16, pos, gamma, beta, st, prompt_len, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_inputs, explicit_pos);
+        launch_k(decoder_embed_ln_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, stream, 1, (const __nv_bfloat16*)emb16, pos, gamma, beta, st, vocab, ts_begin, x, (__nv_bfloat16*)xn, d, explicit_pos);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_embed_ln launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -271,7 +279,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
                               const float* __restrict__ bv, T* __restrict__ kcache, T* __restrict__ vcache,
-                              const int32_t* __restrict__ step, const int32_t* __restrict__ explicit_pos,
+                              const int32_t* __restrict__ pos_ptr, const int32_t* __restrict__ done,
                               T* __restrict__ out, int B, int H, int max_len) {
     __shared__ float sq[4][64];
     __shared__ float skc[4][64];
@@ -283,8 +291,9 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     pdl_wait();
     if (bh >= B * H) return;
     const int b = bh / H, h = bh % H;
+    if (done != nullptr && done[b]) return;   // ended window: no cache traffic
     const int dm = H * 64;
-    const int pos = explicit_pos ? explicit_pos[b] : *step;
+    const int pos = pos_ptr[b];
     const int e = 2 * lane;
     float2 q = make_float2(bq[h * 64 + e], bq[h * 64 + e + 1]);
     float2 k = make_float2(0.f, 0.f);
@@ -412,14 +421,14 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
 }
 
 wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
-                                 void* vcache, const int32_t* step, const int32_t* explicit_pos, void* out, int B, int H,
+                                 void* vcache, const int32_t* pos, const int32_t* done, void* out, int B, int H,
                                  int max_len, int dtype, cudaStream_t stream) {
     if (max_len > kMaxCtx) { set_error("decoder_self_attention: max_len %d > %d", max_len, kMaxCtx); return WK_ERR_INVALID_ARGUMENT; }
     const unsigned grid = (unsigned)((B * H + 3) / 4);
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, step, explicit_pos, (__half*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, pos, done, (__half*)out, B, H, max_len);
     else
-        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, step, explicit_pos, (__nv_bfloat16*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, pos, done, (__nv_bfloat16*)out, B, H, max_len);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_self_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -441,7 +450,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
                                const T* __restrict__ kcross, const T* __restrict__ vcross, T* __restrict__ out, int B, int H,
-                               int Tlen, float* __restrict__ align_scratch, uint32_t align_mask) {
+                               int Tlen, const int32_t* __restrict__ done, float* __restrict__ align_scratch, uint32_t align_mask) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                                   // kCrossStages * 16000
     float* scores = reinterpret_cast<float*>(smem + kCrossStages * kCrossStageBytes);  // [Tlen]
@@ -455,6 +464,9 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
     const int dm = H * 64;
     const int chunks = Tlen / kCrossRows;  // per K and per V
     pdl_launch_dependents();
+    // ended window: skip its 2 x 192 KB K/V stream.  done[] was written by the sampler of the previous step, many kernels upstream, so it
+    // may be read before griddepcontrol.wait; the wait itself still runs so that this grid never completes before its upstream does
+    if (done != nullptr && done[b]) { pdl_wait(); return; }
     if (tid == 0) {
         for (int i = 0; i < kCrossStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
         fence_barrier_init();
@@ -586,22 +598,22 @@ static size_t cross_smem_bytes(int T) {
     return (size_t)kCrossStages * kCrossStageBytes + (size_t)((T + 3) & ~3) * 4 + 64 * 4 + (4 * 64 + 32) * 4 + 2 * kCrossStages * 8 + 64;
 }
 
-__global__ void decoder_align_mean_kernel(const float* __restrict__ scratch, int n_slots, const int32_t* __restrict__ step,
+__global__ void decoder_align_mean_kernel(const float* __restrict__ scratch, int n_slots, const int32_t* __restrict__ steps,
                                           const int32_t* __restrict__ done, __half* __restrict__ out, int B, int Tlen, int max_rows) {
     const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
-    // launched after the sampler advanced the step: *step = tokenIndex + 1 = the row of this step's slice; a window whose segment just
-    // completed (or completed earlier) gets no row - the reference breaks out of its loop before updateAlignmentWeights
+    // launched after the sampler advanced the row's step: steps[b] = tokenIndex + 1 = the row of this step's slice; a window whose
+    // segment just completed (or completed earlier) gets no row - the reference breaks out of its loop before updateAlignmentWeights
     // (TextDecoder.swift:668-674,709-717)
-    const int row = *step;
+    const int row = steps[b];
     if (t >= Tlen || row >= max_rows || done[b]) return;
     float a = 0.f;
     for (int s = 0; s < n_slots; ++s) a += scratch[((long long)s * B + b) * Tlen + t];   // fixed order: deterministic
     out[((long long)b * max_rows + row) * Tlen + t] = __float2half(a / (float)n_slots);
 }
 
-wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* step, const int32_t* done, void* out_f16, int B, int T,
+wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* steps, const int32_t* done, void* out_f16, int B, int T,
                              int max_rows, cudaStream_t stream) {
-    launch_k(decoder_align_mean_kernel, dim3((T + 255) / 256, B), dim3(256), 0, stream, 0, scratch, n_slots, step, done, (__half*)out_f16, B, T, max_rows);
+    launch_k(decoder_align_mean_kernel, dim3((T + 255) / 256, B), dim3(256), 0, stream, 0, scratch, n_slots, steps, done, (__half*)out_f16, B, T, max_rows);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_align_mean launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -610,12 +622,9 @@ wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* s
 
 wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
                                   const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
-                                  float* align_scratch, uint32_t align_mask) {
+                                  const int32_t* done, float* align_scratch, uint32_t align_mask) {
     if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
-    size_t smem = cross_smem_bytes(T);
-    // WKB200_CROSS_SMEM_KB pads the request so that fewer CTAs fit per SM, leaving shared memory for another lane's GEMM CTAs
-    static const int pad_kb = getenv("WKB200_CROSS_SMEM_KB") ? atoi(getenv("WKB200_CROSS_SMEM_KB")) : 0;
-    if (pad_kb > 0 && pad_kb <= 100) smem = std::max(smem, (size_t)pad_kb * 1024);
+    const size_t smem = cross_smem_bytes(T);
     static bool attr_set[2] = {false, false};
     const int ti = dtype == WK_DTYPE_F16 ? 1 : 0;
     if (!attr_set[ti]) {
@@ -626,9 +635,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
         attr_set[ti] = true;
     }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, align_scratch, align_mask);
+        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, done, align_scratch, align_mask);
     else
-        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, align_scratch, align_mask);
+        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, done, align_scratch, align_mask);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_cross_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -659,9 +668,19 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
     __shared__ ArgMax sarg[32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int V = p.vocab;
-    const bool loop_mode = p.prompt_len >= 0;
+    const bool loop_mode = p.loop_mode != 0;
     pdl_launch_dependents();
     pdl_wait();
+    if (loop_mode && st.done[b]) return;   // ended window: its logits row is not even read
+    // per-row options: the decode loop reads them from the row's RowParams, the stateless entry from the call
+    RowParams R;
+    if (loop_mode) {
+        R = st.rp[b];
+    } else {
+        R.prompt_len = -1; R.sample_begin_ts = p.sample_begin_ts; R.sample_begin_blank = p.sample_begin_blank; R.max_steps = 0;
+        R.temperature = p.temperature; R.top_k = p.top_k; R.has_first_thr = 0; R.first_thr = 0.f; R.seed = p.seed;
+        R.suppress_off = 0; R.n_suppress = p.n_suppress;
+    }
     const int32_t* toks = loop_mode ? st.tokens + b * kMaxCtx : tokens_in + (long long)b * ld_tokens;
     const int n_tok = loop_mode ? st.n_tokens[b] : n_tokens_in[b];
     const wk_special_tokens& S = p.st;
@@ -669,14 +688,14 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
     if (tid == 0) {
         // ---- TimestampRulesFilter rule state (LogitsFilter.swift:72-109)
         int active = 0, loA = 0, hiA = 0, loB = 0, hiB = 0;
-        if (p.sample_begin_ts >= 0) {
+        if (R.sample_begin_ts >= 0) {
             int sb = -1;
             if (p.is_multilingual) {
                 const int lim = n_tok < 3 ? n_tok : 3;
                 for (int i = 0; i < lim; ++i)
-                    if (toks[i] == S.transcribe_token || toks[i] == S.translate_token) { sb = max(i + 1, p.sample_begin_ts); break; }
+                    if (toks[i] == S.transcribe_token || toks[i] == S.translate_token) { sb = max(i + 1, R.sample_begin_ts); break; }
             } else {
-                sb = p.sample_begin_ts;
+                sb = R.sample_begin_ts;
             }
             if (sb >= 0 && sb <= n_tok) {
                 active = 1;
@@ -699,7 +718,7 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
             }
         }
         sflag[0] = active; sflag[1] = loA; sflag[2] = hiA; sflag[3] = loB; sflag[4] = hiB;
-        sflag[5] = (p.sample_begin_blank >= 0 && n_tok == p.sample_begin_blank) ? 1 : 0;   // SuppressBlankFilter
+        sflag[5] = (R.sample_begin_blank >= 0 && n_tok == R.sample_begin_blank) ? 1 : 0;   // SuppressBlankFilter
         sflag[6] = (p.language_tokens != nullptr && n_tok >= p.language_sample_begin) ? 1 : 0;  // LanguageLogitsFilter
     }
     __syncthreads();
@@ -733,8 +752,8 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
         }
         __syncthreads();
     }
-    for (int j = tid; j < p.n_suppress; j += kSamplerThreads) {   // SuppressTokensFilter
-        const int t = p.suppress[j];
+    for (int j = tid; j < R.n_suppress; j += kSamplerThreads) {   // SuppressTokensFilter
+        const int t = p.suppress[R.suppress_off + j];
         if (t >= 0 && t < V) srow[t] = -INFINITY;
     }
     __syncthreads();
@@ -806,14 +825,14 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
     };
     ArgMax best;
     float lp_sampled = 0.f;
-    if (p.temperature == 0.f) {
+    if (R.temperature == 0.f) {
         best = block_argmax();
         lp_sampled = best.v - lse;
     } else {
         // GreedyTokenSampler with temperature (TokenSampler.swift:57-73 / :140-180): logits / T, softmax over the whole
         // (filtered) vocabulary, top-k, multinomial draw inside the top-k mass, logprob = log softmax prob of the draw.
         // The reference draws with Float.random (non-deterministic); here the draw is Philox(seed, row, step).
-        const float inv_t = 1.f / p.temperature;
+        const float inv_t = 1.f / R.temperature;
         const float zmax = (ts_wins ? mts : mall) * inv_t;
         float z = 0.f;
         for (int i = lo + tid; i < V; i += kSamplerThreads) {
@@ -823,7 +842,7 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
         z = block_sum(z, scratch);
         __shared__ float topv[32];
         __shared__ int topi[32];
-        const int k = p.top_k < 1 ? 1 : (p.top_k > 32 ? 32 : p.top_k);
+        const int k = R.top_k < 1 ? 1 : (R.top_k > 32 ? 32 : R.top_k);
         int kk = 0;
         for (; kk < k; ++kk) {
             const ArgMax a = block_argmax();
@@ -835,7 +854,7 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
         float mass = 0.f;
         for (int j = 0; j < kk; ++j) mass += topv[j];
         curandStatePhilox4_32_10_t rng;
-        curand_init(p.seed, (unsigned long long)b, (unsigned long long)(loop_mode ? *st.step : n_tok), &rng);
+        curand_init(R.seed, (unsigned long long)b, (unsigned long long)(loop_mode ? st.steps[b] : n_tok), &rng);
         const float u = 1.f - curand_uniform(&rng);   // [0, 1)
         const float rnd = u * mass;
         float acc = 0.f;
@@ -849,34 +868,35 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
         lp_sampled = kk > 0 ? logf(topv[chosen]) : -INFINITY;
     }
     if (tid == 0) {
-        const int tok = best.i;
-        const float lp = lp_sampled;
-        if (token_out) token_out[b] = tok;
+        int tok = best.i;
+        float lp = lp_sampled;
+        // a row with no finite logit (every token masked, or a NaN from upstream) has no argmax: end the window there and flag it instead
+        // of feeding an out-of-range id to the next embedding lookup (the host reports WhisperError.decodingLogitsFailed for the window)
+        const bool bad = tok < 0 || tok >= V;
+        if (bad) { tok = S.end_token; lp = -INFINITY; }
+        if (token_out) token_out[b] = bad ? -1 : tok;
         if (logprob_out) logprob_out[b] = lp;
-        if (loop_mode && !st.done[b]) {
+        if (loop_mode) {
             // decodeText bookkeeping (TextDecoder.swift:654-686)
-            const int step = *st.step;
-            const bool first_low = (step == 0) && p.has_first_thr && (lp < p.first_thr);
+            const int step = st.steps[b];
+            const bool first_low = (step == 0) && R.has_first_thr && (lp < R.first_thr);
             const bool completed = (tok == S.end_token) || (n_tok >= p.max_ctx - 1) || first_low;
             st.next_token[b] = tok;
             st.steps[b] = step + 1;
+            if (bad) st.error[b] = 1;
             if (completed) {
                 st.done[b] = 1;
                 st.first_low[b] = first_low ? 1 : 0;
-                atomicAdd(st.n_done, 1);
-            } else if (!(step < p.prompt_len - 1)) {   // !isPrefill
-                st.tokens[b * kMaxCtx + n_tok] = tok;
-                st.logprobs[b * kMaxCtx + n_tok] = lp;
-                st.n_tokens[b] = n_tok + 1;
+            } else {
+                if (!(step < R.prompt_len - 1)) {   // !isPrefill
+                    st.tokens[b * kMaxCtx + n_tok] = tok;
+                    st.logprobs[b * kMaxCtx + n_tok] = lp;
+                    st.n_tokens[b] = n_tok + 1;
+                }
+                if (step + 1 >= R.max_steps) st.done[b] = 1;   // loop bound min(sampleLength, 223) reached (TextDecoder.swift:566)
             }
         }
     }
-}
-
-__global__ void advance_step_kernel(DecodeState st) {
-    pdl_launch_dependents();
-    pdl_wait();
-    *st.step += 1;
 }
 
 wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
@@ -893,10 +913,6 @@ wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerP
     launch_k(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, stream, 8, logits, (long long)ld_logits, p, st, tokens, ld_tokens,
              n_tokens, token_out, logprob_out, filtered_out);
     count_launch();
-    if (p.prompt_len >= 0) {
-        launch_k(advance_step_kernel, dim3(1), dim3(1), 0, stream, 8, st);
-        count_launch();
-    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("sampler launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     return WK_OK;

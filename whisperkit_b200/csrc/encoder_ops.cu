@@ -85,210 +85,9 @@ wk_status layernorm_f32_to_f32(const float* x, const float* gamma, const float* 
     return launch_ln<float>(x, gamma, beta, out, rows, d, stream);
 }
 
-// =====================================================================================================
-// Encoder attention (round 1: mma.sync m16n8k16 flash attention; tcgen05 version is the next kernel to write)
-// qkv: [B*T, 3*dm] 16-bit (q | k | v, head h at columns h*64); out: [B*T, dm]
-// CTA = 64 query rows of one (batch, head); 4 warps x 16 rows; KV tiles of 64 keys, cp.async double buffer
-// =====================================================================================================
-template <typename T> struct MmaOp;
-template <> struct MmaOp<__nv_bfloat16> {
-    __device__ __forceinline__ static void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-    }
-};
-template <> struct MmaOp<__half> {
-    __device__ __forceinline__ static void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-    }
-};
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-
-static constexpr int kAttnBM = 64, kAttnBN = 64, kAttnD = 64, kAttnThreads = 128;
-
-// smem tile: 64 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
-__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-
-template <typename T>
-__device__ __forceinline__ void attn_load_tile(uint8_t* smem_tile, const T* gbase, long long ld, int row0, int nrows_valid,
-                                               int tid) {
-    // 64 rows x 8 chunks = 512 chunks, 4 per thread
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * kAttnThreads;
-        const int row = idx >> 3, chunk = idx & 7;
-        const bool ok = (row0 + row) < nrows_valid;
-        const T* src = gbase + (long long)(ok ? (row0 + row) : 0) * ld + chunk * 8;
-        cp_async16(smem_tile + tile_off(row, chunk), src, ok);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kAttnThreads)
-encoder_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tlen, int H, int dm, float scale_log2e) {
-    __shared__ __align__(128) uint8_t sQ[kAttnBM * 128];
-    __shared__ __align__(128) uint8_t sK[2][kAttnBN * 128];
-    __shared__ __align__(128) uint8_t sV[2][kAttnBN * 128];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t4 = lane & 3;
-    const int bh = blockIdx.y, b = bh / H, h = bh % H;
-    const int q0 = blockIdx.x * kAttnBM;
-    const long long ld = 3LL * dm;
-    const T* qb = qkv + (long long)b * Tlen * ld + h * 64;
-    const T* kb = qb + dm;
-    const T* vb = qb + 2 * dm;
-
-    attn_load_tile<T>(sQ, qb, ld, q0, Tlen, tid);
-    attn_load_tile<T>(sK[0], kb, ld, 0, Tlen, tid);
-    attn_load_tile<T>(sV[0], vb, ld, 0, Tlen, tid);
-    cp_async_commit();
-
-    const int n_tiles = (Tlen + kAttnBN - 1) / kAttnBN;
-    float o[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    uint32_t qf[4][4];  // Q fragments for the 4 k-steps (d = 64)
-
-    for (int j = 0; j < n_tiles; ++j) {
-        const int buf = j & 1;
-        if (j + 1 < n_tiles) {
-            attn_load_tile<T>(sK[buf ^ 1], kb, ld, (j + 1) * kAttnBN, Tlen, tid);
-            attn_load_tile<T>(sV[buf ^ 1], vb, ld, (j + 1) * kAttnBN, Tlen, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (j == 0) {
-            // A fragments of Q: rows warp*16 + (lane%8) + ((lane/8)%2)*8, chunk = 2*ks + lane/16
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                ldsm_x4(qf[ks], smem_u32(sQ) + tile_off(row, 2 * ks + (lane >> 4)));
-            }
-        }
-        // ---- S = Q K^T (16 x 64 per warp)
-        float s[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-        const uint32_t kbase = smem_u32(sK[buf]);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {  // pairs of 8-key n-tiles
-                uint32_t kf[4];
-                const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
-                ldsm_x4(kf, kbase + tile_off(row, 2 * ks + ((lane >> 3) & 1)));
-                MmaOp<T>::mma(s[2 * np], qf[ks], kf[0], kf[1]);
-                MmaOp<T>::mma(s[2 * np + 1], qf[ks], kf[2], kf[3]);
-            }
-        }
-        // ---- mask keys beyond Tlen (only the last tile)
-        const int key0 = j * kAttnBN;
-        if (key0 + kAttnBN > Tlen) {
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const int c = key0 + nt * 8 + 2 * t4;
-                if (c >= Tlen) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-                if (c + 1 >= Tlen) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            }
-        }
-        // ---- online softmax (rows g and g+8 of this warp's 16)
-        float mx[2] = {m_run[0], m_run[1]};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-        }
-        float corr[2], msc[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            corr[r] = exp2f((m_run[r] - mx[r]) * scale_log2e);  // m_run = -inf on first tile -> 0
-            m_run[r] = mx[r];
-            msc[r] = mx[r] * scale_log2e;
-            l_run[r] *= corr[r];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
-        uint32_t pf[4][4];  // P as A fragments for the 4 key k-steps
-        float ls[2] = {0.f, 0.f};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float p0 = exp2f(s[nt][0] * scale_log2e - msc[0]);
-            const float p1 = exp2f(s[nt][1] * scale_log2e - msc[0]);
-            const float p2 = exp2f(s[nt][2] * scale_log2e - msc[1]);
-            const float p3 = exp2f(s[nt][3] * scale_log2e - msc[1]);
-            ls[0] += p0 + p1;
-            ls[1] += p2 + p3;
-            pf[nt >> 1][(nt & 1) * 2 + 0] = T16<T>::pack2(p0, p1);
-            pf[nt >> 1][(nt & 1) * 2 + 1] = T16<T>::pack2(p2, p3);
-        }
-        l_run[0] += ls[0];
-        l_run[1] += ls[1];
-        // ---- O += P V
-        const uint32_t vbase = smem_u32(sV[buf]);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {      // 16 keys per step
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-wide d n-tiles
-                uint32_t vf[4];
-                const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                ldsm_x4_trans(vf, vbase + tile_off(row, 2 * dp + (lane >> 4)));
-                MmaOp<T>::mma(o[2 * dp], pf[ks], vf[0], vf[1]);
-                MmaOp<T>::mma(o[2 * dp + 1], pf[ks], vf[2], vf[3]);
-            }
-        }
-        __syncthreads();  // everyone done with buf before it is refilled two iterations later
-    }
-    // ---- finalise: quad-reduce row sums, normalise, store
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-    }
-    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
-    T* ob = out + (long long)b * Tlen * dm + h * 64;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const int c = nt * 8 + 2 * t4;
-        if (r0 < Tlen) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * dm + c) = T16<T>::pack2(o[nt][0] * inv0, o[nt][1] * inv0);
-        if (r1 < Tlen) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * dm + c) = T16<T>::pack2(o[nt][2] * inv1, o[nt][3] * inv1);
-    }
-}
-
+// Encoder attention lives in attention_tcgen05.cu (TMA + tcgen05 + TMEM); this is only its entry point.
 wk_status encoder_attention(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream) {
-    static int legacy = -1;
-    if (legacy < 0) { const char* e = getenv("WKB200_ATTN"); legacy = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
-    if (!legacy) return encoder_attention_tcgen05(qkv, out, B, T, n_heads, dtype, stream);
-    const int dm = n_heads * 64;
-    dim3 grid((T + kAttnBM - 1) / kAttnBM, B * n_heads);
-    const float scale_log2e = 0.125f * 1.4426950408889634f;
-    if (dtype == WK_DTYPE_F16)
-        encoder_attention_kernel<__half><<<grid, kAttnThreads, 0, stream>>>((const __half*)qkv, (__half*)out, T, n_heads, dm, scale_log2e);
-    else
-        encoder_attention_kernel<__nv_bfloat16><<<grid, kAttnThreads, 0, stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_heads, dm, scale_log2e);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("encoder_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-    return WK_OK;
+    return encoder_attention_tcgen05(qkv, out, B, T, n_heads, dtype, stream);
 }
 
 // =====================================================================================================

@@ -1,13 +1,12 @@
-// libwkb200 engine: model / session objects, weight ingestion, the encoder and decoder schedules, and the C ABI of
-// include/wkb200.h.  Host-side control flow mirrors the reference's per-window body
-// (Sources/WhisperKit/Core/TranscribeTask.swift:116-278) and decode loop
-// (Sources/WhisperKit/Core/TextDecoder.swift:541-855); all arithmetic runs in the sm_100a kernels of this directory.
+// libwkb200 engine: the model object (weights, mel tables, alignment heads), weight ingestion, the mel + encoder schedule, the
+// piecewise protocol entry points wk_mel / wk_encode and the kernel-level hooks.  Decode sessions and the window scheduler are in
+// session.cu.  Host-side control flow mirrors the reference's per-window body
+// (Sources/WhisperKit/Core/TranscribeTask.swift:116-278); all arithmetic runs in the sm_100a kernels of this directory.
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <zlib.h>
 #include <dirent.h>
 
 #include <algorithm>
@@ -17,7 +16,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "kernels.h"
+#include "engine.h"
 
 namespace wk {
 
@@ -29,152 +28,34 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+const char* last_error_cstr() { return g_err; }
 static std::atomic<long long> g_launches{0};
-static int g_pdl = -1;
+static std::atomic<int> g_pdl{-1};
 int pdl_mode() {
     // Programmatic dependent launch along the decode step.  Measured on B200 (64 windows, 63 steps, ms per hot-path pass): off 495-498,
     // every kernel (63) 480-489, GEMM + split-K reduce (48) 480-481, reduce only (32) 488; on top of 48: + cross-attention (its K chunks
     // are static and prefetched before griddepcontrol.wait) 473, + embed 478, + self-attention 486 (worse), + sampler 481 (neutral).
-    // Default 53 = embed | cross-attention | GEMM | reduce: the kernels with a real prologue to hide under the upstream kernel's tail.
-    if (g_pdl < 0) {
-        static const int by_mode[4] = {0, 63, 48, 32};
-        g_pdl = getenv("WKB200_PDL") ? by_mode[std::min(3, std::max(0, atoi(getenv("WKB200_PDL"))))] : 53;
-        if (const char* e = getenv("WKB200_PDL_MASK")) g_pdl = (int)strtol(e, nullptr, 0) & 63;
+    // Mask 53 = embed | cross-attention | GEMM | reduce: the kernels with a real prologue to hide under the upstream kernel's tail.
+    // WKB200_PDL_MASK (read once per process) overrides it for A/B measurements.
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        v = 53;
+        if (const char* e = getenv("WKB200_PDL_MASK")) v = (int)strtol(e, nullptr, 0) & 63;
+        g_pdl.store(v, std::memory_order_relaxed);
     }
-    return g_pdl;
+    return v;
 }
 bool pdl_enabled() { return pdl_mode() > 0; }
-void pdl_disable() { g_pdl = 0; }
+void pdl_disable() { g_pdl.store(0, std::memory_order_relaxed); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_counter_load() { return g_launches.load(); }
+void launch_counter_sub(long long n) { g_launches.fetch_sub(n); }
 
-static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-static constexpr int kKvMaxLen = 224;  // Constants.maxTokenContext (Models.swift:1334)
-static constexpr int kWindowSamples = 480000;
-
-#define WK_CHECK(expr)                    \
-    do {                                  \
-        wk_status _s = (expr);            \
-        if (_s != WK_OK) return _s;       \
-    } while (0)
-
-template <typename T>
-static wk_status dmalloc(T** p, size_t n, bool zero = true) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
-    if (e != cudaSuccess) {
-        set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
-        return WK_ERR_CUDA;
-    }
-    if (zero) {
-        e = cudaMemset(*p, 0, n * sizeof(T));
-        if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-    }
-    return WK_OK;
-}
-
-struct LayerNormW { float* g = nullptr; float* b = nullptr; };
-struct EncLayer {
-    LayerNormW ln1, ln2;
-    void* wqkv = nullptr; float* bqkv = nullptr;  // [3d, d]
-    void* wo = nullptr; float* bo = nullptr;
-    void* w1 = nullptr; float* b1 = nullptr;      // [4d, d]
-    void* w2 = nullptr; float* b2 = nullptr;      // [d, 4d]
-};
-struct DecLayer {
-    LayerNormW ln1, lnx, ln3;
-    void* wqkv = nullptr; float* bq = nullptr; float* bv = nullptr;
-    void* wo = nullptr; float* bo = nullptr;
-    void* wcq = nullptr; float* bcq = nullptr;
-    void* wco = nullptr; float* bco = nullptr;
-    void* w1 = nullptr; float* b1 = nullptr;
-    void* w2 = nullptr; float* b2 = nullptr;
-};
-
-}  // namespace wk
-
-using namespace wk;
-
-struct wk_tensor {
-    void* data;
-    int kind;      // 0 = mel [B,3002,128] f16 ; 1 = encoder output [B*1500, d] model dtype
-    int dtype;
-    int64_t batch;
-    wk_model* owner;
-};
-
-struct wk_model {
-    wk_model_config cfg;
-    int device = 0;
-    int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    bool finalized = false;
-    int esz = 2;
-    // weights
-    void* conv1_w = nullptr; float* conv1_b = nullptr;   // f16 [d][3][128]
-    void* conv2_w = nullptr; float* conv2_b = nullptr;   // f16 [d][3][d]
-    float* enc_pos = nullptr;                            // [1500][d]
-    std::vector<EncLayer> enc;
-    LayerNormW enc_ln;
-    void* emb = nullptr;                                 // [V][d]
-    float* dec_pos = nullptr;                            // [448][d]
-    std::vector<DecLayer> dec;
-    LayerNormW dec_ln;
-    void* wckv = nullptr; float* bckv = nullptr;         // [2L*d][d], [2L*d]
-    // front end
-    MelTables* mel_tables = nullptr;
-    // workspaces (max_batch windows)
-    float* pcm_dev = nullptr; int32_t* nvalid_dev = nullptr; int32_t* gmax = nullptr;
-    void* mel = nullptr;       // f16 [Bm][3002][128]
-    void* h1 = nullptr;        // f16 [Bm][3002][d]
-    float* x = nullptr;        // f32 [Bm*1500][d]
-    void* xn = nullptr; void* qkv = nullptr; void* attn = nullptr; void* ffn = nullptr; void* enc_out = nullptr;
-    // alignment heads (word timestamps): per decoder layer a head bit mask and the first scratch slot of the layer
-    std::vector<uint32_t> align_mask; std::vector<int> align_base; int n_align_slots = 0;
-    float timings[6] = {0, 0, 0, 0, 0, 0};
-    cudaEvent_t ev[8];
-    wk_tensor mel_tensor, enc_tensor;
-};
-
-// One decode lane: a contiguous slice of the session's windows with its own stream, KV caches and decode state.
-// A session with >= 32 windows runs two lanes concurrently so that one lane's latency-bound kernels (small GEMMs,
-// split-K reduce + LayerNorm, self-attention) overlap the other lane's HBM-bound cross-attention.
-struct Lane {
-    wk_model* m;
-    cudaStream_t stream = nullptr;
-    int max_batch = 0, batch = 0, bp = 16, b0 = 0;
-    void* cross_kv = nullptr;   // [2L][Bs][H][T][64]
-    void* self_k = nullptr;     // [L][Bs][H][224][64]
-    void* self_v = nullptr;
-    float* partial = nullptr; size_t partial_elems = 0;
-    float* x = nullptr; void* xn = nullptr; void* attn = nullptr; void* ffn = nullptr;
-    float* logits = nullptr;
-    DecodeState st;
-    int32_t* prompt_dev = nullptr; int32_t* pos_dev = nullptr; int32_t* suppress_dev = nullptr; int32_t* lang_dev = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    long long launches_per_step = 0;
-    int gemm_max_stages = 0;
-    // word timestamps: per-head softmax rows of the current step, and the [Bs][224][T] Float16 alignmentWeights tensor
-    float* align_scratch = nullptr; void* align_w = nullptr; int align_slots = 0; bool align_on = false;
-    void* align_keep = nullptr;   // alignment of windows already final while the fallback ladder re-decodes the chunk
-    unsigned int* chain_counters = nullptr;   // WKB200_FUSED=1: grid-barrier words of the fused phase chains, zeroed once per step
-};
-
-struct wk_session {
-    wk_model* m;
-    int max_batch = 0, batch = 0;
-    int n_lanes = 1;
-    Lane* lane[2] = {nullptr, nullptr};
-    cudaEvent_t ev_enc = nullptr;
-};
-
-namespace wk {
-
-static int choose_splits(int tiles, int total_kb, int num_sms) {
+int choose_splits(int tiles, int total_kb, int num_sms) {
     // Split-K depth of a decoder swap-AB GEMM: the deepest split that still fits ONE wave of CTAs (tiles * s <= SMs), so every SM that
     // takes part streams its share of the weights exactly once.  Measured with HBM-cold weights on B200 (tools/microbench_cold.py,
     // 64 windows): one SM sustains only ~40 GB/s, so too few CTAs starve (d x d: s=1 11.0 us, s=10 6.1 us) while a second wave costs
     // more than it saves (FC1: s=2 8.5 us, s=4 9.6 us; QKV: s=4 7.3 us, s=5 9.1 us; FC2: s=10 8.1 us, s=20 9.4 us).
-    static const int force = getenv("WKB200_FORCE_SPLITS") ? atoi(getenv("WKB200_FORCE_SPLITS")) : 0;  // microbenchmarks only
-    if (force > 0 && force <= 20 && total_kb % force == 0) return force;
     int best = 1;
     for (int s = 1; s <= total_kb && s <= 20; ++s) {   // 20 = kMaxSplits of the fused reduce kernels
         if (total_kb % s) continue;
@@ -183,7 +64,7 @@ static int choose_splits(int tiles, int total_kb, int num_sms) {
     return best;
 }
 
-static size_t esize(int dtype) { return dtype == WK_DTYPE_F32 || dtype == WK_DTYPE_I32 ? 4 : 2; }
+size_t esize(int dtype) { return dtype == WK_DTYPE_F32 || dtype == WK_DTYPE_I32 ? 4 : 2; }
 
 static wk_status alloc_ln(LayerNormW& ln, int d) {
     WK_CHECK(dmalloc(&ln.g, d));
@@ -191,16 +72,9 @@ static wk_status alloc_ln(LayerNormW& ln, int d) {
     return WK_OK;
 }
 
-static wk_status alloc16(void** p, size_t n) {
-    uint16_t* q = nullptr;
-    WK_CHECK(dmalloc(&q, n));
-    *p = q;
-    return WK_OK;
-}
-
 static wk_status model_alloc(wk_model* m) {
     const wk_model_config& c = m->cfg;
-    const int d = c.d_model, L = c.enc_layers, Ld = c.dec_layers, Bm = c.max_batch;
+    const int d = c.d_model, L = c.enc_layers, Ld = c.dec_layers;
     const size_t T = c.n_audio_ctx;
     WK_CHECK(alloc16(&m->conv1_w, (size_t)d * 3 * 128));
     WK_CHECK(dmalloc(&m->conv1_b, d));
@@ -232,20 +106,35 @@ static wk_status model_alloc(wk_model* m) {
     WK_CHECK(alloc_ln(m->dec_ln, d));
     WK_CHECK(alloc16(&m->wckv, (size_t)2 * Ld * d * d));
     WK_CHECK(dmalloc(&m->bckv, (size_t)2 * Ld * d));
-    // workspaces
-    WK_CHECK(dmalloc(&m->pcm_dev, (size_t)Bm * kWindowSamples, false));
-    WK_CHECK(dmalloc(&m->nvalid_dev, Bm));
-    WK_CHECK(dmalloc(&m->gmax, Bm));
-    WK_CHECK(alloc16(&m->mel, (size_t)Bm * kMelRows * kMelCols));
-    WK_CHECK(alloc16(&m->h1, (size_t)Bm * kMelRows * d));
-    const size_t M = (size_t)Bm * T;
-    WK_CHECK(dmalloc(&m->x, M * d, false));
-    WK_CHECK(alloc16(&m->xn, M * d));
-    WK_CHECK(alloc16(&m->qkv, M * 3 * d));
-    WK_CHECK(alloc16(&m->attn, M * d));
-    WK_CHECK(alloc16(&m->ffn, M * 4 * d));
-    WK_CHECK(alloc16(&m->enc_out, M * d));
     return WK_OK;
+}
+
+wk_status enc_ws_ensure(wk_model* m, EncWorkspace* ws, int max_batch) {
+    if (ws->max_batch >= max_batch) return WK_OK;
+    enc_ws_free(ws);
+    const wk_model_config& c = m->cfg;
+    const int d = c.d_model, Bm = max_batch;
+    const size_t T = c.n_audio_ctx;
+    WK_CHECK(dmalloc(&ws->pcm_dev, (size_t)Bm * kWindowSamples, false));
+    WK_CHECK(dmalloc(&ws->nvalid_dev, Bm));
+    WK_CHECK(dmalloc(&ws->gmax, Bm));
+    WK_CHECK(alloc16(&ws->mel, (size_t)Bm * kMelRows * kMelCols));
+    WK_CHECK(alloc16(&ws->h1, (size_t)Bm * kMelRows * d));
+    const size_t M = (size_t)Bm * T;
+    WK_CHECK(dmalloc(&ws->x, M * d, false));
+    WK_CHECK(alloc16(&ws->xn, M * d));
+    WK_CHECK(alloc16(&ws->qkv, M * 3 * d));
+    WK_CHECK(alloc16(&ws->attn, M * d));
+    WK_CHECK(alloc16(&ws->ffn, M * 4 * d));
+    WK_CHECK(alloc16(&ws->enc_out, M * d));
+    ws->max_batch = Bm;
+    return WK_OK;
+}
+
+void enc_ws_free(EncWorkspace* ws) {
+    void* ptrs[] = {ws->pcm_dev, ws->nvalid_dev, ws->gmax, ws->mel, ws->h1, ws->x, ws->xn, ws->qkv, ws->attn, ws->ffn, ws->enc_out};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    *ws = EncWorkspace();
 }
 
 // ---------------------------------------------------------------------------------------------- weight ingestion
@@ -334,9 +223,9 @@ static bool resolve_name(wk_model* m, const std::string& name, Dest* out) {
     return false;
 }
 
-// ---------------------------------------------------------------------------------------------- encoder schedule
-static GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int dtype, int mode, void* out, int64_t ld_out,
-                           const float* bias, int gelu) {
+// ---------------------------------------------------------------------------------------------- mel + encoder schedule
+GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int dtype, int mode, void* out, int64_t ld_out,
+                    const float* bias, int gelu) {
     GemmDesc g;
     memset(&g, 0, sizeof(g));
     g.a = a; g.a_rows = M; g.a_cols = K; g.a_ld = K; g.a_batches = 1;
@@ -347,23 +236,49 @@ static GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N
     return g;
 }
 
-static wk_status encode_chunk(wk_model* m, int B) {
+wk_status mel_run(wk_model* m, EncWorkspace* ws, const float* pcm, int64_t n, int64_t stride, const int32_t* samples_per_window,
+                  void* mel_out, cudaStream_t stream) {
+    if (n < 1 || n > ws->max_batch) { set_error("log-mel: %lld windows outside [1, %d]", (long long)n, ws->max_batch); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+    if (stride < kWindowSamples && !samples_per_window) { set_error("log-mel: stride %lld < 480000 requires samples_per_window", (long long)stride); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+    cudaPointerAttributes at;
+    const bool on_device = cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const float* src = pcm;
+    int64_t src_stride = stride;
+    if (!on_device || stride < kWindowSamples) {   // host PCM, or short rows: stage (padOrTrimAudio, AudioProcessor.swift:151-174)
+        if (stride < kWindowSamples) WK_CUDA_CHECK(cudaMemsetAsync(ws->pcm_dev, 0, (size_t)n * kWindowSamples * 4, stream));
+        WK_CUDA_CHECK(cudaMemcpy2DAsync(ws->pcm_dev, kWindowSamples * 4, pcm, stride * 4, std::min<int64_t>(stride, kWindowSamples) * 4, n,
+                                        cudaMemcpyDefault, stream));
+        src = ws->pcm_dev;
+        src_stride = kWindowSamples;
+    }
+    const int32_t* nv = nullptr;
+    if (samples_per_window) {
+        for (int64_t i = 0; i < n; ++i)
+            if (samples_per_window[i] < 0 || samples_per_window[i] > kWindowSamples) { set_error("log-mel: samples_per_window[%lld] out of range", (long long)i); return WK_ERR_AUDIO_PROCESSING_FAILED; }
+        WK_CUDA_CHECK(cudaMemcpyAsync(ws->nvalid_dev, samples_per_window, n * 4, cudaMemcpyHostToDevice, stream));
+        nv = ws->nvalid_dev;
+    }
+    return mel_forward(m->mel_tables, src, n, src_stride, nv, mel_out, ws->gmax, stream);
+}
+
+wk_status encode_chunk(wk_model* m, EncWorkspace* ws, const void* mel, int B, void* enc_out, cudaStream_t s) {
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, T = c.n_audio_ctx, dt = c.dtype;
-    cudaStream_t s = m->stream;
     const int64_t M = (int64_t)B * T;
+    if (B < 1 || B > ws->max_batch) { set_error("encoder: %d windows outside [1, %d]", B, ws->max_batch); return WK_ERR_INVALID_ARGUMENT; }
     // conv1 (k=3, pad 1) + GELU as implicit GEMM over the time-major mel: taps = 3 row shifts of the same tensor map
     {
         GemmDesc g;
         memset(&g, 0, sizeof(g));
-        g.a = m->mel; g.a_rows = kMelRows; g.a_cols = kMelCols; g.a_ld = kMelCols; g.a_batch_stride = (int64_t)kMelRows * kMelCols;
+        g.a = mel; g.a_rows = kMelRows; g.a_cols = kMelCols; g.a_ld = kMelCols; g.a_batch_stride = (int64_t)kMelRows * kMelCols;
         g.a_batches = B; g.a_3d = 1;
         g.b = m->conv1_w; g.b_rows = d; g.b_ld = 3 * kMelCols; g.in_dtype = WK_DTYPE_F16;
         g.m_rows_per_batch = 2 * T; g.n = d; g.k = kMelCols; g.taps = 3;
         for (int t = 0; t < 3; ++t) { g.tap_row_shift[t] = t; g.tap_col_off[t] = 0; }
         g.bn = d >= 256 ? 256 : round_up(d, 16);
         g.splits = 1; g.mode = GEMM_OUT_T16; g.gelu = 1;
-        g.out = (char*)m->h1 + (size_t)d * 2;  // row 0 of every window is the zero pad
+        g.out = (char*)ws->h1 + (size_t)d * 2;  // row 0 of every window is the zero pad
         g.ld_out = d; g.out_rows_per_batch = kMelRows; g.bias = m->conv1_b;
         WK_CHECK(gemm_tcgen05(g, m->num_sms, s));
     }
@@ -371,7 +286,7 @@ static wk_status encode_chunk(wk_model* m, int B) {
     {
         GemmDesc g;
         memset(&g, 0, sizeof(g));
-        g.a = m->h1; g.a_rows = kMelRows / 2; g.a_cols = 2 * d; g.a_ld = 2 * d; g.a_batch_stride = (int64_t)kMelRows * d;
+        g.a = ws->h1; g.a_rows = kMelRows / 2; g.a_cols = 2 * d; g.a_ld = 2 * d; g.a_batch_stride = (int64_t)kMelRows * d;
         g.a_batches = B; g.a_3d = 1;
         g.b = m->conv2_w; g.b_rows = d; g.b_ld = 3 * d; g.in_dtype = WK_DTYPE_F16;
         g.m_rows_per_batch = T; g.n = d; g.k = d; g.taps = 3;
@@ -380,198 +295,34 @@ static wk_status encode_chunk(wk_model* m, int B) {
         g.tap_row_shift[2] = 1; g.tap_col_off[2] = 0;
         g.bn = d >= 256 ? 256 : round_up(d, 16);
         g.splits = 1; g.mode = GEMM_OUT_F32_GELU_POS; g.gelu = 1;
-        g.out = m->x; g.ld_out = d; g.out_rows_per_batch = T; g.bias = m->conv2_b; g.pos = m->enc_pos; g.ld_pos = d;
+        g.out = ws->x; g.ld_out = d; g.out_rows_per_batch = T; g.bias = m->conv2_b; g.pos = m->enc_pos; g.ld_pos = d;
         WK_CHECK(gemm_tcgen05(g, m->num_sms, s));
     }
-    int n_layers = c.enc_layers;
-    if (const char* e = getenv("WKB200_DEBUG_ENC_LAYERS")) n_layers = std::min(n_layers, atoi(e));  // stage debugging only
-    for (int li = 0; li < n_layers; ++li) {
+    for (int li = 0; li < c.enc_layers; ++li) {
         EncLayer& l = m->enc[li];
-        WK_CHECK(layernorm_f32_to_16(m->x, l.ln1.g, l.ln1.b, m->xn, M, d, dt, s));
-        WK_CHECK(gemm_tcgen05(plain_gemm(m->xn, M, d, l.wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, l.bqkv, 0), m->num_sms, s));
-        WK_CHECK(encoder_attention(m->qkv, m->attn, B, T, c.n_heads, dt, s));
-        WK_CHECK(gemm_tcgen05(plain_gemm(m->attn, M, d, l.wo, d, dt, GEMM_OUT_F32_ADD, m->x, d, l.bo, 0), m->num_sms, s));
-        WK_CHECK(layernorm_f32_to_16(m->x, l.ln2.g, l.ln2.b, m->xn, M, d, dt, s));
-        WK_CHECK(gemm_tcgen05(plain_gemm(m->xn, M, d, l.w1, 4 * d, dt, GEMM_OUT_T16, m->ffn, 4 * d, l.b1, 1), m->num_sms, s));
-        WK_CHECK(gemm_tcgen05(plain_gemm(m->ffn, M, 4 * d, l.w2, d, dt, GEMM_OUT_F32_ADD, m->x, d, l.b2, 0), m->num_sms, s));
+        WK_CHECK(layernorm_f32_to_16(ws->x, l.ln1.g, l.ln1.b, ws->xn, M, d, dt, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(ws->xn, M, d, l.wqkv, 3 * d, dt, GEMM_OUT_T16, ws->qkv, 3 * d, l.bqkv, 0), m->num_sms, s));
+        WK_CHECK(encoder_attention(ws->qkv, ws->attn, B, T, c.n_heads, dt, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(ws->attn, M, d, l.wo, d, dt, GEMM_OUT_F32_ADD, ws->x, d, l.bo, 0), m->num_sms, s));
+        WK_CHECK(layernorm_f32_to_16(ws->x, l.ln2.g, l.ln2.b, ws->xn, M, d, dt, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(ws->xn, M, d, l.w1, 4 * d, dt, GEMM_OUT_T16, ws->ffn, 4 * d, l.b1, 1), m->num_sms, s));
+        WK_CHECK(gemm_tcgen05(plain_gemm(ws->ffn, M, 4 * d, l.w2, d, dt, GEMM_OUT_F32_ADD, ws->x, d, l.b2, 0), m->num_sms, s));
     }
-    WK_CHECK(layernorm_f32_to_16(m->x, m->enc_ln.g, m->enc_ln.b, m->enc_out, M, d, dt, s));
+    WK_CHECK(layernorm_f32_to_16(ws->x, m->enc_ln.g, m->enc_ln.b, enc_out, M, d, dt, s));
     return WK_OK;
-}
-
-// ---------------------------------------------------------------------------------------------- decoder schedule
-static wk_status dec_gemm(Lane* s, const void* w, int N, int K, const void* act, int* splits_out) {
-    wk_model* m = s->m;
-    GemmDesc g;
-    memset(&g, 0, sizeof(g));
-    // swap-AB: A = weights [N, K] (128 output features per tile), B = activations [Bp, K]
-    g.a = w; g.a_rows = N; g.a_cols = K; g.a_ld = K; g.a_batches = 1;
-    g.b = act; g.b_rows = s->bp; g.b_ld = K; g.in_dtype = m->cfg.dtype;
-    g.m_rows_per_batch = N; g.n = s->bp; g.k = K; g.taps = 1; g.bn = s->bp;
-    const int tiles = (N + 127) / 128;
-    g.splits = choose_splits(tiles, K / 64, m->num_sms);
-    g.mode = GEMM_OUT_PARTIAL_T; g.out = s->partial; g.ld_out = N; g.out_rows_per_batch = N; g.partial_cols = s->bp;
-    g.pdl = 1; g.a_static = 1;
-    if ((size_t)g.splits * s->bp * N > s->partial_elems) { set_error("partial workspace too small"); return WK_ERR_DECODING_FAILED; }
-    *splits_out = g.splits;
-    g.max_stages = s->gemm_max_stages;
-    return gemm_tcgen05(g, m->num_sms, s->stream);
-}
-
-// one decoder forward for every bound sequence.  explicit_pos == nullptr: loop mode (token/position from DecodeState)
-static wk_status decoder_forward(Lane* s, int prompt_len, int ts_begin, const int32_t* explicit_pos) {
-    wk_model* m = s->m;
-    const wk_model_config& c = m->cfg;
-    const int d = c.d_model, H = c.n_heads, dt = c.dtype, B = s->batch, Bp = s->bp, T = c.n_audio_ctx;
-    cudaStream_t st = s->stream;
-    const size_t self_layer = (size_t)s->max_batch * H * kKvMaxLen * 64 * 2;   // bytes per layer
-    const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;          // bytes per (layer, k|v)
-    int sp = 1;
-    WK_CHECK(decoder_embed_ln(m->emb, m->dec_pos, m->dec[0].ln1.g, m->dec[0].ln1.b, s->st, prompt_len, ts_begin, s->x, s->xn, B, d, dt,
-                              explicit_pos ? 1 : 0, explicit_pos, st));
-    int n_layers = c.dec_layers;
-    if (const char* e = getenv("WKB200_DEBUG_DEC_LAYERS")) n_layers = std::min(n_layers, atoi(e));  // stage debugging only
-    static const bool fused = getenv("WKB200_FUSED") && atoi(getenv("WKB200_FUSED")) == 1;
-    if (fused) {
-        // EXPERIMENTAL (fused_chain.cu, not validated on a GPU yet): per layer, self-attention -> chain B -> cross-attention -> chain C
-        const int kWords = 8;
-        if (!s->chain_counters) WK_CUDA_CHECK(cudaMalloc((void**)&s->chain_counters, (size_t)c.dec_layers * 2 * kWords * 4));
-        WK_CUDA_CHECK(cudaMemsetAsync(s->chain_counters, 0, (size_t)c.dec_layers * 2 * kWords * 4, st));
-        auto gemm_phase = [&](const void* w, int N, int K, const void* act) {
-            ChainPhaseDesc ph; memset(&ph, 0, sizeof(ph));
-            ph.kind = 0; ph.w = w; ph.n = N; ph.k = K; ph.act = act; ph.splits = choose_splits((N + 127) / 128, K / 64, m->num_sms);
-            return ph;
-        };
-        auto ln_phase = [&](const float* bias, const LayerNormW& ln) {
-            ChainPhaseDesc ph; memset(&ph, 0, sizeof(ph));
-            ph.kind = 1; ph.bias = bias; ph.gamma = ln.g; ph.beta = ln.b; ph.out16 = s->xn;
-            return ph;
-        };
-        auto chain_base = [&](int li, int which) {
-            ChainDesc cd; memset(&cd, 0, sizeof(cd));
-            cd.partial = s->partial; cd.x = s->x; cd.B = B; cd.Bp = Bp; cd.d = d; cd.dtype = dt; cd.pdl = 1;
-            cd.counters = s->chain_counters + ((size_t)li * 2 + which) * kWords;
-            return cd;
-        };
-        WK_CHECK(dec_gemm(s, m->dec[0].wqkv, 3 * d, d, s->xn, &sp));
-        for (int li = 0; li < n_layers; ++li) {
-            DecLayer& l = m->dec[li];
-            WK_CHECK(decoder_self_attention(s->partial, sp, Bp, l.bq, l.bv, (char*)s->self_k + li * self_layer, (char*)s->self_v + li * self_layer,
-                                            s->st.step, explicit_pos, s->attn, B, H, kKvMaxLen, dt, st));
-            ChainDesc cb = chain_base(li, 0);
-            cb.ph[0] = gemm_phase(l.wo, d, d, s->attn);
-            cb.ph[1] = ln_phase(l.bo, l.lnx);
-            cb.ph[2] = gemm_phase(l.wcq, d, d, s->xn);
-            cb.n_phases = 3;
-            WK_CHECK(decoder_chain(cb, m->num_sms, st));
-            sp = cb.ph[2].splits;
-            const bool align = s->align_on && !explicit_pos && m->align_mask[li] != 0;
-            WK_CHECK(decoder_cross_attention(s->partial, sp, Bp, l.bcq, (char*)s->cross_kv + (size_t)(2 * li) * cross_block,
-                                             (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st,
-                                             align ? s->align_scratch + (size_t)m->align_base[li] * B * T : nullptr, align ? m->align_mask[li] : 0u));
-            ChainDesc cc = chain_base(li, 1);
-            const LayerNormW& nxt = (li + 1 < n_layers) ? m->dec[li + 1].ln1 : m->dec_ln;
-            cc.ph[0] = gemm_phase(l.wco, d, d, s->attn);
-            cc.ph[1] = ln_phase(l.bco, l.ln3);
-            cc.ph[2] = gemm_phase(l.w1, 4 * d, d, s->xn);
-            cc.ph[3].kind = 2; cc.ph[3].bias = l.b1; cc.ph[3].out16 = s->ffn;
-            cc.ph[4] = gemm_phase(l.w2, d, 4 * d, s->ffn);
-            cc.ph[5] = ln_phase(l.b2, nxt);
-            cc.n_phases = 6;
-            if (li + 1 < n_layers) { cc.ph[6] = gemm_phase(m->dec[li + 1].wqkv, 3 * d, d, s->xn); cc.n_phases = 7; sp = cc.ph[6].splits; }
-            WK_CHECK(decoder_chain(cc, m->num_sms, st));
-        }
-    } else
-    for (int li = 0; li < n_layers; ++li) {
-        DecLayer& l = m->dec[li];
-        WK_CHECK(dec_gemm(s, l.wqkv, 3 * d, d, s->xn, &sp));
-        WK_CHECK(decoder_self_attention(s->partial, sp, Bp, l.bq, l.bv, (char*)s->self_k + li * self_layer, (char*)s->self_v + li * self_layer,
-                                        s->st.step, explicit_pos, s->attn, B, H, kKvMaxLen, dt, st));
-        WK_CHECK(dec_gemm(s, l.wo, d, d, s->attn, &sp));
-        WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.bo, l.lnx.g, l.lnx.b, s->x, s->xn, B, d, dt, st));
-        WK_CHECK(dec_gemm(s, l.wcq, d, d, s->xn, &sp));
-        const bool align = s->align_on && !explicit_pos && m->align_mask[li] != 0;
-        WK_CHECK(decoder_cross_attention(s->partial, sp, Bp, l.bcq, (char*)s->cross_kv + (size_t)(2 * li) * cross_block,
-                                         (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st,
-                                         align ? s->align_scratch + (size_t)m->align_base[li] * B * T : nullptr, align ? m->align_mask[li] : 0u));
-        WK_CHECK(dec_gemm(s, l.wco, d, d, s->attn, &sp));
-        WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.bco, l.ln3.g, l.ln3.b, s->x, s->xn, B, d, dt, st));
-        WK_CHECK(dec_gemm(s, l.w1, 4 * d, d, s->xn, &sp));
-        WK_CHECK(decoder_reduce_bias_gelu(s->partial, sp, Bp, l.b1, s->ffn, B, 4 * d, dt, st));
-        WK_CHECK(dec_gemm(s, l.w2, d, 4 * d, s->ffn, &sp));
-        const LayerNormW& nxt = (li + 1 < n_layers) ? m->dec[li + 1].ln1 : m->dec_ln;
-        WK_CHECK(decoder_reduce_resid_ln(s->partial, sp, Bp, l.b2, nxt.g, nxt.b, s->x, s->xn, B, d, dt, st));
-    }
-    // logits = xn . E^T  (tied embedding), written [B][V] f32 by the transposed-store epilogue (splits = 1)
-    {
-        GemmDesc g;
-        memset(&g, 0, sizeof(g));
-        g.a = m->emb; g.a_rows = c.vocab; g.a_cols = d; g.a_ld = d; g.a_batches = 1;
-        g.b = s->xn; g.b_rows = Bp; g.b_ld = d; g.in_dtype = dt;
-        g.m_rows_per_batch = c.vocab; g.n = Bp; g.k = d; g.taps = 1; g.bn = Bp; g.splits = 1;
-        g.mode = GEMM_OUT_PARTIAL_T; g.out = s->logits; g.ld_out = c.vocab; g.out_rows_per_batch = c.vocab; g.partial_cols = B;
-        g.pdl = 1; g.a_static = 1;
-        g.max_stages = s->gemm_max_stages;
-        WK_CHECK(gemm_tcgen05(g, m->num_sms, st));
-    }
-    return WK_OK;
-}
-
-static SamplerParams make_sampler_params(Lane* s, const wk_special_tokens* st, const wk_decode_opts* o, int is_multilingual,
-                                         int sample_begin_ts, int sample_begin_blank, int prompt_len) {
-    SamplerParams p;
-    memset(&p, 0, sizeof(p));
-    p.st = *st;
-    p.vocab = s->m->cfg.vocab;
-    p.is_multilingual = is_multilingual;
-    p.sample_begin_ts = sample_begin_ts;
-    p.sample_begin_blank = sample_begin_blank;
-    p.suppress = s->suppress_dev; p.n_suppress = 0;
-    p.language_tokens = nullptr; p.n_language_tokens = 0; p.language_sample_begin = 0;
-    p.temperature = o->temperature; p.top_k = o->top_k; p.seed = o->seed;
-    p.has_first_thr = o->has_first_token_logprob_threshold; p.first_thr = o->first_token_logprob_threshold;
-    p.prompt_len = prompt_len;
-    p.max_ctx = kKvMaxLen;
-    return p;
-}
-
-// uploads the (< specialTokenBegin) suppress list (TextDecoder.swift:876-879); returns count
-static wk_status upload_suppress(Lane* s, const wk_special_tokens* st, const wk_decode_opts* o, int* n_out) {
-    std::vector<int32_t> sup;
-    for (int i = 0; i < o->n_suppress_tokens; ++i)
-        if (o->suppress_tokens[i] < st->special_token_begin && o->suppress_tokens[i] >= 0) sup.push_back(o->suppress_tokens[i]);
-    if (sup.size() > 4096) { set_error("too many suppress tokens"); return WK_ERR_INVALID_ARGUMENT; }
-    if (!sup.empty()) WK_CUDA_CHECK(cudaMemcpyAsync(s->suppress_dev, sup.data(), sup.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    *n_out = (int)sup.size();
-    return WK_OK;
-}
-
-// TextUtilities.compressionRatio(of: [Int]) (TextUtilities.swift:14-28): raw DEFLATE of the Int32 LE bytes
-static float compression_ratio(const std::vector<int32_t>& toks) {
-    if (toks.empty()) return INFINITY;
-    const uLong n = (uLong)toks.size() * 4;
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (deflateInit2(&zs, 5, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return INFINITY;
-    std::vector<unsigned char> out(deflateBound(&zs, n) + 64);
-    zs.next_in = (Bytef*)toks.data(); zs.avail_in = n;
-    zs.next_out = out.data(); zs.avail_out = (uInt)out.size();
-    const int r = deflate(&zs, Z_FINISH);
-    const uLong clen = zs.total_out;
-    deflateEnd(&zs);
-    if (r != Z_STREAM_END || clen == 0) return INFINITY;
-    return (float)n / (float)clen;
 }
 
 }  // namespace wk
+
+using namespace wk;
 
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
 extern "C" {
 
-const char* wk_last_error(void) { return wk::g_err; }
-const char* wk_version(void) { return "wkb200 0.1 (sm_100a)"; }
+const char* wk_last_error(void) { return wk::last_error_cstr(); }
+const char* wk_version(void) { return "wkb200 0.2 (sm_100a)"; }
 
 int32_t wk_device_available(void) {
     int n = 0;
@@ -649,8 +400,6 @@ wk_status wk_model_create(const wk_model_config* cfg, int32_t device, wk_model**
     if (s != WK_OK) return s;
     WK_CHECK(mel_tables_create(cfg->n_mels, &m->mel_tables));
     WK_CUDA_CHECK(cudaDeviceSynchronize());  // setup memsets / table uploads ran on the legacy default stream
-    m->mel_tensor = {m->mel, 0, WK_DTYPE_F16, 0, m};
-    m->enc_tensor = {m->enc_out, 1, cfg->dtype, 0, m};
     *out = m;
     return WK_OK;
 }
@@ -838,6 +587,30 @@ wk_status wk_model_load(const char* weights_dir, int32_t device, int32_t max_bat
     }
     const int expected = 4 + 1 + 2 + c.enc_layers * 15 + 1 + 1 + 2 + c.dec_layers * 24;
     if (n_loaded < expected) { wk_model_free(m); set_error("wk_model_load: only %d of %d expected tensors found in %s", n_loaded, expected, weights_dir); return WK_ERR_MODELS_UNAVAILABLE; }
+    // generation_config.json "alignment_heads": [[layer, head], ...] - the checkpoint's own word-timestamp heads, which the reference's
+    // decoder model bakes into its alignment_heads_weights output (TextDecoder.swift:310,414)
+    std::vector<char> gbuf;
+    if (read_file(dir + "/generation_config.json", &gbuf)) {
+        const std::string gj(gbuf.begin(), gbuf.end());
+        size_t pos = gj.find("\"alignment_heads\"");
+        if (pos != std::string::npos && (pos = gj.find('[', pos)) != std::string::npos) {
+            std::vector<int32_t> pairs;
+            int depth = 0;
+            for (size_t i = pos; i < gj.size(); ++i) {
+                const char ch = gj[i];
+                if (ch == '[') ++depth;
+                else if (ch == ']') { if (--depth == 0) break; }
+                else if (ch >= '0' && ch <= '9') {
+                    pairs.push_back((int32_t)atol(gj.c_str() + i));
+                    while (i + 1 < gj.size() && gj[i + 1] >= '0' && gj[i + 1] <= '9') ++i;
+                }
+            }
+            if (!pairs.empty() && pairs.size() % 2 == 0) {
+                wk_status st = wk_model_set_alignment_heads(m, pairs.data(), (int32_t)pairs.size() / 2);
+                if (st != WK_OK) { wk_model_free(m); return st; }
+            }
+        }
+    }
     WK_CHECK(wk_model_finalize(m));
     *out = m;
     return WK_OK;
@@ -920,7 +693,9 @@ wk_status wk_model_info_get(const wk_model* m, wk_model_info* o) {
     o->n_mels = c.n_mels; o->n_audio_ctx = c.n_audio_ctx; o->d_model = c.d_model; o->n_heads = c.n_heads;
     o->enc_layers = c.enc_layers; o->dec_layers = c.dec_layers; o->vocab = c.vocab;
     o->kv_embed_dim = c.dec_layers * c.d_model; o->kv_max_len = kKvMaxLen; o->window_samples = kWindowSamples;
-    o->has_alignment_heads = 0;
+    // the reference derives supportsWordTimestamps from the presence of the alignment_heads_weights output (TextDecoder.swift:309-311);
+    // here: checkpoint-specific heads were supplied (generation_config.json or wk_model_set_alignment_heads)
+    o->has_alignment_heads = m->has_alignment_heads;
     o->is_multilingual = c.vocab != 51864;
     o->dtype = c.dtype; o->max_batch = c.max_batch;
     return WK_OK;
@@ -939,7 +714,7 @@ void wk_model_free(wk_model* m) {
         fr(l.wcq); fr(l.bcq); fr(l.wco); fr(l.bco); fr(l.w1); fr(l.b1); fr(l.w2); fr(l.b2);
     }
     fr(m->dec_ln.g); fr(m->dec_ln.b); fr(m->wckv); fr(m->bckv);
-    fr(m->pcm_dev); fr(m->nvalid_dev); fr(m->gmax); fr(m->mel); fr(m->h1); fr(m->x); fr(m->xn); fr(m->qkv); fr(m->attn); fr(m->ffn); fr(m->enc_out);
+    enc_ws_free(&m->ws);
     mel_tables_free(m->mel_tables);
     for (auto& e : m->ev) cudaEventDestroy(e);
     cudaStreamDestroy(m->stream);
@@ -949,6 +724,20 @@ void wk_model_free(wk_model* m) {
 void* wk_model_stream(wk_model* m) { return m ? (void*)m->stream : nullptr; }
 
 // ---------------------------------------------------------------------------------------------- tensors
+// A wk_tensor owns its device buffer (stream-ordered allocation on the model stream): the MLMultiArray a Swift host gets back from
+// logMelSpectrogram / encodeFeatures stays valid until it is released, whatever the host does with the model in between.
+static wk_status tensor_new(wk_model* m, int kind, int dtype, int64_t batch, size_t bytes, wk_tensor** out) {
+    wk_tensor* t = new wk_tensor();
+    t->kind = kind; t->dtype = dtype; t->batch = batch; t->owner = m; t->data = nullptr;
+    cudaEvent_t ready = nullptr;
+    cudaError_t e = cudaMallocAsync(&t->data, bytes, m->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) t->events.push_back(ready);
+    if (e != cudaSuccess) { set_error("tensor allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); delete t; return WK_ERR_CUDA; }
+    *out = t;
+    return WK_OK;
+}
+
 wk_status wk_tensor_shape(const wk_tensor* t, int64_t* shape4, int32_t* ndim, int32_t* dtype) {
     if (!t) return WK_ERR_INVALID_ARGUMENT;
     const wk_model_config& c = t->owner->cfg;
@@ -959,68 +748,79 @@ wk_status wk_tensor_shape(const wk_tensor* t, int64_t* shape4, int32_t* ndim, in
     return WK_OK;
 }
 
-wk_status wk_tensor_to_host(const wk_tensor* t, float* dst, int64_t dst_elems) {
+wk_status wk_tensor_to_host_strided(const wk_tensor* t, float* dst, int64_t stride_b, int64_t stride_c, int64_t stride_t, int64_t dst_elems) {
     if (!t || !dst) return WK_ERR_INVALID_ARGUMENT;
     wk_model* m = t->owner;
     WK_CUDA_CHECK(cudaSetDevice(m->device));
     const wk_model_config& c = m->cfg;
     const int64_t rows = t->kind == 0 ? 3000 : c.n_audio_ctx, cols = t->kind == 0 ? c.n_mels : c.d_model;
     const int64_t n = t->batch * rows * cols;
-    if (dst_elems < n) { set_error("wk_tensor_to_host: destination too small (%lld < %lld)", (long long)dst_elems, (long long)n); return WK_ERR_INVALID_ARGUMENT; }
+    const bool packed = stride_t == 1 && stride_c == rows && stride_b == rows * cols;
+    const int64_t span = (t->batch - 1) * stride_b + (cols - 1) * stride_c + (rows - 1) * stride_t + 1;
+    if (stride_b < 1 || stride_c < 1 || stride_t < 1 || dst_elems < span) {
+        set_error("wk_tensor_to_host: destination too small or bad strides (%lld elements, need %lld)", (long long)dst_elems, (long long)span);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    std::lock_guard<std::mutex> lock(m->api_mu);
     float* tmp = nullptr;
-    WK_CUDA_CHECK(cudaMalloc(&tmp, n * 4));
+    WK_CUDA_CHECK(cudaMallocAsync((void**)&tmp, n * 4, m->stream));
     wk_status s = t->kind == 0
         ? transpose_to_host_layout(t->data, tmp, t->batch, rows, cols, kMelRows, 1, kMelCols, WK_DTYPE_F16, m->stream)
         : transpose_to_host_layout(t->data, tmp, t->batch, rows, cols, rows, 0, cols, t->dtype, m->stream);
     if (s == WK_OK) {
-        cudaError_t e = cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        cudaError_t e;
+        if (packed) {
+            e = cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        } else {
+            // padded MLMultiArray rows (IOSurface-backed Float16/Float32 arrays, MLMultiArrayExtensions.swift:11-21): element strides
+            std::vector<float> host((size_t)n);
+            e = cudaMemcpyAsync(host.data(), tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+            if (e == cudaSuccess)
+                for (int64_t b = 0; b < t->batch; ++b)
+                    for (int64_t ch = 0; ch < cols; ++ch)
+                        for (int64_t r = 0; r < rows; ++r) dst[b * stride_b + ch * stride_c + r * stride_t] = host[(size_t)((b * cols + ch) * rows + r)];
+        }
         if (e != cudaSuccess) { set_error("wk_tensor_to_host: %s", cudaGetErrorString(e)); s = WK_ERR_CUDA; }
     }
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, m->stream);
     return s;
 }
 
-void wk_tensor_free(wk_tensor*) { /* tensors are views into model-owned workspaces */ }
-
-// ---------------------------------------------------------------------------------------------- mel / encode
-static wk_status mel_device(wk_model* m, const float* pcm_dev, int64_t n, int64_t stride, const int32_t* nvalid_dev) {
-    return mel_forward(m->mel_tables, pcm_dev, n, stride, nvalid_dev, m->mel, m->gmax, m->stream);
+wk_status wk_tensor_to_host(const wk_tensor* t, float* dst, int64_t dst_elems) {
+    if (!t) return WK_ERR_INVALID_ARGUMENT;
+    const wk_model_config& c = t->owner->cfg;
+    const int64_t rows = t->kind == 0 ? 3000 : c.n_audio_ctx, cols = t->kind == 0 ? c.n_mels : c.d_model;
+    return wk_tensor_to_host_strided(t, dst, rows * cols, rows, 1, dst_elems);
 }
 
+void wk_tensor_free(wk_tensor* t) {
+    if (!t) return;
+    wk_model* m = t->owner;
+    cudaSetDevice(m->device);
+    {
+        std::lock_guard<std::mutex> lock(m->api_mu);
+        for (cudaEvent_t e : t->events) cudaStreamWaitEvent(m->stream, e, 0);   // readers on session streams (cross-KV projection) finish first
+        cudaFreeAsync(t->data, m->stream);
+    }
+    for (cudaEvent_t e : t->events) cudaEventDestroy(e);
+    delete t;
+}
+
+// ---------------------------------------------------------------------------------------------- mel / encode
 wk_status wk_mel(wk_model* m, const float* pcm, int64_t n_windows, int64_t stride, const int32_t* samples_per_window, wk_tensor** mel_out) {
     if (!m || !pcm || !mel_out) { set_error("wk_mel: null argument"); return WK_ERR_INVALID_ARGUMENT; }
     if (n_windows < 1 || n_windows > m->cfg.max_batch) { set_error("wk_mel: n_windows %lld outside [1, max_batch=%d]", (long long)n_windows, m->cfg.max_batch); return WK_ERR_AUDIO_PROCESSING_FAILED; }
-    if (stride < kWindowSamples) {
-        // short rows: treat as padOrTrim of each row
-        if (!samples_per_window) { set_error("wk_mel: stride %lld < 480000 requires samples_per_window", (long long)stride); return WK_ERR_AUDIO_PROCESSING_FAILED; }
-    }
     WK_CUDA_CHECK(cudaSetDevice(m->device));
-    cudaPointerAttributes at;
-    const bool on_device = cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeDevice;
-    cudaGetLastError();
-    const float* src = pcm;
-    int64_t src_stride = stride;
-    if (!on_device || stride < kWindowSamples) {
-        if (stride >= kWindowSamples) {
-            WK_CUDA_CHECK(cudaMemcpy2DAsync(m->pcm_dev, kWindowSamples * 4, pcm, stride * 4, kWindowSamples * 4, n_windows, cudaMemcpyDefault, m->stream));
-        } else {
-            WK_CUDA_CHECK(cudaMemsetAsync(m->pcm_dev, 0, (size_t)n_windows * kWindowSamples * 4, m->stream));
-            WK_CUDA_CHECK(cudaMemcpy2DAsync(m->pcm_dev, kWindowSamples * 4, pcm, stride * 4, stride * 4, n_windows, cudaMemcpyDefault, m->stream));
-        }
-        src = m->pcm_dev;
-        src_stride = kWindowSamples;
-    }
-    const int32_t* nv = nullptr;
-    if (samples_per_window) {
-        for (int64_t i = 0; i < n_windows; ++i)
-            if (samples_per_window[i] < 0 || samples_per_window[i] > kWindowSamples) { set_error("wk_mel: samples_per_window[%lld] out of range", (long long)i); return WK_ERR_AUDIO_PROCESSING_FAILED; }
-        WK_CUDA_CHECK(cudaMemcpyAsync(m->nvalid_dev, samples_per_window, n_windows * 4, cudaMemcpyHostToDevice, m->stream));
-        nv = m->nvalid_dev;
-    }
-    WK_CHECK(mel_device(m, src, n_windows, src_stride, nv));
-    m->mel_tensor.batch = n_windows;
-    *mel_out = &m->mel_tensor;
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    WK_CHECK(enc_ws_ensure(m, &m->ws, m->cfg.max_batch));
+    wk_tensor* t = nullptr;
+    WK_CHECK(tensor_new(m, 0, WK_DTYPE_F16, n_windows, (size_t)n_windows * kMelRows * kMelCols * 2, &t));
+    wk_status s = mel_run(m, &m->ws, pcm, n_windows, stride, samples_per_window, t->data, m->stream);
+    if (s != WK_OK) { cudaFreeAsync(t->data, m->stream); cudaEventDestroy(t->events[0]); delete t; return s; }
+    WK_CUDA_CHECK(cudaEventRecord(t->events[0], m->stream));
+    *mel_out = t;
     return WK_OK;
 }
 
@@ -1029,265 +829,14 @@ wk_status wk_encode(wk_model* m, const wk_tensor* mel, wk_tensor** enc_out) {
     if (!m->finalized) { set_error("wk_encode: model weights not finalized"); return WK_ERR_MODELS_UNAVAILABLE; }
     if (mel->kind != 0 || mel->owner != m) { set_error("wk_encode: input is not this model's mel tensor"); return WK_ERR_INVALID_ARGUMENT; }
     WK_CUDA_CHECK(cudaSetDevice(m->device));
-    WK_CHECK(encode_chunk(m, (int)mel->batch));
-    m->enc_tensor.batch = mel->batch;
-    *enc_out = &m->enc_tensor;
-    return WK_OK;
-}
-
-// ---------------------------------------------------------------------------------------------- session
-static wk_status lane_create(wk_model* m, int max_batch, Lane** out) {
-    const wk_model_config& c = m->cfg;
-    const int d = c.d_model, H = c.n_heads, L = c.dec_layers, T = c.n_audio_ctx;
-    Lane* s = new Lane();
-    s->m = m;
-    s->max_batch = max_batch;
-    WK_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    const int bpm = round_up(max_batch, 16);
-    WK_CHECK(alloc16(&s->cross_kv, (size_t)2 * L * max_batch * H * T * 64));
-    WK_CHECK(alloc16(&s->self_k, (size_t)L * max_batch * H * kKvMaxLen * 64));
-    WK_CHECK(alloc16(&s->self_v, (size_t)L * max_batch * H * kKvMaxLen * 64));
-    // split-K partial workspace: max over the decoder GEMM shapes of splits * N
-    size_t pe = 0;
-    const int shapes[4][2] = {{3 * d, d}, {d, d}, {4 * d, d}, {d, 4 * d}};
-    for (auto& sh : shapes) {
-        const int sp = choose_splits((sh[0] + 127) / 128, sh[1] / 64, m->num_sms);
-        pe = std::max(pe, (size_t)sp * sh[0]);
-    }
-    s->partial_elems = pe * bpm;
-    WK_CHECK(dmalloc(&s->partial, s->partial_elems));
-    WK_CHECK(dmalloc(&s->x, (size_t)bpm * d));
-    WK_CHECK(alloc16(&s->xn, (size_t)bpm * d));
-    WK_CHECK(alloc16(&s->attn, (size_t)bpm * d));
-    WK_CHECK(alloc16(&s->ffn, (size_t)bpm * 4 * d));
-    WK_CHECK(dmalloc(&s->logits, (size_t)max_batch * c.vocab));
-    WK_CHECK(dmalloc(&s->st.tokens, (size_t)max_batch * kKvMaxLen));
-    WK_CHECK(dmalloc(&s->st.n_tokens, max_batch));
-    WK_CHECK(dmalloc(&s->st.logprobs, (size_t)max_batch * kKvMaxLen));
-    WK_CHECK(dmalloc(&s->st.next_token, max_batch));
-    WK_CHECK(dmalloc(&s->st.done, max_batch));
-    WK_CHECK(dmalloc(&s->st.first_low, max_batch));
-    WK_CHECK(dmalloc(&s->st.steps, max_batch));
-    WK_CHECK(dmalloc(&s->st.step, 1));
-    WK_CHECK(dmalloc(&s->st.n_done, 1));
-    WK_CHECK(dmalloc(&s->st.input_ids, max_batch));
-    WK_CHECK(dmalloc(&s->prompt_dev, kKvMaxLen));
-    WK_CHECK(dmalloc(&s->pos_dev, max_batch));
-    WK_CHECK(dmalloc(&s->suppress_dev, 4096));
-    WK_CHECK(dmalloc(&s->lang_dev, 4096));
-    *out = s;
-    return WK_OK;
-}
-
-static void lane_free(Lane* s) {
-    if (!s) return;
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-    void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
-                    s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.step, s->st.n_done, s->st.input_ids,
-                    s->prompt_dev, s->pos_dev, s->suppress_dev, s->lang_dev, s->align_scratch, s->align_w, s->align_keep, s->chain_counters};
-    for (void* p : ptrs) if (p) cudaFree(p);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    delete s;
-}
-
-wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
-    if (!m || !out || max_batch < 1 || max_batch > 512) { set_error("wk_session_create: bad arguments (max_batch %d)", max_batch); return WK_ERR_INVALID_ARGUMENT; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    wk_session* s = new wk_session();
-    s->m = m;
-    s->max_batch = max_batch;
-    // Optional second lane (WKB200_DECODE_LANES=2): measured on B200 at 64 windows it is bit-identical but not faster
-    // (1371 vs 1324 ms/step) - every decode kernel already fills the machine, so the two chains serialise - hence opt-in.
-    const char* lanes_env = getenv("WKB200_DECODE_LANES");
-    s->n_lanes = (max_batch >= 32 && lanes_env && atoi(lanes_env) == 2) ? 2 : 1;
-    if (max_batch > 256 && s->n_lanes == 1) { set_error("wk_session_create: max_batch %d > 256 needs two lanes", max_batch); return WK_ERR_INVALID_ARGUMENT; }
-    const int cap0 = s->n_lanes == 2 ? (max_batch + 1) / 2 : max_batch;
-    WK_CHECK(lane_create(m, cap0, &s->lane[0]));
-    if (s->n_lanes == 2) {
-        WK_CHECK(lane_create(m, max_batch - cap0 > 0 ? max_batch - cap0 : 1, &s->lane[1]));
-        // leave shared memory for the other lane's kernels on the same SM
-        s->lane[0]->gemm_max_stages = 3;
-        s->lane[1]->gemm_max_stages = 3;
-    }
-    WK_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_enc, cudaEventDisableTiming));
-    WK_CUDA_CHECK(cudaDeviceSynchronize());  // setup memsets ran on the legacy default stream
-    *out = s;
-    return WK_OK;
-}
-
-void wk_session_free(wk_session* s) {
-    if (!s) return;
-    cudaSetDevice(s->m->device);
-    cudaDeviceSynchronize();
-    lane_free(s->lane[0]);
-    lane_free(s->lane[1]);
-    if (s->ev_enc) cudaEventDestroy(s->ev_enc);
-    delete s;
-}
-
-wk_status wk_session_reset(wk_session* s) {
-    if (!s) return WK_ERR_INVALID_ARGUMENT;
-    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
-    const wk_model_config& c = s->m->cfg;
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        const size_t n = (size_t)c.dec_layers * ln->max_batch * c.n_heads * kKvMaxLen * 64 * 2;
-        WK_CUDA_CHECK(cudaMemsetAsync(ln->self_k, 0, n, ln->stream));
-        WK_CUDA_CHECK(cudaMemsetAsync(ln->self_v, 0, n, ln->stream));
-    }
-    return WK_OK;
-}
-
-wk_status wk_session_set_encoder_output(wk_session* s, const wk_tensor* enc) {
-    if (!s || !enc) { set_error("wk_session_set_encoder_output: null argument"); return WK_ERR_INVALID_ARGUMENT; }
-    wk_model* m = s->m;
-    if (enc->kind != 1 || enc->owner != m) { set_error("encoder output does not belong to this model"); return WK_ERR_INVALID_ARGUMENT; }
-    if (enc->batch < 1 || enc->batch > s->max_batch) { set_error("encoder batch %lld exceeds session max_batch %d", (long long)enc->batch, s->max_batch); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    const wk_model_config& c = m->cfg;
-    const int d = c.d_model, T = c.n_audio_ctx;
-    s->batch = (int)enc->batch;
-    const int B0 = s->n_lanes == 2 ? (s->batch + 1) / 2 : s->batch;
-    // the encoder ran on the model stream; lanes consume its output on their own streams
-    WK_CUDA_CHECK(cudaEventRecord(s->ev_enc, m->stream));
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        ln->b0 = li == 0 ? 0 : B0;
-        ln->batch = li == 0 ? B0 : s->batch - B0;
-        ln->bp = round_up(ln->batch > 0 ? ln->batch : 1, 16);
-        if (ln->batch == 0) continue;
-        WK_CUDA_CHECK(cudaStreamWaitEvent(ln->stream, s->ev_enc, 0));
-        const int64_t M = (int64_t)ln->batch * T;
-        const char* a = (const char*)enc->data + (size_t)ln->b0 * T * d * 2;
-        GemmDesc g = plain_gemm(a, M, d, m->wckv, 2 * c.dec_layers * d, c.dtype, GEMM_OUT_T16_HEADS, ln->cross_kv, 0, m->bckv, 0);
-        g.heads_T = T; g.heads_B = ln->max_batch; g.heads_H = c.n_heads; g.heads_dmodel = d;
-        WK_CHECK(gemm_tcgen05(g, m->num_sms, ln->stream));
-    }
-    return WK_OK;
-}
-
-wk_status wk_build_prompt(const wk_model* m, const wk_special_tokens* st, const wk_decode_opts* o, int32_t use_options, int32_t* out, int32_t cap, int32_t* n) {
-    // prefillDecoderInputs (TextDecoder.swift:163-216)
-    if (!m || !st || !out || !n) return WK_ERR_INVALID_ARGUMENT;
-    std::vector<int32_t> p;
-    p.push_back(st->start_of_transcript_token);
-    if (use_options && o) {
-        const bool multilingual = m->cfg.vocab != 51864;
-        if (multilingual) {
-            p.push_back(o->language_token >= 0 ? o->language_token : st->english_token);
-            p.push_back(o->task_translate ? st->translate_token : st->transcribe_token);
-        }
-        p.push_back(o->without_timestamps ? st->no_timestamps_token : st->time_token_begin);
-        if (o->n_prompt_tokens >= 0 && (o->prompt_tokens || o->n_prompt_tokens == 0)) {
-            const int maxlen = kKvMaxLen / 2 - 1;
-            std::vector<int32_t> q;
-            const int start = o->n_prompt_tokens > maxlen ? o->n_prompt_tokens - maxlen : 0;
-            q.push_back(st->start_of_previous_token);
-            for (int i = start; i < o->n_prompt_tokens; ++i)
-                if (o->prompt_tokens[i] < st->special_token_begin) q.push_back(o->prompt_tokens[i]);
-            q.insert(q.end(), p.begin(), p.end());
-            p.swap(q);
-        }
-        if (o->n_prefix_tokens >= 0 && (o->prefix_tokens || o->n_prefix_tokens == 0)) {
-            const int maxlen = kKvMaxLen / 2;
-            const int start = o->n_prefix_tokens > maxlen ? o->n_prefix_tokens - maxlen : 0;
-            for (int i = start; i < o->n_prefix_tokens; ++i)
-                if (o->prefix_tokens[i] < st->special_token_begin) p.push_back(o->prefix_tokens[i]);
-        }
-    }
-    if ((int)p.size() > cap) { set_error("wk_build_prompt: capacity %d < %zu", cap, p.size()); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    memcpy(out, p.data(), p.size() * 4);
-    *n = (int)p.size();
-    return WK_OK;
-}
-
-wk_status wk_decode_step(wk_session* s, const int32_t* input_ids, const int32_t* cache_length, float* logits_out) {
-    if (!s || !input_ids || !cache_length) { set_error("wk_decode_step: null argument"); return WK_ERR_INVALID_ARGUMENT; }
-    wk_model* m = s->m;
-    if (s->batch < 1) { set_error("wk_decode_step: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    for (int i = 0; i < s->batch; ++i) {
-        if (cache_length[i] < 0 || cache_length[i] >= kKvMaxLen) { set_error("wk_decode_step: cache_length[%d]=%d out of range", i, cache_length[i]); return WK_ERR_DECODING_LOGITS_FAILED; }
-        if (input_ids[i] < 0 || input_ids[i] >= m->cfg.vocab) { set_error("wk_decode_step: input_ids[%d]=%d out of range", i, input_ids[i]); return WK_ERR_DECODING_LOGITS_FAILED; }
-    }
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        if (ln->batch == 0) continue;
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.input_ids, input_ids + ln->b0, ln->batch * 4, cudaMemcpyHostToDevice, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->pos_dev, cache_length + ln->b0, ln->batch * 4, cudaMemcpyHostToDevice, ln->stream));
-        WK_CHECK(decoder_forward(ln, 0, 0, ln->pos_dev));
-        if (logits_out)
-            WK_CUDA_CHECK(cudaMemcpyAsync(logits_out + (size_t)ln->b0 * m->cfg.vocab, ln->logits, (size_t)ln->batch * m->cfg.vocab * 4,
-                                          cudaMemcpyDeviceToHost, ln->stream));
-    }
-    for (int li = 0; li < s->n_lanes; ++li) {
-        if (s->lane[li]->batch == 0) continue;
-        cudaError_t e = cudaStreamSynchronize(s->lane[li]->stream);
-        if (e != cudaSuccess) { set_error("wk_decode_step: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_LOGITS_FAILED; }
-    }
-    return WK_OK;
-}
-
-wk_status wk_session_last_logits(wk_session* s, float* logits_out) {
-    if (!s || !logits_out) return WK_ERR_INVALID_ARGUMENT;
-    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        if (ln->batch == 0) continue;
-        WK_CUDA_CHECK(cudaMemcpyAsync(logits_out + (size_t)ln->b0 * s->m->cfg.vocab, ln->logits, (size_t)ln->batch * s->m->cfg.vocab * 4,
-                                      cudaMemcpyDeviceToHost, ln->stream));
-        WK_CUDA_CHECK(cudaStreamSynchronize(ln->stream));
-    }
-    return WK_OK;
-}
-
-// Number of concurrent decode lanes and the windows currently bound to each (bench / tests).
-wk_status wk_session_lanes(const wk_session* s, int32_t* n_lanes, int32_t* lane_batch2) {
-    if (!s || !n_lanes) return WK_ERR_INVALID_ARGUMENT;
-    *n_lanes = s->n_lanes;
-    if (lane_batch2) { lane_batch2[0] = s->lane[0]->batch; lane_batch2[1] = s->n_lanes == 2 ? s->lane[1]->batch : 0; }
-    return WK_OK;
-}
-
-// TextDecoder.detectLanguage (TextDecoder.swift:420-539): one decoder step on [SOT] at position 0, LanguageLogitsFilter
-// (keep only the language tokens), GreedyTokenSampler -> language token id + logprob for every bound window.
-wk_status wk_detect_language(wk_session* s, const wk_special_tokens* st, const int32_t* language_tokens, int32_t n_language_tokens,
-                             float temperature, int32_t* token_out, float* logprob_out) {
-    if (!s || !st || !language_tokens || n_language_tokens < 1 || n_language_tokens > 4096 || !token_out) {
-        set_error("wk_detect_language: bad arguments");
-        return WK_ERR_INVALID_ARGUMENT;
-    }
-    wk_model* m = s->m;
-    if (s->batch < 1) { set_error("wk_detect_language: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        const int B = ln->batch;
-        if (B == 0) continue;
-        std::vector<int32_t> ids(B, st->start_of_transcript_token), zeros(B, 0), ones(B, 1);
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.input_ids, ids.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->pos_dev, zeros.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));
-        WK_CHECK(decoder_forward(ln, 0, 0, ln->pos_dev));
-        // currentTokens = [SOT] for every window: reuse the decode-state arrays as the stateless token history
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.tokens, ids.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));   // ld_tokens = 1
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->st.n_tokens, ones.data(), B * 4, cudaMemcpyHostToDevice, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->lang_dev, language_tokens, n_language_tokens * 4, cudaMemcpyHostToDevice, ln->stream));
-        SamplerParams p;
-        memset(&p, 0, sizeof(p));
-        p.st = *st; p.vocab = m->cfg.vocab; p.is_multilingual = 1;
-        p.sample_begin_ts = -1; p.sample_begin_blank = -1;
-        p.language_tokens = ln->lang_dev; p.n_language_tokens = n_language_tokens; p.language_sample_begin = 0;
-        p.temperature = temperature; p.top_k = 5; p.seed = 0;
-        p.prompt_len = -1; p.max_ctx = kKvMaxLen;
-        DecodeState none;
-        memset(&none, 0, sizeof(none));
-        WK_CHECK(sampler_filter_sample(ln->logits, m->cfg.vocab, p, none, ln->st.tokens, 1, ln->st.n_tokens, ln->st.next_token,
-                                       ln->st.logprobs, nullptr, B, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(token_out + ln->b0, ln->st.next_token, B * 4, cudaMemcpyDeviceToHost, ln->stream));
-        if (logprob_out) WK_CUDA_CHECK(cudaMemcpyAsync(logprob_out + ln->b0, ln->st.logprobs, B * 4, cudaMemcpyDeviceToHost, ln->stream));
-        cudaError_t e = cudaStreamSynchronize(ln->stream);
-        if (e != cudaSuccess) { set_error("wk_detect_language: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
-    }
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    WK_CHECK(enc_ws_ensure(m, &m->ws, m->cfg.max_batch));
+    wk_tensor* t = nullptr;
+    WK_CHECK(tensor_new(m, 1, m->cfg.dtype, mel->batch, (size_t)mel->batch * m->cfg.n_audio_ctx * m->cfg.d_model * 2, &t));
+    wk_status s = encode_chunk(m, &m->ws, mel->data, (int)mel->batch, t->data, m->stream);
+    if (s != WK_OK) { cudaFreeAsync(t->data, m->stream); cudaEventDestroy(t->events[0]); delete t; return s; }
+    WK_CUDA_CHECK(cudaEventRecord(t->events[0], m->stream));   // (the mel tensor is read and released on this same stream: ordered)
+    *enc_out = t;
     return WK_OK;
 }
 
@@ -1298,6 +847,7 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
                            int32_t* token_out, float* logprob_out, float* filtered_out) {
     if (!m || !st || !opts || !logits || !n_tokens || batch < 1 || vocab < 2) { set_error("wk_filter_sample: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
     WK_CUDA_CHECK(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->api_mu);
     cudaStream_t s = m->stream;
     float *dlog = nullptr, *dfil = nullptr, *dlp = nullptr;
     int32_t *dtok = nullptr, *dn = nullptr, *dout = nullptr, *dsup = nullptr, *dlang = nullptr;
@@ -1315,7 +865,7 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
     WK_CUDA_CHECK(cudaMemcpyAsync(dn, n_tokens, batch * 4, cudaMemcpyDefault, s));
     SamplerParams p;
     memset(&p, 0, sizeof(p));
-    p.st = *st; p.vocab = vocab; p.is_multilingual = is_multilingual;
+    p.st = *st; p.vocab = vocab; p.is_multilingual = is_multilingual; p.loop_mode = 0;
     p.sample_begin_ts = sample_begin_ts; p.sample_begin_blank = sample_begin_blank;
     std::vector<int32_t> sup;
     for (int i = 0; i < opts->n_suppress_tokens; ++i)
@@ -1328,7 +878,7 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
         p.language_tokens = dlang; p.n_language_tokens = n_language_tokens; p.language_sample_begin = language_sample_begin;
     }
     p.temperature = opts->temperature; p.top_k = opts->top_k; p.seed = opts->seed;
-    p.prompt_len = -1; p.max_ctx = kKvMaxLen;
+    p.max_ctx = kKvMaxLen;
     DecodeState none;
     memset(&none, 0, sizeof(none));
     wk_status r = sampler_filter_sample(dlog, vocab, p, none, dtok, ldt, dn, dout, dlp, dfil, batch, s);
@@ -1342,245 +892,6 @@ wk_status wk_filter_sample(wk_model* m, const wk_special_tokens* st, const wk_de
     }
     cudaFree(dlog); cudaFree(dfil); cudaFree(dlp); cudaFree(dtok); cudaFree(dn); cudaFree(dout); cudaFree(dsup); cudaFree(dlang);
     return r;
-}
-
-// finalisation of one window on the host: finalize + slicing + averages (TextDecoder.swift:776-853)
-static void finalize_result(wk_decode_result& r, const int32_t* tokens, const float* lps, int n_tok, int steps, int first_low,
-                            const wk_special_tokens* st, const wk_decode_opts* o) {
-    memset(&r, 0, sizeof(r));
-    std::vector<int32_t> seg(tokens, tokens + n_tok);
-    std::vector<float> slp(lps, lps + n_tok);
-    r.n_current_tokens = n_tok;
-    r.steps = steps;
-    r.first_token_logprob_too_low = first_low;
-    if (seg.empty() || seg.back() != st->end_token) { seg.push_back(st->end_token); slp.push_back(0.f); }  // sampler.finalize
-    size_t start = 0, end = seg.size();
-    for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->start_of_transcript_token) { start = i; break; }
-    for (size_t i = 0; i < seg.size(); ++i) if (seg[i] == st->end_token) { end = i; break; }
-    if (end >= seg.size()) end = seg.size() - 1;
-    if (end < start) start = 0;
-    float sum = 0.f;
-    std::vector<int32_t> words;
-    r.n_tokens = 0;
-    for (size_t i = start; i <= end && r.n_tokens < 226; ++i) {
-        r.tokens[r.n_tokens] = seg[i];
-        r.token_logprobs[r.n_tokens] = slp[i];
-        sum += slp[i];
-        if (seg[i] < st->special_token_begin) words.push_back(seg[i]);
-        ++r.n_tokens;
-    }
-    r.avg_logprob = sum / (float)r.n_tokens;
-    r.compression_ratio = compression_ratio(words);
-    r.temperature = roundf(o->temperature * 1000.f) / 1000.f;
-    // DecodingFallback (Models.swift:357-381); noSpeechProb is always 0 in the reference (TextDecoder.swift:802)
-    r.needs_fallback = 0; r.fallback_reason = 0;
-    if (first_low) { r.needs_fallback = 1; r.fallback_reason = 1; }
-    else if (o->has_no_speech_threshold && 0.f > o->no_speech_threshold) { r.needs_fallback = 0; r.fallback_reason = 2; }
-    else if (o->has_compression_ratio_threshold && r.compression_ratio > o->compression_ratio_threshold) { r.needs_fallback = 1; r.fallback_reason = 3; }
-    else if (o->has_logprob_threshold && r.avg_logprob < o->logprob_threshold) { r.needs_fallback = 1; r.fallback_reason = 4; }
-}
-
-wk_status wk_decode_text(wk_session* s, const wk_special_tokens* st, const wk_decode_opts* o, const int32_t* prompt, int32_t n_prompt,
-                         wk_decode_result* results) {
-    if (!s || !st || !o || !prompt || !results) { set_error("wk_decode_text: null argument"); return WK_ERR_INVALID_ARGUMENT; }
-    wk_model* m = s->m;
-    if (s->batch < 1) { set_error("wk_decode_text: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    if (n_prompt < 1 || n_prompt >= kKvMaxLen) { set_error("wk_decode_text: prompt length %d out of range", n_prompt); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    for (int i = 0; i < n_prompt; ++i)
-        if (prompt[i] < 0 || prompt[i] >= m->cfg.vocab) { set_error("wk_decode_text: prompt token %d out of range", prompt[i]); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    const bool multilingual = m->cfg.vocab != 51864;
-    const int loop_count = std::min(o->sample_length, kKvMaxLen - 1);  // TextDecoder.swift:566
-    const bool use_graph = getenv("WKB200_NO_GRAPH") == nullptr;
-    // createLogitsFilters (TextDecoder.swift:857-899): SuppressBlank(sampleBegin = prefilledIndex = 0),
-    // SuppressTokens(< specialTokenBegin), TimestampRules(sampleBegin = initialPrompt.count)
-    SamplerParams sp[2];
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        if (ln->batch == 0) continue;
-        WK_CUDA_CHECK(cudaMemcpyAsync(ln->prompt_dev, prompt, n_prompt * 4, cudaMemcpyHostToDevice, ln->stream));
-        WK_CHECK(decode_state_init(ln->st, ln->prompt_dev, n_prompt, ln->batch, ln->stream));
-        sp[li] = make_sampler_params(ln, st, o, multilingual ? 1 : 0, o->without_timestamps ? -1 : n_prompt, o->suppress_blank ? 0 : -1, n_prompt);
-        WK_CHECK(upload_suppress(ln, st, o, &sp[li].n_suppress));
-        if (ln->graph_exec) { cudaGraphExecDestroy(ln->graph_exec); ln->graph_exec = nullptr; }
-        ln->launches_per_step = 0;
-        ln->align_on = o->word_timestamps != 0;
-        if (ln->align_on) {
-            const size_t T = m->cfg.n_audio_ctx;
-            if (!ln->align_w || ln->align_slots != m->n_align_slots) {
-                if (ln->align_scratch) { cudaFree(ln->align_scratch); ln->align_scratch = nullptr; }
-                if (!ln->align_w) WK_CUDA_CHECK(cudaMalloc(&ln->align_w, (size_t)ln->max_batch * kKvMaxLen * T * 2));
-                WK_CUDA_CHECK(cudaMalloc((void**)&ln->align_scratch, (size_t)m->n_align_slots * ln->max_batch * T * 4));
-                ln->align_slots = m->n_align_slots;
-            }
-            WK_CUDA_CHECK(cudaMemsetAsync(ln->align_w, 0, (size_t)ln->batch * kKvMaxLen * T * 2, ln->stream));   // row 0 and unreached rows stay 0
-        }
-    }
-    auto one_step = [&](int li) -> wk_status {
-        Lane* ln = s->lane[li];
-        WK_CHECK(decoder_forward(ln, n_prompt, st->time_token_begin, nullptr));
-        WK_CHECK(sampler_filter_sample(ln->logits, m->cfg.vocab, sp[li], ln->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, ln->batch, ln->stream));
-        if (ln->align_on)
-            WK_CHECK(decoder_align_mean(ln->align_scratch, m->n_align_slots, ln->st.step, ln->st.done, ln->align_w, ln->batch, m->cfg.n_audio_ctx,
-                                        kKvMaxLen, ln->stream));
-        return WK_OK;
-    };
-    for (int step = 0; step < loop_count; ++step) {
-        bool redo = false;
-        for (int li = 0; li < s->n_lanes && !redo; ++li) {
-            Lane* ln = s->lane[li];
-            if (ln->batch == 0) continue;
-            if (step == 0 || !use_graph) {
-                WK_CHECK(one_step(li));
-                continue;
-            }
-            if (!ln->graph_exec) {
-                cudaGraph_t graph = nullptr;
-                const long long before = g_launches.load();
-                WK_CUDA_CHECK(cudaStreamBeginCapture(ln->stream, cudaStreamCaptureModeThreadLocal));
-                wk_status r = one_step(li);
-                cudaError_t e = cudaStreamEndCapture(ln->stream, &graph);
-                ln->launches_per_step = g_launches.load() - before;
-                g_launches.fetch_sub(ln->launches_per_step);  // captured, not executed
-                if (r != WK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
-                if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-                e = cudaGraphInstantiate(&ln->graph_exec, graph, 0);
-                cudaGraphDestroy(graph);
-                if (e != cudaSuccess && pdl_enabled()) {
-                    // programmatic edges rejected by this driver: fall back to plain serialisation and re-capture
-                    cudaGetLastError();
-                    pdl_disable();
-                    ln->graph_exec = nullptr;
-                    redo = true;
-                    break;
-                }
-                if (e != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-            }
-            WK_CUDA_CHECK(cudaGraphLaunch(ln->graph_exec, ln->stream));
-            count_launch((int)ln->launches_per_step);
-        }
-        if (redo) { --step; continue; }
-        if ((step & 15) == 15) {  // early exit when every window has completed
-            int done = 0, total = 0;
-            for (int li = 0; li < s->n_lanes; ++li) {
-                Lane* ln = s->lane[li];
-                if (ln->batch == 0) continue;
-                int32_t nd = 0;
-                WK_CUDA_CHECK(cudaMemcpyAsync(&nd, ln->st.n_done, 4, cudaMemcpyDeviceToHost, ln->stream));
-                WK_CUDA_CHECK(cudaStreamSynchronize(ln->stream));
-                done += nd; total += ln->batch;
-            }
-            if (done >= total) break;
-        }
-    }
-    // ---- read back and finalise on the host
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        const int B = ln->batch;
-        if (B == 0) continue;
-        std::vector<int32_t> tokens((size_t)B * kKvMaxLen), n_tok(B), first_low(B), steps(B);
-        std::vector<float> lps((size_t)B * kKvMaxLen);
-        WK_CUDA_CHECK(cudaMemcpyAsync(tokens.data(), ln->st.tokens, tokens.size() * 4, cudaMemcpyDeviceToHost, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(lps.data(), ln->st.logprobs, lps.size() * 4, cudaMemcpyDeviceToHost, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(n_tok.data(), ln->st.n_tokens, B * 4, cudaMemcpyDeviceToHost, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(first_low.data(), ln->st.first_low, B * 4, cudaMemcpyDeviceToHost, ln->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(steps.data(), ln->st.steps, B * 4, cudaMemcpyDeviceToHost, ln->stream));
-        cudaError_t e = cudaStreamSynchronize(ln->stream);
-        if (e != cudaSuccess) { set_error("wk_decode_text: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
-        for (int b = 0; b < B; ++b)
-            finalize_result(results[ln->b0 + b], tokens.data() + (size_t)b * kKvMaxLen, lps.data() + (size_t)b * kKvMaxLen, n_tok[b], steps[b],
-                            first_low[b], st, o);
-    }
-    return WK_OK;
-}
-
-// word timestamps across the fallback ladder: align_w belongs to the LAST decode; align_keep collects, per window, the alignment of
-// the decode whose result was kept.  window < 0 = every bound window; to_keep = align_w -> align_keep, else back.
-static wk_status align_keep_copy(wk_session* s, int window, bool to_keep) {
-    const size_t T = s->m->cfg.n_audio_ctx, block = (size_t)kKvMaxLen * T * 2;
-    for (int li = 0; li < s->n_lanes; ++li) {
-        Lane* ln = s->lane[li];
-        if (ln->batch == 0 || !ln->align_w) continue;
-        if (!ln->align_keep) WK_CUDA_CHECK(cudaMalloc(&ln->align_keep, (size_t)ln->max_batch * block));
-        int b0 = 0, nb = ln->batch;
-        if (window >= 0) {
-            if (window < ln->b0 || window >= ln->b0 + ln->batch) continue;
-            b0 = window - ln->b0; nb = 1;
-        }
-        char* w = (char*)ln->align_w + (size_t)b0 * block;
-        char* k = (char*)ln->align_keep + (size_t)b0 * block;
-        WK_CUDA_CHECK(cudaMemcpyAsync(to_keep ? k : w, to_keep ? w : k, (size_t)nb * block, cudaMemcpyDeviceToDevice, ln->stream));
-    }
-    return WK_OK;
-}
-
-wk_status wk_transcribe_windows(wk_model* m, wk_session* s, const float* pcm_host, int64_t n_windows, int64_t stride,
-                                const int32_t* samples_per_window, const wk_special_tokens* st, const wk_decode_opts* opts,
-                                const int32_t* prompt, int32_t n_prompt, wk_decode_result* results) {
-    if (!m || !s || !pcm_host || !st || !opts || !prompt || !results) { set_error("wk_transcribe_windows: null argument"); return WK_ERR_INVALID_ARGUMENT; }
-    if (s->m != m) { set_error("wk_transcribe_windows: session belongs to another model"); return WK_ERR_INVALID_ARGUMENT; }
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    const int chunk = std::min(m->cfg.max_batch, s->max_batch);
-    float acc[6] = {0, 0, 0, 0, 0, 0};
-    cudaPointerAttributes pat;
-    const bool pcm_on_device = cudaPointerGetAttributes(&pat, pcm_host) == cudaSuccess && pat.type == cudaMemoryTypeDevice;
-    cudaGetLastError();
-    for (int64_t w0 = 0; w0 < n_windows; w0 += chunk) {
-        const int64_t nb = std::min<int64_t>(chunk, n_windows - w0);
-        wk_tensor *mel = nullptr, *enc = nullptr;
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[0], m->stream));
-        // H2D inside wk_mel (host pointer) ; time it separately by staging first
-        if (stride < kWindowSamples && !samples_per_window) { set_error("wk_transcribe_windows: stride < 480000 requires samples_per_window"); return WK_ERR_AUDIO_PROCESSING_FAILED; }
-        const float* src = pcm_host + w0 * stride;
-        int64_t src_stride = stride;
-        if (!(pcm_on_device && stride >= kWindowSamples)) {   // host PCM (or short rows): stage into the device workspace
-            WK_CUDA_CHECK(cudaMemcpy2DAsync(m->pcm_dev, kWindowSamples * 4, src, stride * 4,
-                                            std::min<int64_t>(stride, kWindowSamples) * 4, nb, cudaMemcpyDefault, m->stream));
-            src = m->pcm_dev;
-            src_stride = kWindowSamples;
-        }
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[1], m->stream));
-        WK_CHECK(wk_mel(m, src, nb, src_stride, samples_per_window ? samples_per_window + w0 : nullptr, &mel));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[2], m->stream));
-        WK_CHECK(wk_encode(m, mel, &enc));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[3], m->stream));
-        WK_CHECK(wk_session_set_encoder_output(s, enc));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[4], s->lane[0]->stream));   // lane 0's cross-KV projection done
-        WK_CHECK(wk_decode_text(s, st, opts, prompt, n_prompt, results + w0));   // returns with both lanes drained
-        // decodeWithFallback (TranscribeTask.swift:316-411): the encoder output and cross-attention K/V of the chunk stay bound;
-        // only the token loop reruns, at Float16(temperature) + Float16(i) * Float16(increment) (:327), for windows that ask.
-        bool retried = false;
-        for (int i = 1; i <= opts->temperature_fallback_count; ++i) {
-            bool any = false;
-            for (int64_t b = 0; b < nb; ++b) any |= results[w0 + b].needs_fallback != 0;
-            if (!any) break;
-            if (opts->word_timestamps && !retried) WK_CHECK(align_keep_copy(s, -1, true));   // alignment of every window of the first pass
-            retried = true;
-            wk_decode_opts o2 = *opts;
-            const float f16_t = __half2float(__float2half(opts->temperature));
-            const float f16_step = __half2float(__float2half(__half2float(__float2half((float)i)) * __half2float(__float2half(opts->temperature_increment_on_fallback))));
-            o2.temperature = __half2float(__float2half(f16_t + f16_step));
-            o2.seed = opts->seed + (uint64_t)i;
-            std::vector<wk_decode_result> retry((size_t)nb);
-            WK_CHECK(wk_decode_text(s, st, &o2, prompt, n_prompt, retry.data()));
-            for (int64_t b = 0; b < nb; ++b)
-                if (results[w0 + b].needs_fallback) {
-                    results[w0 + b] = retry[b];
-                    if (opts->word_timestamps) WK_CHECK(align_keep_copy(s, (int)b, true));   // this window's alignment now comes from the retry
-                }
-        }
-        if (opts->word_timestamps && retried) WK_CHECK(align_keep_copy(s, -1, false));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[5], m->stream));
-        WK_CUDA_CHECK(cudaEventSynchronize(m->ev[5]));
-        float t;
-        cudaEventElapsedTime(&t, m->ev[0], m->ev[1]); acc[4] += t;
-        cudaEventElapsedTime(&t, m->ev[1], m->ev[2]); acc[0] += t;
-        cudaEventElapsedTime(&t, m->ev[2], m->ev[3]); acc[1] += t;
-        cudaEventElapsedTime(&t, m->ev[3], m->ev[4]); acc[2] += t;
-        cudaEventElapsedTime(&t, m->ev[4], m->ev[5]); acc[3] += t;
-    }
-    memcpy(m->timings, acc, sizeof(acc));
-    return WK_OK;
 }
 
 static void default_alignment_heads(wk_model* m) {
@@ -1598,7 +909,7 @@ static void default_alignment_heads(wk_model* m) {
 
 wk_status wk_model_set_alignment_heads(wk_model* m, const int32_t* layer_head_pairs, int32_t n_pairs) {
     if (!m || n_pairs < 0 || (n_pairs > 0 && !layer_head_pairs)) { set_error("wk_model_set_alignment_heads: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
-    if (n_pairs == 0) { default_alignment_heads(m); return WK_OK; }
+    if (n_pairs == 0) { default_alignment_heads(m); m->has_alignment_heads = 0; return WK_OK; }
     const int L = m->cfg.dec_layers, H = m->cfg.n_heads;
     std::vector<uint32_t> mask(L, 0u);
     for (int i = 0; i < n_pairs; ++i) {
@@ -1611,27 +922,13 @@ wk_status wk_model_set_alignment_heads(wk_model* m, const int32_t* layer_head_pa
     int slots = 0;
     for (int l = 0; l < L; ++l) { m->align_base[l] = slots; slots += __builtin_popcount(mask[l]); }
     m->n_align_slots = slots;
-    return WK_OK;
-}
-
-wk_status wk_session_alignment_weights(wk_session* s, int32_t window, int32_t rows, float* out) {
-    if (!s || !out || window < 0 || window >= s->batch || rows < 0 || rows > kKvMaxLen) { set_error("wk_session_alignment_weights: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
-    Lane* ln = s->lane[0];
-    for (int li = 0; li < s->n_lanes; ++li)
-        if (s->lane[li]->batch > 0 && window >= s->lane[li]->b0 && window < s->lane[li]->b0 + s->lane[li]->batch) ln = s->lane[li];
-    if (!ln->align_on || !ln->align_w) { set_error("wk_session_alignment_weights: the last decode did not ask for word timestamps"); return WK_ERR_INVALID_ARGUMENT; }
-    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
-    const size_t T = s->m->cfg.n_audio_ctx;
-    std::vector<__half> h((size_t)rows * T);
-    WK_CUDA_CHECK(cudaMemcpyAsync(h.data(), (const __half*)ln->align_w + (size_t)(window - ln->b0) * kKvMaxLen * T, h.size() * 2, cudaMemcpyDeviceToHost, ln->stream));
-    WK_CUDA_CHECK(cudaStreamSynchronize(ln->stream));
-    for (size_t i = 0; i < h.size(); ++i) out[i] = __half2float(h[i]);
+    m->has_alignment_heads = 1;
     return WK_OK;
 }
 
 int64_t wk_kernel_launch_count(int32_t reset) {
-    const long long v = wk::g_launches.load();
-    if (reset) wk::g_launches.store(0);
+    const long long v = wk::launch_counter_load();
+    if (reset) wk::launch_counter_sub(v);
     return v;
 }
 
@@ -1643,12 +940,14 @@ wk_status wk_last_timings(wk_model* m, float* ms6) {
 
 // ---------------------------------------------------------------------------------------------- kernel-level hooks
 wk_status wk_test_gemm(wk_model* m, const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
-                       int32_t in_dtype, int32_t out_dtype, int32_t gelu, int32_t simt_reference) {
+                       int32_t in_dtype, int32_t out_dtype, int32_t gelu) {
     if (!m) return WK_ERR_INVALID_ARGUMENT;
     WK_CUDA_CHECK(cudaSetDevice(m->device));
-    if (simt_reference) return gemm_simt_reference(a, w, bias, out, M, N, K, in_dtype, out_dtype, gelu, m->stream);
+    std::lock_guard<std::mutex> lock(m->api_mu);
     const int mode = out_dtype == WK_DTYPE_F32 ? GEMM_OUT_F32 : GEMM_OUT_T16;
-    return gemm_tcgen05(plain_gemm(a, M, K, w, N, in_dtype, mode, out, N, bias, gelu), m->num_sms, m->stream);
+    WK_CHECK(gemm_tcgen05(plain_gemm(a, M, K, w, N, in_dtype, mode, out, N, bias, gelu), m->num_sms, m->stream));
+    WK_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return WK_OK;
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int Bp, int N, int rows, float* __restrict__ out) {
@@ -1663,6 +962,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sp
 wk_status wk_test_gemm_splitk(wk_model* m, const void* w, const void* x, float* out, int32_t N, int32_t rows_x, int32_t K, int32_t in_dtype, int32_t splits) {
     if (!m) return WK_ERR_INVALID_ARGUMENT;
     WK_CUDA_CHECK(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->api_mu);
     if (rows_x % 16 != 0 || rows_x > 256) { set_error("wk_test_gemm_splitk: rows_x must be a multiple of 16 <= 256"); return WK_ERR_INVALID_ARGUMENT; }
     const int tiles = (N + 127) / 128;
     const int sp = splits > 0 ? splits : choose_splits(tiles, K / 64, m->num_sms);
@@ -1685,153 +985,44 @@ wk_status wk_test_gemm_splitk(wk_model* m, const void* w, const void* x, float* 
     return r;
 }
 
-// Average device time (ms, CUDA events on the library stream) of one launch of a named hot kernel on the session's
-// current buffers: which = 0 decoder cross-attention (one layer, bound batch), 1 encoder FC1 GEMM (M = B*1500),
-// 2 log-mel (pass 1 + pass 2, B windows), 3 encoder attention, 4 decoder QKV swap-AB GEMM, 5 encoder QKV GEMM,
-// 6 sampler.  Also returns the algorithmic bytes (HBM-bound kernels) or FLOPs (tensor-bound) of one launch.
-wk_status wk_bench_kernel(wk_model* m, wk_session* s, int32_t which, int32_t batch, int32_t iters, float* ms_out, double* work_out) {
-    if (!m || !ms_out || !work_out || iters < 1) return WK_ERR_INVALID_ARGUMENT;
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    const wk_model_config& c = m->cfg;
-    const int d = c.d_model, T = c.n_audio_ctx, H = c.n_heads, dt = c.dtype;
-    Lane* ln = s ? s->lane[0] : nullptr;
-    int B = batch;
-    if (ln && which != 1 && which != 2 && which != 3 && which != 5 && B > ln->max_batch) B = ln->max_batch;   // lane-local kernels run per lane
-    if (B < 1 || B > c.max_batch) { set_error("wk_bench_kernel: bad batch"); return WK_ERR_INVALID_ARGUMENT; }
-    const int64_t M = (int64_t)B * T;
-    cudaStream_t st = (ln && which != 1 && which != 2 && which != 3 && which != 5) ? ln->stream : m->stream;
-    auto run = [&]() -> wk_status {
-        switch (which) {
-            case 0: {
-                if (!ln) return WK_ERR_INVALID_ARGUMENT;
-                const size_t cross_block = (size_t)ln->max_batch * H * T * 64 * 2;
-                return decoder_cross_attention(ln->partial, 1, round_up(B, 16), m->dec[0].bcq, ln->cross_kv, (char*)ln->cross_kv + cross_block, ln->attn, B, H, T, dt, st);
-            }
-            case 1: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].w1, 4 * d, dt, GEMM_OUT_T16, m->ffn, 4 * d, m->enc[0].b1, 1), m->num_sms, st);
-            case 2: return mel_forward(m->mel_tables, m->pcm_dev, B, kWindowSamples, nullptr, m->mel, m->gmax, st);
-            case 3: return encoder_attention(m->qkv, m->attn, B, T, H, dt, st);
-            case 4: { if (!ln) return WK_ERR_INVALID_ARGUMENT; ln->bp = round_up(B, 16); int sp; return dec_gemm(ln, m->dec[0].wqkv, 3 * d, d, ln->xn, &sp); }
-            case 5: return gemm_tcgen05(plain_gemm(m->xn, M, d, m->enc[0].wqkv, 3 * d, dt, GEMM_OUT_T16, m->qkv, 3 * d, m->enc[0].bqkv, 0), m->num_sms, st);
-            case 6: { if (!ln) return WK_ERR_INVALID_ARGUMENT; ln->bp = round_up(B, 16); int sp; return dec_gemm(ln, m->dec[0].wo, d, d, ln->attn, &sp); }
-            case 7: { if (!ln) return WK_ERR_INVALID_ARGUMENT; ln->bp = round_up(B, 16); int sp; return dec_gemm(ln, m->dec[0].w2, d, 4 * d, ln->ffn, &sp); }
-            case 8: { if (!ln) return WK_ERR_INVALID_ARGUMENT;
-                      return decoder_reduce_resid_ln(ln->partial, choose_splits((d + 127) / 128, d / 64, m->num_sms), round_up(B, 16), m->dec[0].bo,
-                                                     m->dec[0].lnx.g, m->dec[0].lnx.b, ln->x, ln->xn, B, d, dt, st); }
-            case 9: { if (!ln) return WK_ERR_INVALID_ARGUMENT;
-                      static int32_t* pos100 = nullptr;
-                      if (!pos100) { std::vector<int32_t> h(256, 100); cudaMalloc(&pos100, 256 * 4); cudaMemcpy(pos100, h.data(), 256 * 4, cudaMemcpyHostToDevice); }
-                      return decoder_self_attention(ln->partial, 1, round_up(B, 16), m->dec[0].bq, m->dec[0].bv, ln->self_k, ln->self_v, ln->st.step, pos100,
-                                                    ln->attn, B, H, kKvMaxLen, dt, st); }
-            // 14-17: the decoder GEMMs with the weights rotating over all layers, so they stream from HBM as in a real step
-            case 14: case 15: case 16: case 17: {
-                if (!ln) return WK_ERR_INVALID_ARGUMENT;
-                static int rot = 0;
-                const int r = rot++;
-                const DecLayer& l = m->dec[r % c.dec_layers];
-                ln->bp = round_up(B, 16);
-                int sp;
-                if (which == 14) { const void* w3[3] = {l.wo, l.wcq, l.wco}; return dec_gemm(ln, w3[(r / c.dec_layers) % 3], d, d, ln->attn, &sp); }
-                if (which == 15) return dec_gemm(ln, l.w1, 4 * d, d, ln->xn, &sp);
-                if (which == 16) return dec_gemm(ln, l.w2, d, 4 * d, ln->ffn, &sp);
-                return dec_gemm(ln, l.wqkv, 3 * d, d, ln->xn, &sp);
-            }
-            default: set_error("wk_bench_kernel: unknown kernel %d", which); return WK_ERR_INVALID_ARGUMENT;
-        }
-    };
-    switch (which) {
-        case 0: *work_out = (double)B * H * T * 64 * 2 * 2; break;                         // K + V bytes
-        case 1: *work_out = 2.0 * (double)M * d * 4 * d; break;                            // FLOPs
-        case 2: *work_out = (double)B * (kWindowSamples * 4.0 + c.n_mels * 3000 * 2.0); break;  // bytes
-        case 3: *work_out = 4.0 * (double)B * H * T * T * 64; break;                       // FLOPs
-        case 4: *work_out = 3.0 * d * d * 2; break;                                        // weight bytes
-        case 5: *work_out = 2.0 * (double)M * d * 3 * d; break;
-        case 6: *work_out = 1.0 * d * d * 2; break;
-        case 7: *work_out = 4.0 * d * d * 2; break;
-        default: *work_out = 0; break;
-    }
-    for (int i = 0; i < 2; ++i) WK_CHECK(run());
-    float t = 0.f;
-    if (getenv("WKB200_BENCH_GRAPH")) {   // host launch cost removed: `iters` launches replayed as one CUDA graph
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        WK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        wk_status r = WK_OK;
-        for (int i = 0; i < iters && r == WK_OK; ++i) r = run();
-        WK_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
-        if (r != WK_OK) return r;
-        WK_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
-        WK_CUDA_CHECK(cudaGraphLaunch(exec, st));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[6], st));
-        WK_CUDA_CHECK(cudaGraphLaunch(exec, st));
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[7], st));
-        WK_CUDA_CHECK(cudaEventSynchronize(m->ev[7]));
-        cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
-    } else {
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[6], st));
-        for (int i = 0; i < iters; ++i) WK_CHECK(run());
-        WK_CUDA_CHECK(cudaEventRecord(m->ev[7], st));
-        WK_CUDA_CHECK(cudaEventSynchronize(m->ev[7]));
-        cudaEventElapsedTime(&t, m->ev[6], m->ev[7]);
-    }
-    *ms_out = t / iters;
-    return WK_OK;
-}
-
-// Debug readback of an internal buffer as f32 (tests/tools only).  which: 0 mel[Bm,3002,128] 1 h1[Bm,3002,d] 2 x[M,d]
-// 3 xn[M,d] 4 qkv[M,3d] 5 attn[M,d] 6 ffn[M,4d] 7 enc_out[M,d]; session: 10 x[Bp,d] 11 xn[Bp,d] 12 attn[Bp,d]
-// 13 ffn[Bp,4d] 14 logits[Bs,V] 15 cross_kv (all) 16 self_k (all) 17 self_v (all) 18 partial
-wk_status wk_debug_read(wk_model* m, wk_session* s, int32_t which, int64_t offset_elems, float* dst, int64_t n) {
-    if (!m || !dst) return WK_ERR_INVALID_ARGUMENT;
-    WK_CUDA_CHECK(cudaSetDevice(m->device));
-    Lane* ln = s ? s->lane[0] : nullptr;
-    const void* src = nullptr;
-    int dt = m->cfg.dtype;
-    switch (which) {
-        case 0: src = m->mel; dt = WK_DTYPE_F16; break;
-        case 1: src = m->h1; dt = WK_DTYPE_F16; break;
-        case 2: src = m->x; dt = WK_DTYPE_F32; break;
-        case 3: src = m->xn; break;
-        case 4: src = m->qkv; break;
-        case 5: src = m->attn; break;
-        case 6: src = m->ffn; break;
-        case 7: src = m->enc_out; break;
-        case 10: src = ln ? ln->x : nullptr; dt = WK_DTYPE_F32; break;
-        case 11: src = ln ? ln->xn : nullptr; break;
-        case 12: src = ln ? ln->attn : nullptr; break;
-        case 13: src = ln ? ln->ffn : nullptr; break;
-        case 14: src = ln ? ln->logits : nullptr; dt = WK_DTYPE_F32; break;
-        case 15: src = ln ? ln->cross_kv : nullptr; break;
-        case 16: src = ln ? ln->self_k : nullptr; break;
-        case 17: src = ln ? ln->self_v : nullptr; break;
-        case 18: src = ln ? ln->partial : nullptr; dt = WK_DTYPE_F32; break;
-        case 20: src = m->enc[0].wqkv; break;
-        case 21: src = m->emb; break;
-        case 22: src = m->enc[0].w1; break;
-        case 23: src = m->wckv; break;
-        case 24: src = m->enc[0].b1; dt = WK_DTYPE_F32; break;
-        case 25: src = m->enc[0].bqkv; dt = WK_DTYPE_F32; break;
-        default: break;
-    }
-    if (!src) { set_error("wk_debug_read: unknown buffer %d", which); return WK_ERR_INVALID_ARGUMENT; }
-    float* tmp = nullptr;
-    WK_CUDA_CHECK(cudaMalloc(&tmp, n * 4));
-    WK_CUDA_CHECK(cudaStreamSynchronize(m->stream));
-    wk_status r = convert_to_16((const char*)src + offset_elems * esize(dt), dt, tmp, WK_DTYPE_F32, n, m->stream);
-    if (r == WK_OK) {
-        cudaError_t e = cudaMemcpyAsync(dst, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
-        if (e != cudaSuccess) { set_error("wk_debug_read: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
-    }
-    cudaFree(tmp);
-    return r;
-}
-
 wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, int32_t T, int32_t n_heads, int32_t dtype) {
     if (!m) return WK_ERR_INVALID_ARGUMENT;
     WK_CUDA_CHECK(cudaSetDevice(m->device));
-    return encoder_attention(qkv, out, B, T, n_heads, dtype, m->stream);
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    WK_CHECK(encoder_attention(qkv, out, B, T, n_heads, dtype, m->stream));
+    WK_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return WK_OK;
+}
+
+// decoder_cross_attention_kernel alone: q [B][H*64] f32 (the un-reduced query, bias included), K/V [B][H][T][64] 16-bit -> out [B][H*64]
+wk_status wk_test_cross_attention(wk_model* m, const float* q, const void* kcross, const void* vcross, void* out, int32_t B, int32_t H,
+                                  int32_t T, int32_t dtype, const int32_t* done) {
+    if (!m || !q || !kcross || !vcross || !out || B < 1 || H < 1 || H > 32) { set_error("wk_test_cross_attention: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    float* zero = nullptr;
+    WK_CHECK(dmalloc(&zero, (size_t)H * 64));
+    wk_status r = decoder_cross_attention(q, 1, B, zero, kcross, vcross, out, B, H, T, dtype, m->stream, done);
+    cudaError_t e = cudaStreamSynchronize(m->stream);
+    cudaFree(zero);
+    if (r == WK_OK && e != cudaSuccess) { set_error("wk_test_cross_attention: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
+    return r;
+}
+
+// decoder_self_attention_kernel alone: qkv [B][3*H*64] f32 (q | k | v of the new token, biases included), caches [B][H][224][64] 16-bit
+// holding positions < pos[b]; appends the new K/V row at pos[b] and writes out [B][H*64]
+wk_status wk_test_self_attention(wk_model* m, const float* qkv, void* kcache, void* vcache, const int32_t* pos, void* out, int32_t B,
+                                 int32_t H, int32_t dtype, const int32_t* done) {
+    if (!m || !qkv || !kcache || !vcache || !pos || !out || B < 1 || H < 1) { set_error("wk_test_self_attention: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    float* zero = nullptr;
+    WK_CHECK(dmalloc(&zero, (size_t)H * 64));
+    wk_status r = decoder_self_attention(qkv, 1, B, zero, zero, kcache, vcache, pos, done, out, B, H, kKvMaxLen, dtype, m->stream);
+    cudaError_t e = cudaStreamSynchronize(m->stream);
+    cudaFree(zero);
+    if (r == WK_OK && e != cudaSuccess) { set_error("wk_test_self_attention: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
+    return r;
 }
 
 }  // extern "C"

@@ -1,6 +1,4 @@
-// fused_chain.cu - EXPERIMENTAL, opt-in (WKB200_FUSED=1), written at the end of round 1 and NOT yet validated on a GPU.
-//
-// One persistent kernel runs a CHAIN of decoder phases that today are separate launches:
+// fused_chain.cu - decoder phase chains: one persistent kernel runs a CHAIN of decoder phases that today are separate launches:
 //     swap-AB split-K GEMM -> split-K reduce (+bias +residual +LayerNorm | +bias +GELU) -> GEMM -> ...
 // with a grid-wide barrier between phases instead of a kernel boundary.  Motivation (profiles/r01_summary.md section 6): a decoder GEMM
 // launch is ~5.2 us of fixed cost around ~0.9 us of weight streaming, 11 such launches per layer; inside one kernel TMEM, mbarriers and
@@ -56,6 +54,7 @@ struct ChainK {
     uint32_t idesc;
     int stages, stage_b_bytes, tmem_cols, acc_stride;
     unsigned int* counters;
+    unsigned int* reset;
 };
 struct ChainMaps {
     CUtensorMap a[kChainMaxGemms];
@@ -77,7 +76,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n_c
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
-        while (ld_acquire_gpu(ctr) < n_ctas) __nanosleep(32);
+        if (ld_acquire_gpu(ctr) < n_ctas) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned int spins = 0;
+            while (ld_acquire_gpu(ctr) < n_ctas) {
+                __nanosleep(20);
+                if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > kSpinLimitNs) {
+                    printf("wkb200: grid barrier timed out (block %d: %u of %u CTAs arrived)\n", (int)blockIdx.x, ld_acquire_gpu(ctr), n_ctas);
+                    __trap();
+                }
+            }
+        }
         __threadfence();
     }
     __syncthreads();
@@ -218,7 +227,7 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
         if (!work_of(P, &tile, &split)) return;
         const int n_pre = P.kb_per_split < p.stages ? P.kb_per_split : p.stages;
         for (int i = 0; i < n_pre; ++i) {
-            mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
+            mbar_wait_bounded(&empty_bar[p_stage], p_phase ^ 1);
             uint8_t* sa = smem + (size_t)p_stage * stage_bytes;
             mbar_expect_tx(&full_bar[p_stage], (uint32_t)stage_bytes);
             tma_load_2d(sa, &maps.a[P.map], &full_bar[p_stage], (split * P.kb_per_split + i) * kK, tile * kM);
@@ -230,6 +239,9 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
     // the first phase is always a GEMM: its weights go out before griddepcontrol.wait, everything else after
     if (warp == 0 && lane == 0 && p.ph[0].kind == 0) prefetch_weights(0);
     pdl_wait();
+    // every kernel upstream of this one has completed: the barrier words of the sibling chain (last used before this launch) can be
+    // re-armed here, which keeps memset nodes out of the step graph
+    if (blockIdx.x == 0 && threadIdx.x < 8 && p.reset != nullptr) p.reset[threadIdx.x] = 0u;
 
     for (int ph = 0; ph < p.n_phases; ++ph) {
         const PhaseK& P = p.ph[ph];
@@ -246,7 +258,7 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
                         tma_load_2d(smem + (size_t)st * stage_bytes + kStageABytes, &maps.b[P.map], &full_bar[st], (kb0 + i) * kK, 0);
                     }
                     for (int kb = kb0 + pre_n; kb < kb0 + P.kb_per_split; ++kb) {
-                        mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
+                        mbar_wait_bounded(&empty_bar[p_stage], p_phase ^ 1);
                         uint8_t* sa = smem + (size_t)p_stage * stage_bytes;
                         mbar_expect_tx(&full_bar[p_stage], (uint32_t)stage_bytes);
                         tma_load_2d(sa, &maps.a[P.map], &full_bar[p_stage], kb * kK, tile * kM);
@@ -259,11 +271,11 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
                 // ===================== MMA issuer =====================
                 const int acc = acc_it & 1;
                 const uint32_t acc_phase = (acc_it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait_bounded(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
                 for (int kb = 0; kb < P.kb_per_split; ++kb) {
-                    mbar_wait(&full_bar[m_stage], m_phase);
+                    mbar_wait_bounded(&full_bar[m_stage], m_phase);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + (size_t)m_stage * stage_bytes);
@@ -285,7 +297,7 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
                 const uint32_t acc_phase = (acc_it >> 1) & 1;
                 const int row = tile * kM + quarter * 32 + lane;
                 const bool row_ok = row < P.n;
-                mbar_wait(&tfull_bar[acc], acc_phase);
+                mbar_wait_bounded(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(quarter * 32) << 16);
                 for (int c = csub * 32; c < p.Bp; c += 64) {
@@ -334,7 +346,7 @@ wk_status decoder_chain(const ChainDesc& c, int num_sms, cudaStream_t stream) {
     ChainK p;
     memset(&maps, 0, sizeof(maps));
     memset(&p, 0, sizeof(p));
-    p.n_phases = c.n_phases; p.partial = c.partial; p.x = c.x; p.B = c.B; p.Bp = c.Bp; p.d = c.d; p.counters = c.counters;
+    p.n_phases = c.n_phases; p.partial = c.partial; p.x = c.x; p.B = c.B; p.Bp = c.Bp; p.d = c.d; p.counters = c.counters; p.reset = c.reset_counters;
     p.idesc = 0;
     {
         const uint32_t fmt = c.dtype == WK_DTYPE_F16 ? 0u : 1u;

@@ -52,7 +52,6 @@ struct GemmKParams {
     const float* pos;
     long long ld_pos;
     int heads_T, heads_B, heads_H, heads_dmodel;
-    int debug_mode;   // 0 normal; 1 exit after setup; 2 skip the epilogue stores (latency decomposition, WKB200_GEMM_DEBUG)
     int tmem_cols;
     int a_static;     // see GemmDesc::a_static
 };
@@ -99,14 +98,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     // upstream results visible from here on (barrier init / TMEM alloc overlapped its tail).  With a static A operand the producer warp
     // waits later, after it has put the first weight tiles in flight; every other warp only sees data that arrived after that wait.
-    const bool early_a = p.a_static != 0 && p.debug_mode == 0;
+    const bool early_a = p.a_static != 0;
     if (!(early_a && warp == 0)) pdl_wait();
 
-    if (p.debug_mode == 1) {
-        __syncthreads();
-        if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-        return;
-    }
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -214,7 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld_wait();
                 const int col0 = col_base + c;
                 if (p.mode == GEMM_OUT_PARTIAL_T) {
-                    if (row_ok && p.debug_mode != 2) {
+                    if (row_ok) {
                         float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -402,16 +396,11 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
     if (stages > total_kb / p.splits + 2) stages = total_kb / p.splits + 2;
     if (stages < 2) stages = 2;
     if (d.max_stages > 0 && stages > d.max_stages) stages = d.max_stages;
-    if (const char* e = getenv("WKB200_GEMM_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     p.stages = stages;
-    p.debug_mode = 0;
-    if (const char* e = getenv("WKB200_GEMM_DEBUG")) p.debug_mode = atoi(e);
     // TMEM: two accumulator stages of kAccStride columns when a CTA may run several tiles, else the smallest power of two >= BN
     p.tmem_cols = kTmemCols;
     if (p.work <= num_sms) { int c = 32; while (c < d.bn) c <<= 1; p.tmem_cols = c; }
-    if (const char* e = getenv("WKB200_GEMM_TMEM")) p.tmem_cols = atoi(e);
-    static const bool early_a_off = getenv("WKB200_EARLY_A") && atoi(getenv("WKB200_EARLY_A")) == 0;   // A/B knob
-    p.a_static = early_a_off ? 0 : d.a_static;
+    p.a_static = d.a_static;
     p.mode = d.mode;
     p.gelu = d.gelu;
     p.out = d.out;
@@ -471,53 +460,6 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
         set_error("gemm_tcgen05 launch: %s", cudaGetErrorString(e));
         return WK_ERR_CUDA;
     }
-    return WK_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// CUDA-core reference used only by tests to validate the tcgen05 path on the device.
-template <typename T, typename O>
-__global__ void gemm_simt_kernel(const T* __restrict__ a, const T* __restrict__ w, const float* __restrict__ bias,
-                                 O* __restrict__ out, int M, int N, int K, int gelu) {
-    __shared__ float sa[16][17];
-    __shared__ float sw[16][17];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        const int ar = blockIdx.y * 16 + ty, wr = blockIdx.x * 16 + ty;
-        sa[ty][tx] = (ar < M && k0 + tx < K) ? T16<T>::to_f(a[(long long)ar * K + k0 + tx]) : 0.f;
-        sw[ty][tx] = (wr < N && k0 + tx < K) ? T16<T>::to_f(w[(long long)wr * K + k0 + tx]) : 0.f;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sw[tx][k];
-        __syncthreads();
-    }
-    if (row < M && col < N) {
-        if (bias) acc += bias[col];
-        if (gelu) acc = gelu_erf(acc);
-        if constexpr (sizeof(O) == 4) out[(long long)row * N + col] = acc;
-        else out[(long long)row * N + col] = T16<O>::from_f(acc);
-    }
-}
-
-wk_status gemm_simt_reference(const void* a, const void* w, const float* bias, void* out, int M, int N, int K, int in_dtype,
-                              int out_dtype, int gelu, cudaStream_t stream) {
-    dim3 block(16, 16), grid((N + 15) / 16, (M + 15) / 16);
-    if (in_dtype == WK_DTYPE_BF16) {
-        if (out_dtype == WK_DTYPE_F32)
-            gemm_simt_kernel<__nv_bfloat16, float><<<grid, block, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias, (float*)out, M, N, K, gelu);
-        else
-            gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, M, N, K, gelu);
-    } else {
-        if (out_dtype == WK_DTYPE_F32)
-            gemm_simt_kernel<__half, float><<<grid, block, 0, stream>>>((const __half*)a, (const __half*)w, bias, (float*)out, M, N, K, gelu);
-        else
-            gemm_simt_kernel<__half, __half><<<grid, block, 0, stream>>>((const __half*)a, (const __half*)w, bias, (__half*)out, M, N, K, gelu);
-    }
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("gemm_simt launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     return WK_OK;
 }
 

@@ -9,6 +9,7 @@
 namespace wk {
 
 void set_error(const char* fmt, ...);
+const char* last_error_cstr();
 void count_launch(int n = 1);
 
 // ---------------------------------------------------------------- GEMM (gemm_tcgen05.cu)
@@ -63,9 +64,6 @@ struct GemmDesc {
 };
 
 wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream);
-// plain CUDA-core reference for tests (same semantics, mode OUT_T16/OUT_F32 only)
-wk_status gemm_simt_reference(const void* a, const void* w, const float* bias, void* out, int M, int N, int K, int in_dtype,
-                              int out_dtype, int gelu, cudaStream_t stream);
 
 // ---------------------------------------------------------------- mel (mel.cu)
 struct MelTables;  // device tables (window, twiddles, sparse filterbank)
@@ -84,7 +82,7 @@ wk_status layernorm_f32_to_16(const float* x, const float* gamma, const float* b
 wk_status layernorm_f32_to_f32(const float* x, const float* gamma, const float* beta, float* out, int64_t rows, int d,
                                cudaStream_t stream);
 wk_status encoder_attention(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream);
-// tcgen05/TMA implementation (attention_tcgen05.cu); encoder_attention() dispatches to it unless WKB200_ATTN=legacy
+// tcgen05/TMA implementation (attention_tcgen05.cu) behind encoder_attention()
 wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream);
 wk_status transpose_to_host_layout(const void* src, float* dst, int64_t B, int64_t rows, int64_t cols, int64_t src_rows_alloc,
                                    int64_t src_row_off, int64_t src_ld, int dtype, cudaStream_t stream);
@@ -93,65 +91,81 @@ wk_status fill_random_f32(float* dst, int64_t n, uint64_t seed, float std, float
 wk_status convert_to_16(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, cudaStream_t stream);
 
 // ---------------------------------------------------------------- decoder ops (decoder_ops.cu)
+// Per-row decode options, device-resident: what differs between the items of transcribeWithOptions' decodeOptionsArray
+// (WhisperKit.swift:716-735) and between the rungs of the temperature ladder (TranscribeTask.swift:316-411).
+struct RowParams {
+    int32_t prompt_len;          // initialPrompt.count
+    int32_t sample_begin_ts;     // TimestampRulesFilter.sampleBegin, <0 = filter absent
+    int32_t sample_begin_blank;  // SuppressBlankFilter.sampleBegin, <0 = absent
+    int32_t max_steps;           // min(sampleLength, 223): loop bound (TextDecoder.swift:566)
+    float temperature; int32_t top_k;
+    int32_t has_first_thr; float first_thr;
+    uint64_t seed;
+    int32_t suppress_off, n_suppress;   // slice of the session's suppress-token pool
+    int32_t pad_[2];
+};
+
 struct DecodeState {
-    // all device pointers; B = bound batch, Bp = padded batch (multiple of 16)
+    // all device pointers; one entry per decode row (slot).  A slot with done != 0 is skipped by every kernel of the step.
     int32_t* tokens;      // [Bmax, 224] currentTokens
     int32_t* n_tokens;    // [Bmax]
     float* logprobs;      // [Bmax, 224]
     int32_t* next_token;  // [Bmax]
     int32_t* done;        // [Bmax]
     int32_t* first_low;   // [Bmax]
-    int32_t* steps;       // [Bmax] forward passes consumed
-    int32_t* step;        // [1] tokenIndex of the step about to run
-    int32_t* n_done;      // [1]
+    int32_t* steps;       // [Bmax] forward passes consumed = tokenIndex of the step about to run = KV-cache position
     int32_t* input_ids;   // [Bmax] token fed at this step (written by embed)
+    int32_t* error;       // [Bmax] 1 = the sampler saw no finite logit (WhisperError.decodingLogitsFailed)
+    const RowParams* rp;  // [Bmax]
 };
 
 struct SamplerParams {
     wk_special_tokens st;
     int vocab;
     int is_multilingual;
-    int sample_begin_ts;     // TimestampRulesFilter.sampleBegin, <0 = filter absent
-    int sample_begin_blank;  // SuppressBlankFilter.sampleBegin, <0 = absent
-    const int32_t* suppress; int n_suppress;
+    int loop_mode;           // 1: decode loop (per-row options from DecodeState.rp); 0: stateless (wk_filter_sample / detectLanguage)
+    const int32_t* suppress; // loop mode: the pool RowParams.suppress_off indexes; stateless: the list itself
     const int32_t* language_tokens; int n_language_tokens; int language_sample_begin;
-    float temperature; int top_k; uint64_t seed;
-    int has_first_thr; float first_thr;
-    int prompt_len;          // initialPrompt.count (decode loop) ; <0 = stateless (wk_filter_sample)
     int max_ctx;             // 224
+    // stateless mode only
+    int sample_begin_ts, sample_begin_blank, n_suppress;
+    float temperature; int top_k; uint64_t seed;
 };
 
-wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gamma, const float* beta, DecodeState st,
-                           int prompt_len, int ts_begin, float* x, void* xn, int B, int d, int dtype, int explicit_inputs,
-                           const int32_t* explicit_pos, cudaStream_t stream);
+// pos: explicit per-row positions (wk_decode_step) or nullptr = DecodeState.steps
+wk_status decoder_embed_ln(const void* emb16, const float* pos, const float* gamma, const float* beta, DecodeState st, int vocab,
+                           int ts_begin, float* x, void* xn, int B, int d, int dtype, const int32_t* explicit_pos, cudaStream_t stream);
 // x[b,:] += bias + sum_s partial[s][b][:]; xn = LN(x) (16-bit).  partial layout [S][Bp][d]
 wk_status decoder_reduce_resid_ln(const float* partial, int splits, int Bp, const float* bias, const float* gamma,
                                   const float* beta, float* x, void* xn, int B, int d, int dtype, cudaStream_t stream);
 // h = gelu(bias + sum partial) 16-bit [B, n]
 wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, const float* bias, void* out, int B, int n,
                                    int dtype, cudaStream_t stream);
-// self attention for one new token per sequence; reduces qkv partials [S][Bp][3d], appends K/V at pos
+// self attention for one new token per sequence; reduces qkv partials [S][Bp][3d], appends K/V at pos[b].  done != nullptr: rows with
+// done[b] != 0 are skipped (their window has ended: no cache traffic)
 wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
-                                 void* vcache, const int32_t* step, const int32_t* explicit_pos, void* out, int B, int H,
+                                 void* vcache, const int32_t* pos, const int32_t* done, void* out, int B, int H,
                                  int max_len, int dtype, cudaStream_t stream);
 // cross attention over T encoder positions; reduces q partials [S][Bp][d]; K/V [B][H][T][64]
 // align_scratch != nullptr: heads h with bit h of align_mask set also write their softmax row (f32, [slot][B][T], slot = rank of h in
 // the mask) - the alignment heads behind the reference decoder's `alignment_heads_weights` output (TextDecoder.swift:310,414)
 wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
                                   const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
-                                  float* align_scratch = nullptr, uint32_t align_mask = 0);
-// alignment row of the step just sampled (run AFTER the sampler advanced *step to tokenIndex + 1): out[b][*step][t] =
+                                  const int32_t* done = nullptr, float* align_scratch = nullptr, uint32_t align_mask = 0);
+// alignment row of the step just sampled (run AFTER the sampler advanced steps[b] to tokenIndex + 1): out[b][steps[b]][t] =
 // Float16(mean over n_slots of scratch[slot][b][t]) unless done[b] (TextDecoder.updateAlignmentWeights, TextDecoder.swift:272-296:
 // the slice of step tokenIndex lands in row tokenIndex + 1; a completed segment breaks out before the update, :668-674)
-wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* step, const int32_t* done, void* out_f16, int B, int T,
+wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* steps, const int32_t* done, void* out_f16, int B, int T,
                              int max_rows, cudaStream_t stream);
 wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,
                                 int ld_tokens, const int32_t* n_tokens, int32_t* token_out, float* logprob_out,
                                 float* filtered_out, int B, cudaStream_t stream);
-wk_status decode_state_init(DecodeState st, const int32_t* prompt_dev, int n_prompt, int B, cudaStream_t stream);
+// (re)starts the decode of n slots: slot_ids[i] gets prompt row i of prompts [n][224] (length rp[i].prompt_len) and RowParams rp[i]
+wk_status decode_slots_init(DecodeState st, RowParams* rp_dev, const int32_t* slot_ids, const int32_t* prompts, const RowParams* rp_new,
+                            int n, cudaStream_t stream);
 
-// ---- experimental (WKB200_FUSED=1): a chain of decoder GEMM / split-K reduce phases in ONE persistent kernel with grid-wide barriers
-// between the phases instead of kernel boundaries.  fused_chain.cu
+// ---- a chain of decoder GEMM / split-K reduce phases in ONE persistent kernel with grid-wide barriers between the phases instead of
+// kernel boundaries (fused_chain.cu)
 wk_status make_tmap_2d(void* tm, const void* base, int dtype, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);
 constexpr int kChainMaxPhases = 7;
 constexpr int kChainMaxGemms = 4;
@@ -170,7 +184,8 @@ struct ChainDesc {
     ChainPhaseDesc ph[kChainMaxPhases];
     float* partial; float* x;  // split-K workspace, f32 residual stream [Bp][d]
     int B, Bp, d, dtype;
-    unsigned int* counters;    // n_phases - 1 words, zero before the launch
+    unsigned int* counters;    // 8 words, zero before the launch: one per phase boundary
+    unsigned int* reset_counters;  // 8 words of the sibling chain (already completed): zeroed by this launch; may be nullptr
     int pdl;
 };
 wk_status decoder_chain(const ChainDesc& c, int num_sms, cudaStream_t stream);

@@ -269,8 +269,11 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
     for (int i = 0; i < n_streams; ++i) {
         if (n_samples[i] < 0 || (n_samples[i] > 0 && !audio[i])) { set_error("wk_transcribe_streams: stream %d invalid", i); return WK_ERR_AUDIO_PROCESSING_FAILED; }
         std::vector<int64_t> chunks;
-        if (chunking_vad) {
-            // WhisperKit.transcribe(audioArray:) with chunkingStrategy .vad (WhisperKit.swift:878-911): EnergyVAD defaults
+        // WhisperKit.transcribe(audioArray:) takes the VAD route only for (isChunkable, .vad) with isChunkable = count > windowSamples
+        // (WhisperKit.swift:876-878); shorter audio goes to runTranscribeTask with the caller's options, clipTimestamps included (:912-919)
+        const bool vad_stream = chunking_vad && n_samples[i] > kWindow;
+        if (vad_stream) {
+            // chunkingStrategy .vad (WhisperKit.swift:878-911): EnergyVAD defaults
             rc = chunk_all(audio[i], n_samples[i], kWindow, cts, n_cts, kSampleRate, 1600, 0, 0.02f, chunks);
             if (rc != WK_OK) return rc;
         } else {
@@ -282,7 +285,7 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
             // chunks are transcribed as whole arrays (clip timestamps were consumed by the chunker); plain streams use them directly
             u.clips.resize(2 * (n_cts / 2 + 2));
             int nc = 0;
-            rc = wk_prepare_seek_clips(chunking_vad ? nullptr : cts, chunking_vad ? 0 : n_cts, u.n, u.clips.data(), (int)u.clips.size() / 2, &nc);
+            rc = wk_prepare_seek_clips(vad_stream ? nullptr : cts, vad_stream ? 0 : n_cts, u.n, u.clips.data(), (int)u.clips.size() / 2, &nc);
             if (rc != WK_OK) return rc;
             u.clips.resize(2 * nc);
             // a clip is live while seek < clipEnd - windowPadding (TranscribeTask.swift:118) and, as a guard the reference lacks (it would

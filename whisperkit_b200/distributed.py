@@ -21,25 +21,40 @@ def shard_bounds(n_windows: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def scatter_windows(all_pcm: Optional[torch.Tensor], n_windows: int, stride: int, device, src: int = 0) -> torch.Tensor:
-    """rank `src` holds all_pcm [n_windows, stride] on `device`; every rank returns its contiguous shard."""
+    """rank `src` holds all_pcm [n_windows, stride] (pinned host memory or already on `device`); every rank returns its contiguous shard
+    on `device`.  Point-to-point sends (NCCL: ncclSend / ncclRecv over NVLink), no padded copies: rank `src` stages and sends the other
+    ranks' shards in rank order - the copy of shard r + 1 from the host runs while shard r is on the wire - and takes its own shard last."""
     world, rank = dist.get_world_size(), dist.get_rank()
     lo, hi = shard_bounds(n_windows, world, rank)
-    per = max(shard_bounds(n_windows, world, r)[1] - shard_bounds(n_windows, world, r)[0] for r in range(world))
-    out = torch.empty(per, stride, dtype=torch.float32, device=device)
-    chunks = None
-    if rank == src:
-        chunks = []
-        for r in range(world):
-            a, b = shard_bounds(n_windows, world, r)
-            c = torch.zeros(per, stride, dtype=torch.float32, device=device)
-            c[: b - a] = all_pcm[a:b]
-            chunks.append(c)
-    dist.scatter(out, chunks, src=src)
-    return out[: hi - lo]
+    if rank != src:
+        out = torch.empty(hi - lo, stride, dtype=torch.float32, device=device)
+        if hi > lo:
+            dist.recv(out, src=src)
+        return out
+    keep = []
+    for r in range(world):
+        if r == src:
+            continue
+        a, b = shard_bounds(n_windows, world, r)
+        if b > a:
+            part = all_pcm[a:b].to(device, non_blocking=True)
+            keep.append(part)      # stays alive until the send has been enqueued behind the copy
+            dist.send(part, dst=r)
+    return all_pcm[lo:hi].to(device, non_blocking=True)
 
 
 def pack_tokens(results, device) -> torch.Tensor:
-    """results: list of objects with .tokens -> int32 [n, TOKEN_ROW] (row = [count, ids...])."""
+    """results -> int32 [n, TOKEN_ROW] (row = [count, ids...]).  `results` is a ctypes array of wk_decode_result (its first 227 words are
+    exactly that row) or a list of objects with .tokens."""
+    import ctypes
+    import numpy as np
+    if isinstance(results, ctypes.Array):
+        n = len(results)
+        words = ctypes.sizeof(results) // 4 // max(n, 1)
+        flat = np.frombuffer(results, dtype=np.int32).reshape(n, words)
+        t = torch.zeros(n, TOKEN_ROW, dtype=torch.int32)
+        t[:, :227] = torch.from_numpy(flat[:, :227].copy())
+        return t.to(device)
     t = torch.zeros(len(results), TOKEN_ROW, dtype=torch.int32)
     for i, r in enumerate(results):
         toks = list(r.tokens)[: TOKEN_ROW - 2]
@@ -49,31 +64,52 @@ def pack_tokens(results, device) -> torch.Tensor:
 
 
 def gather_tokens(local: torch.Tensor, n_windows: int, dst: int = 0) -> Optional[List[List[int]]]:
-    """Gathers per-rank packed token rows on `dst`, restoring the global window order."""
+    """Gathers per-rank packed token rows on `dst` (ncclSend / ncclRecv straight into the rows of one buffer), restoring the global
+    window order."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    per = max(shard_bounds(n_windows, world, r)[1] - shard_bounds(n_windows, world, r)[0] for r in range(world))
-    pad = torch.zeros(per, TOKEN_ROW, dtype=torch.int32, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst)
     if rank != dst:
+        if local.shape[0] > 0:
+            dist.send(local.contiguous(), dst=dst)
         return None
-    out: List[List[int]] = []
+    buf = torch.empty(n_windows, TOKEN_ROW, dtype=torch.int32, device=local.device)
     for r in range(world):
         a, b = shard_bounds(n_windows, world, r)
-        rows = bufs[r][: b - a].cpu()
-        for row in rows:
-            n = int(row[0])
-            out.append([int(v) for v in row[1:1 + n]])
-    return out
+        if b <= a:
+            continue
+        if r == dst:
+            buf[a:b] = local
+        else:
+            dist.recv(buf[a:b], src=r)
+    rows = buf.cpu().numpy()
+    return [row[1:1 + int(row[0])].tolist() for row in rows]
 
 
 def transcribe_sharded(all_pcm: Optional[torch.Tensor], n_windows: int, stride: int, device,
-                       transcribe_local: Callable[[torch.Tensor], list]) -> Optional[List[List[int]]]:
-    """scatter -> per-rank transcribe -> gather.  `transcribe_local(pcm_shard)` returns one result per window."""
+                       transcribe_local: Callable[[torch.Tensor], list], stages: Optional[dict] = None) -> Optional[List[List[int]]]:
+    """scatter -> per-rank transcribe -> gather.  `transcribe_local(pcm_shard)` returns one result per window.  `stages` (a dict)
+    accumulates this rank's wall-clock milliseconds per stage - scatter (host-to-device copies + sends), compute, pack, gather (+ unpack
+    on the destination) - so a bench can show where the end-to-end time of rank 0 goes."""
+    import time
+
+    def mark(name, t0):
+        if stages is not None:
+            if device.type == "cuda":
+                torch.cuda.synchronize(device)
+            stages[name] = stages.get(name, 0.0) + (time.perf_counter() - t0) * 1000.0
+        return time.perf_counter()
+
+    t = time.perf_counter()
     shard = scatter_windows(all_pcm, n_windows, stride, device)
+    t = mark("scatter", t)
     res = transcribe_local(shard)
-    return gather_tokens(pack_tokens(res, device), n_windows)
+    t = mark("compute", t)
+    packed = pack_tokens(res, device)
+    t = mark("pack", t)
+    out = gather_tokens(packed, n_windows)
+    mark("gather_unpack", t)
+    if stages is not None:
+        stages["_calls"] = stages.get("_calls", 0) + 1
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------

@@ -144,7 +144,7 @@ def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional
                        chunkingStrategy: Optional[str] = None, split_to_word_tokens=None, decode=None):
     """TranscribeTask.run's seek loop for many audio arrays at once (TranscribeTask.swift:98-279; `chunkingStrategy="vad"`
     = WhisperKit.swift:878-911).  Returns (segments per stream, number of 30 s windows decoded)."""
-    opts = options or DecodingOptions()
+    opts = kit.resolveLanguage(options or DecodingOptions())   # DecodingOptions.language -> <|xx|> through the tokenizer
     lib = kit.model.lib
     arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in audioArrays]
     ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
