@@ -5,7 +5,7 @@ out=gpurun_out/${1:-stage}
 mkdir -p $out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $out/gpu.txt 2>&1
-(time WKB200_FUSED=0 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 -s) > $out/pytest_unfused.log 2>&1
+(time WKB200_FUSED=0 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -s) > $out/pytest_unfused.log 2>&1
 echo "unfused rc $?" >> $out/summary.txt
 (time timeout 600 python tools/fused_check.py) > $out/fused_check.log 2>&1
 rc=$?
@@ -20,3 +20,5 @@ WKB200_FUSED=0 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baselin
 echo "bench unfused rc $?" >> $out/summary.txt
 cat $out/summary.txt
 tail -5 $out/pytest_unfused.log
+timeout 300 python tools/microbench_cold.py 64 > $out/microbench.log 2>&1
+tail -12 $out/microbench.log
