@@ -377,6 +377,13 @@ int32_t wk_tokenizer_split_to_word_tokens(const wk_tokenizer* t, const int32_t* 
 /* Fills `hooks` with this tokenizer's split / decode so wk_transcribe_streams and wk_add_word_timestamps run without host callbacks. */
 wk_status wk_tokenizer_hooks_init(wk_tokenizer* t, wk_tokenizer_hooks* hooks);
 
+/* ---- result writers (Sources/WhisperKit/Utilities/ResultWriter.swift) ----
+ * Cues are flat: one per word where the segment has word timings, else one per segment (the order WriteSRT / WriteVTT iterate).
+ * Each function writes NUL-terminated UTF-8 into out and returns the byte count (without NUL), or -(bytes needed) if cap is short. */
+int32_t wk_format_time(float seconds, int32_t always_include_hours, const char* decimal_marker, char* out, int32_t cap);   /* ResultWriting.formatTime, :14-26 */
+int32_t wk_write_srt(const float* starts, const float* ends, const char* const* texts, int32_t n, char* out, int32_t cap);   /* WriteSRT, :70-101 */
+int32_t wk_write_vtt(const float* starts, const float* ends, const char* const* texts, int32_t n, char* out, int32_t cap);   /* WriteVTT, :103-134 */
+
 /* ---- instrumentation ---- */
 /* Number of kernels launched by this library on the calling process since the last reset. */
 int64_t wk_kernel_launch_count(int32_t reset);

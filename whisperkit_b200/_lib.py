@@ -187,6 +187,9 @@ SYMBOLS = [
     ("wk_tokenizer_special_tokens", I32, [P, C.POINTER(wk_special_tokens)]),
     ("wk_tokenizer_split_to_word_tokens", I32, [P, PI32, I32, C.POINTER(C.c_char), I32, PI32, I32]),
     ("wk_tokenizer_hooks_init", I32, [P, C.POINTER(wk_tokenizer_hooks)]),
+    ("wk_format_time", I32, [F32, I32, C.c_char_p, C.POINTER(C.c_char), I32]),
+    ("wk_write_srt", I32, [PF32, PF32, C.POINTER(C.c_char_p), I32, C.POINTER(C.c_char), I32]),
+    ("wk_write_vtt", I32, [PF32, PF32, C.POINTER(C.c_char_p), I32, C.POINTER(C.c_char), I32]),
     ("wk_kernel_launch_count", I64, [I32]),
     ("wk_last_timings", I32, [P, PF32]),
     ("wk_model_stream", P, [P]),
