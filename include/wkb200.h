@@ -118,6 +118,13 @@ typedef struct wk_decode_opts {
     int32_t temperature_fallback_count;        /* default 5; 0 = no retries */
     float temperature_increment_on_fallback;   /* default 0.2 */
     int32_t word_timestamps;      /* wordTimestamps: the decode loop also fills the alignmentWeights tensor (wk_session_alignment_weights) */
+    /* Beam search.  The reference's BeamSearchTokenSampler is an unimplemented stub (TokenSampler.swift:254-290) and its
+     * DecodingOptions has no beam field, so these two are an extension: beam_size > 1 decodes every window with that many beams
+     * (openai/whisper BeamSearchDecoder semantics inside the decodeText loop, specified by oracle/beam_ref.py; self-oracle parity only),
+     * maxCandidates = Int(Float(beam_size) * beam_patience) as the stub fixes (:266).  One setting per call; the temperature ladder and
+     * word timestamps do not combine with it. */
+    int32_t beam_size;            /* <= 1: greedy / temperature sampling (default) */
+    float beam_patience;          /* default 1 */
 } wk_decode_opts;
 
 /* Per-window DecodingResult (Models.swift:383-439) in flat arrays; tokens = SOT..EOT slice. */
@@ -242,6 +249,25 @@ wk_status wk_decode_text_ex(wk_session* s, const wk_special_tokens* st, const wk
 wk_status wk_transcribe_windows_ex(wk_model* m, wk_session* s, const float* pcm_host, int64_t n_windows, int64_t stride,
                                    const int32_t* samples_per_window, const wk_special_tokens* st, const wk_batch_opts* bo,
                                    wk_decode_result* results);
+
+/* ---- multi-GPU edges: one process per GPU, windows sharded, weights replicated; NCCL only moves PCM out and
+ * results back (grouped ncclSend / ncclRecv over NVLink).  NCCL is resolved at run time from the process; wk_comm_unique_id fails with
+ * WK_ERR_MODELS_UNAVAILABLE if it is not there.  The 128-byte id from rank 0 reaches the other ranks by whatever the host uses for
+ * rendezvous (torch.distributed in bench.py, MPI, a file). */
+typedef struct wk_comm wk_comm;
+void wk_comm_shard_bounds(int64_t n_windows, int32_t world, int32_t rank, int64_t* lo, int64_t* hi);   /* contiguous, order preserving */
+wk_status wk_comm_unique_id(uint8_t* out128);
+wk_status wk_comm_create(const uint8_t* id128, int32_t rank, int32_t world, int32_t device, wk_comm** out);
+void wk_comm_free(wk_comm* c);
+/* root holds all_pcm [n_windows][stride] (host or device); every rank receives its shard into shard_dev (device). */
+wk_status wk_comm_scatter_windows(wk_comm* c, const float* all_pcm, int64_t n_windows, int64_t stride, int32_t root, float* shard_dev, int64_t* n_local);
+/* every rank hands in the results of its shard; root receives all n_windows in window order. */
+wk_status wk_comm_gather_results(wk_comm* c, const wk_decode_result* local, int64_t n_local, int64_t n_windows, int32_t root, wk_decode_result* all);
+/* scatter -> wk_transcribe_windows_ex on the shard -> gather; bo must carry shared options (n_opts == 1, no per-window arrays). */
+wk_status wk_transcribe_windows_sharded(wk_comm* c, wk_model* m, wk_session* s, const float* all_pcm, int64_t n_windows, int64_t stride, int32_t root,
+                                        const wk_special_tokens* st, const wk_batch_opts* bo, wk_decode_result* results);
+/* host wall-clock milliseconds of the last sharded call on this rank: [0] scatter [1] transcribe [2] gather [3] total */
+wk_status wk_comm_last_stage_ms(const wk_comm* c, float* ms4);
 
 /* ---- long-form windowing: host logic, callable without a GPU ---- */
 typedef struct wk_tokenizer_hooks wk_tokenizer_hooks;   /* defined with the word-timestamp API below */

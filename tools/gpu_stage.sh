@@ -11,7 +11,7 @@ echo "unfused rc $?" >> $out/summary.txt
 rc=$?
 echo "fused_check rc $rc" >> $out/summary.txt
 if [ $rc -eq 0 ]; then
-  (time timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_scheduler.py -m gpu -q --timeout 600 -s) > $out/pytest_fused.log 2>&1
+  (time timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_scheduler.py tests/test_gpu_beam.py -m gpu -q --timeout 600 -s) > $out/pytest_fused.log 2>&1
   echo "fused suite rc $?" >> $out/summary.txt
   timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_fused.json 2> $out/bench_fused.err
   echo "bench fused rc $?" >> $out/summary.txt

@@ -62,6 +62,7 @@ class wk_decode_opts(C.Structure):
         ("seed", C.c_uint64),
         ("temperature_fallback_count", C.c_int32), ("temperature_increment_on_fallback", C.c_float),
         ("word_timestamps", C.c_int32),
+        ("beam_size", C.c_int32), ("beam_patience", C.c_float),
     ]
 
 
@@ -144,6 +145,15 @@ SYMBOLS = [
                                        C.POINTER(wk_decode_result)]),
     ("wk_transcribe_windows", I32, [P, P, P, I64, I64, PI32, C.POINTER(wk_special_tokens), C.POINTER(wk_decode_opts),
                                     PI32, I32, C.POINTER(wk_decode_result)]),
+    ("wk_comm_shard_bounds", None, [I64, I32, I32, PI64, PI64]),
+    ("wk_comm_unique_id", I32, [P]),
+    ("wk_comm_create", I32, [P, I32, I32, I32, C.POINTER(P)]),
+    ("wk_comm_free", None, [P]),
+    ("wk_comm_scatter_windows", I32, [P, P, I64, I64, I32, P, PI64]),
+    ("wk_comm_gather_results", I32, [P, C.POINTER(wk_decode_result), I64, I64, I32, C.POINTER(wk_decode_result)]),
+    ("wk_transcribe_windows_sharded", I32, [P, P, P, P, I64, I64, I32, C.POINTER(wk_special_tokens), C.POINTER(wk_batch_opts),
+                                            C.POINTER(wk_decode_result)]),
+    ("wk_comm_last_stage_ms", I32, [P, PF32]),
     ("wk_find_seek_point_and_segments", I32, [PI32, PF32, I32, F32, F32, F32, F32, C.POINTER(wk_decode_opts), I32, I64, I64, I32, I32,
                                               PI64, C.POINTER(wk_segment), I32, PI32]),
     ("wk_prepare_seek_clips", I32, [PF32, I32, I64, PI64, I32, PI32]),

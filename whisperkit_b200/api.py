@@ -89,6 +89,8 @@ class DecodingOptions:
     concurrentWorkerCount: int = 16
     wordTimestamps: bool = False
     seed: int = 0
+    beamSize: int = 1                 # extension: the reference's BeamSearchTokenSampler is an unimplemented stub (TokenSampler.swift:254-290)
+    beamPatience: float = 1.0
 
     def to_c(self):
         """Returns (struct, keepalive) - keepalive holds the int arrays the struct points into."""
@@ -128,6 +130,8 @@ class DecodingOptions:
         o.temperature_fallback_count = int(self.temperatureFallbackCount)
         o.temperature_increment_on_fallback = float(self.temperatureIncrementOnFallback)
         o.word_timestamps = int(self.wordTimestamps)
+        o.beam_size = int(self.beamSize)
+        o.beam_patience = float(self.beamPatience)
         return o, keep
 
 

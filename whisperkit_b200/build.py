@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libwkb200.so")
-SOURCES = ["gemm_tcgen05.cu", "attention_tcgen05.cu", "mel.cu", "encoder_ops.cu", "decoder_ops.cu", "engine.cu", "session.cu", "longform.cu", "wordtiming.cu", "tokenizer.cu", "fused_chain.cu", "writers.cu"]
+SOURCES = ["gemm_tcgen05.cu", "attention_tcgen05.cu", "mel.cu", "encoder_ops.cu", "decoder_ops.cu", "engine.cu", "session.cu", "longform.cu", "wordtiming.cu", "tokenizer.cu", "fused_chain.cu", "writers.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",
@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-lz", "-Xlinker", "-rpath=$ORIGIN"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-lz", "-ldl", "-Xlinker", "-rpath=$ORIGIN"]
     # cudart is linked dynamically: torch ships the same major runtime; curand device headers are header-only
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -41,7 +41,7 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 // decode state
 // =====================================================================================================
 __global__ void decode_slots_init_kernel(DecodeState st, RowParams* __restrict__ rp_dev, const int32_t* __restrict__ slot_ids,
-                                         const int32_t* __restrict__ prompts, const RowParams* __restrict__ rp_new) {
+                                         const int32_t* __restrict__ prompts, const RowParams* __restrict__ rp_new, BeamState bs) {
     const int i = blockIdx.x, b = slot_ids[i];
     const RowParams R = rp_new[i];
     const int n_prompt = R.prompt_len;
@@ -58,13 +58,17 @@ __global__ void decode_slots_init_kernel(DecodeState st, RowParams* __restrict__
         st.steps[b] = 0;
         st.input_ids[b] = 0;
         st.error[b] = 0;
+        if (bs.beam > 1) {
+            bs.sum_lp[b] = 0.f;
+            if (b % bs.beam == 0) bs.n_fin[b / bs.beam] = 0;
+        }
     }
 }
 
 wk_status decode_slots_init(DecodeState st, RowParams* rp_dev, const int32_t* slot_ids, const int32_t* prompts, const RowParams* rp_new,
-                            int n, cudaStream_t stream) {
+                            int n, cudaStream_t stream, BeamState beam) {
     if (n < 1) return WK_OK;
-    decode_slots_init_kernel<<<n, 64, 0, stream>>>(st, rp_dev, slot_ids, prompts, rp_new);
+    decode_slots_init_kernel<<<n, 64, 0, stream>>>(st, rp_dev, slot_ids, prompts, rp_new, beam);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decode_slots_init launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(128)
 decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
                               const float* __restrict__ bv, T* __restrict__ kcache, T* __restrict__ vcache,
                               const int32_t* __restrict__ pos_ptr, const int32_t* __restrict__ done,
-                              T* __restrict__ out, int B, int H, int max_len) {
+                              T* __restrict__ out, int B, int H, int max_len, const int32_t* __restrict__ anc) {
     __shared__ float sq[4][64];
     __shared__ float skc[4][64];
     __shared__ float svc[4][64];
@@ -319,18 +323,21 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
     // scores: lane handles keys lane, lane+32, ...; the cache row of key i+1 is fetched while key i is reduced (double-buffered
     // registers), and the first V tile is put in flight before any of it: the kernel is latency-bound, not bandwidth-bound
     const int sub = lane & 7, rsel = lane >> 3;
-    const T* vb = vcache + (long long)bh * max_len * 64 + sub * 8;
+    // cache row of position t: this sequence's own row, or (beam search) the row of the ancestor beam that produced position t
+    const int32_t* arow = anc ? anc + (long long)b * max_len : nullptr;
+    auto row_of = [&](int t) -> long long { return ((long long)(arow ? arow[t] : b) * H + h) * max_len + t; };
+    const T* vb = vcache + sub * 8;
     uint4 u[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int t = 4 * j + rsel;
-        u[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + (long long)t * 64) : make_uint4(0u, 0u, 0u, 0u);
+        u[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + row_of(t) * 64) : make_uint4(0u, 0u, 0u, 0u);
     }
     float smax = -INFINITY;
     float sc[7];
     uint4 kbuf[2][8];
     {
-        const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)bh * max_len + lane) * 64);
+        const uint4* kp = reinterpret_cast<const uint4*>(kcache + (lane < pos ? row_of(lane) : 0) * 64);
 #pragma unroll
         for (int c = 0; c < 8; ++c) kbuf[0][c] = (lane < pos) ? kp[c] : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -339,7 +346,7 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
         const int t = lane + 32 * i;
         if (i + 1 < 7) {
             const int tn = t + 32;
-            const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)bh * max_len + tn) * 64);
+            const uint4* kp = reinterpret_cast<const uint4*>(kcache + (tn < pos ? row_of(tn) : 0) * 64);
 #pragma unroll
             for (int c = 0; c < 8; ++c) kbuf[(i + 1) & 1][c] = (tn < pos) ? kp[c] : make_uint4(0u, 0u, 0u, 0u);
         }
@@ -385,7 +392,7 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int t = t0 + 32 + 4 * j + rsel;
-            un[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + (long long)t * 64) : make_uint4(0u, 0u, 0u, 0u);
+            un[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + row_of(t) * 64) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -422,13 +429,13 @@ decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int
 
 wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
                                  void* vcache, const int32_t* pos, const int32_t* done, void* out, int B, int H,
-                                 int max_len, int dtype, cudaStream_t stream) {
+                                 int max_len, int dtype, cudaStream_t stream, const int32_t* anc) {
     if (max_len > kMaxCtx) { set_error("decoder_self_attention: max_len %d > %d", max_len, kMaxCtx); return WK_ERR_INVALID_ARGUMENT; }
     const unsigned grid = (unsigned)((B * H + 3) / 4);
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, pos, done, (__half*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, pos, done, (__half*)out, B, H, max_len, anc);
     else
-        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, pos, done, (__nv_bfloat16*)out, B, H, max_len);
+        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, pos, done, (__nv_bfloat16*)out, B, H, max_len, anc);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_self_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -450,7 +457,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
                                const T* __restrict__ kcross, const T* __restrict__ vcross, T* __restrict__ out, int B, int H,
-                               int Tlen, const int32_t* __restrict__ done, float* __restrict__ align_scratch, uint32_t align_mask) {
+                               int Tlen, const int32_t* __restrict__ done, float* __restrict__ align_scratch, uint32_t align_mask, int kv_div) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                                   // kCrossStages * 16000
     float* scores = reinterpret_cast<float*>(smem + kCrossStages * kCrossStageBytes);  // [Tlen]
@@ -460,7 +467,10 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
     uint64_t* empty_bar = full_bar + kCrossStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bh = blockIdx.x, b = bh / H, h = bh % H;
+    // grid order: (window, head, beam) - the kv_div rows that share one K/V block are adjacent, so their streams meet in L2
+    const int beam_j = blockIdx.x % kv_div, wh = blockIdx.x / kv_div;
+    const int win = wh / H, h = wh % H, b = win * kv_div + beam_j;
+    const int kvh = win * H + h;             // K/V block index: [window][head]
     const int dm = H * 64;
     const int chunks = Tlen / kCrossRows;  // per K and per V
     pdl_launch_dependents();
@@ -478,8 +488,8 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
         // no griddepcontrol.wait here: the cross K/V cache is written once before the decode loop starts, so when this kernel is
         // launched as a programmatic dependent the first K chunks are already in flight while the upstream GEMM drains
         if (lane == 0) {
-            const uint8_t* kb = reinterpret_cast<const uint8_t*>(kcross + (long long)bh * Tlen * 64);
-            const uint8_t* vb = reinterpret_cast<const uint8_t*>(vcross + (long long)bh * Tlen * 64);
+            const uint8_t* kb = reinterpret_cast<const uint8_t*>(kcross + (long long)kvh * Tlen * 64);
+            const uint8_t* vb = reinterpret_cast<const uint8_t*>(vcross + (long long)kvh * Tlen * 64);
             for (int c = 0; c < 2 * chunks; ++c) {
                 const int stage = c % kCrossStages;
                 const uint32_t ph = (c / kCrossStages) & 1;
@@ -622,7 +632,8 @@ wk_status decoder_align_mean(const float* scratch, int n_slots, const int32_t* s
 
 wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
                                   const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
-                                  const int32_t* done, float* align_scratch, uint32_t align_mask) {
+                                  const int32_t* done, float* align_scratch, uint32_t align_mask, int kv_div) {
+    if (kv_div < 1 || B % kv_div != 0) { set_error("decoder_cross_attention: %d rows do not split into groups of %d", B, kv_div); return WK_ERR_INVALID_ARGUMENT; }
     if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
     const size_t smem = cross_smem_bytes(T);
     static bool attr_set[2] = {false, false};
@@ -635,9 +646,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
         attr_set[ti] = true;
     }
     if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, done, align_scratch, align_mask);
+        launch_k(decoder_cross_attention_kernel<__half>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __half*)kcross, (const __half*)vcross, (__half*)out, B, H, T, done, align_scratch, align_mask, kv_div);
     else
-        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, done, align_scratch, align_mask);
+        launch_k(decoder_cross_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const __nv_bfloat16*)kcross, (const __nv_bfloat16*)vcross, (__nv_bfloat16*)out, B, H, T, done, align_scratch, align_mask, kv_div);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_cross_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -823,6 +834,22 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
         }
         return best;   // identical in every thread
     };
+    if (loop_mode && p.beam.beam > 1) {
+        // beam search: rank the row's (beam + 1) best tokens of the filtered log-softmax, best first (whisper BeamSearchDecoder.update step 1);
+        // the per-window merge and every state update happen in beam_update_kernel
+        const int k = p.beam.beam + 1;
+        for (int kk = 0; kk < k; ++kk) {
+            const ArgMax a = block_argmax();
+            const bool ok = a.v != -INFINITY && a.i >= 0 && a.i < V;   // (a NaN row yields the initial index: no candidate)
+            if (tid == 0) {
+                p.beam.cand_tok[b * (kMaxBeam + 1) + kk] = ok ? a.i : -1;
+                p.beam.cand_lp[b * (kMaxBeam + 1) + kk] = ok ? a.v - lse : -INFINITY;
+                if (ok) srow[a.i] = -INFINITY;
+            }
+            __syncthreads();
+        }
+        return;
+    }
     ArgMax best;
     float lp_sampled = 0.f;
     if (R.temperature == 0.f) {
@@ -897,6 +924,134 @@ sampler_kernel(const float* __restrict__ logits, long long ld_logits, SamplerPar
             }
         }
     }
+}
+
+// =====================================================================================================
+// Beam search step (oracle/beam_ref.py is the specification).  One CTA per window; rows r0 .. r0 + beam - 1 are its beams.
+// =====================================================================================================
+static constexpr int kBeamThreads = 128;
+
+__global__ void __launch_bounds__(kBeamThreads)
+beam_update_kernel(DecodeState st, BeamState bs, wk_special_tokens S, int max_ctx) {
+    __shared__ int32_t s_tok[kMaxBeam][kMaxCtx];
+    __shared__ float s_lp[kMaxBeam][kMaxCtx];
+    __shared__ int32_t s_anc[kMaxBeam][kMaxCtx];
+    __shared__ float c_score[kMaxBeam * (kMaxBeam + 1)], c_lp[kMaxBeam * (kMaxBeam + 1)];
+    __shared__ int c_src[kMaxBeam * (kMaxBeam + 1)], c_tok[kMaxBeam * (kMaxBeam + 1)], c_ord[kMaxBeam * (kMaxBeam + 1)];
+    __shared__ int n_src[kMaxBeam], n_tokv[kMaxBeam];
+    __shared__ float n_lp[kMaxBeam], n_score[kMaxBeam];
+    __shared__ int f_src[kMaxCand]; __shared__ float f_score[kMaxCand];
+    __shared__ int sh[4];   // 0: mode (0 prefill/plain advance, 1 ranked, 2 ended without ranking)  1: new finished count  2: window done  3: finished before
+    const int g = blockIdx.x, tid = threadIdx.x, beam = bs.beam, r0 = g * beam;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (st.done[r0]) return;
+    const RowParams R = st.rp[r0];
+    const int step = st.steps[r0], n_tok = st.n_tokens[r0], P = R.prompt_len;
+    const int C1 = kMaxBeam + 1;
+    if (tid == 0) {
+        const int gtok = bs.cand_tok[r0 * C1];
+        const float glp = bs.cand_lp[r0 * C1];
+        const bool bad = gtok < 0;
+        const bool first_low = (step == 0) && R.has_first_thr && (glp < R.first_thr);
+        int mode = 0, done = 0;
+        int nf_before = bs.n_fin[g];
+        int nf_new = 0;
+        if (bad) { done = 1; mode = 2; }
+        else if (step < P - 1) {                       // prefill: every beam is the same forced copy; greedy bookkeeping
+            if (gtok == S.end_token || first_low) done = 1;
+        } else if (n_tok >= max_ctx - 1 || first_low) {
+            done = 1; mode = 2;
+        } else {
+            mode = 1;
+            const int considered = (step == P - 1) ? 1 : beam;   // identical beams count once
+            int nc = 0;
+            for (int j = 0; j < considered; ++j)
+                for (int k = 0; k <= beam; ++k) {
+                    const int t = bs.cand_tok[(r0 + j) * C1 + k];
+                    if (t < 0) continue;
+                    const float v = bs.cand_lp[(r0 + j) * C1 + k];
+                    c_score[nc] = bs.sum_lp[r0 + j] + v; c_lp[nc] = v; c_src[nc] = j; c_tok[nc] = t; c_ord[nc] = nc; ++nc;
+                }
+            for (int i = 1; i < nc; ++i) {             // stable insertion sort, best score first
+                const int o = c_ord[i];
+                int k = i - 1;
+                while (k >= 0 && c_score[c_ord[k]] < c_score[o]) { c_ord[k + 1] = c_ord[k]; --k; }
+                c_ord[k + 1] = o;
+            }
+            int saved = 0;
+            for (int i = 0; i < nc && saved < beam; ++i) {
+                const int o = c_ord[i];
+                if (c_tok[o] == S.end_token) {
+                    if (nf_before + nf_new < bs.max_candidates) { f_src[nf_new] = c_src[o]; f_score[nf_new] = c_score[o]; ++nf_new; }
+                } else {
+                    n_src[saved] = c_src[o]; n_tokv[saved] = c_tok[o]; n_lp[saved] = c_lp[o]; n_score[saved] = c_score[o]; ++saved;
+                }
+            }
+            for (; saved < beam; ++saved) {            // (cannot happen with beam + 1 candidates per beam; keeps the state well formed)
+                n_src[saved] = n_src[saved > 0 ? saved - 1 : 0]; n_tokv[saved] = n_tokv[saved > 0 ? saved - 1 : 0]; n_lp[saved] = 0.f; n_score[saved] = -INFINITY;
+            }
+            if (nf_before + nf_new >= bs.max_candidates) done = 1;
+        }
+        if (!done && step + 1 >= R.max_steps) done = 1;   // loop bound (TextDecoder.swift:566)
+        sh[0] = mode; sh[1] = nf_new; sh[2] = done; sh[3] = nf_before;
+        for (int j = 0; j < beam; ++j) {
+            const int r = r0 + j;
+            st.steps[r] = step + 1;
+            if (bad) st.error[r] = 1;
+            if (mode != 1) st.next_token[r] = bad ? S.end_token : gtok;
+            if (done) { st.done[r] = 1; st.first_low[r] = first_low ? 1 : 0; }
+            bs.anc[r * kMaxCtx + step] = r;             // position `step` of this row's cache was written by the row itself
+        }
+    }
+    __syncthreads();
+    if (sh[0] != 1) return;
+    // ---- ranked step: histories and ancestry move to the surviving beams
+    for (int i = tid; i < beam * kMaxCtx; i += kBeamThreads) {
+        const int j = i / kMaxCtx, t = i % kMaxCtx;
+        s_tok[j][t] = st.tokens[(r0 + j) * kMaxCtx + t];
+        s_lp[j][t] = st.logprobs[(r0 + j) * kMaxCtx + t];
+        s_anc[j][t] = bs.anc[(r0 + j) * kMaxCtx + t];
+    }
+    __syncthreads();
+    for (int f = 0; f < sh[1]; ++f) {                   // newly finished: prefix of the source beam + EOT (log-prob 0, like sampler.finalize)
+        const int slot = g * kMaxCand + sh[3] + f, src = f_src[f];
+        for (int t = tid; t < n_tok; t += kBeamThreads) {
+            bs.fin_tokens[slot * kMaxCtx + t] = s_tok[src][t];
+            bs.fin_lps[slot * kMaxCtx + t] = s_lp[src][t];
+        }
+        if (tid == 0) {
+            bs.fin_tokens[slot * kMaxCtx + n_tok] = S.end_token;
+            bs.fin_lps[slot * kMaxCtx + n_tok] = 0.f;
+            bs.fin_len[slot] = n_tok + 1;
+            bs.fin_score[slot] = f_score[f];
+        }
+    }
+    if (tid == 0) bs.n_fin[g] = sh[3] + sh[1];
+    for (int i = tid; i < beam * kMaxCtx; i += kBeamThreads) {
+        const int j = i / kMaxCtx, t = i % kMaxCtx, r = r0 + j, src = n_src[j];
+        if (t < n_tok) { st.tokens[r * kMaxCtx + t] = s_tok[src][t]; st.logprobs[r * kMaxCtx + t] = s_lp[src][t]; }
+        else if (t == n_tok) { st.tokens[r * kMaxCtx + t] = n_tokv[j]; st.logprobs[r * kMaxCtx + t] = n_lp[j]; }
+        if (t <= step) bs.anc[r * kMaxCtx + t] = (t == step) ? r0 + src : s_anc[src][t];
+    }
+    if (tid < beam) {
+        const int r = r0 + tid;
+        st.n_tokens[r] = n_tok + 1;
+        st.next_token[r] = n_tokv[tid];
+        bs.sum_lp[r] = n_score[tid];
+    }
+}
+
+wk_status beam_update(DecodeState st, BeamState beam, wk_special_tokens sp, int max_ctx, int groups, cudaStream_t stream) {
+    if (beam.beam < 2 || beam.beam > kMaxBeam || beam.max_candidates < 1 || beam.max_candidates > kMaxCand) {
+        set_error("beam_update: beam %d / candidates %d outside [2, %d] / [1, %d]", beam.beam, beam.max_candidates, kMaxBeam, kMaxCand);
+        return WK_ERR_INVALID_ARGUMENT;
+    }
+    launch_k(beam_update_kernel, dim3(groups), dim3(kBeamThreads), 0, stream, 8, st, beam, sp, max_ctx);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("beam_update launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+    return WK_OK;
 }
 
 wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerParams p, DecodeState st, const int32_t* tokens,

@@ -9,7 +9,7 @@
 //
 // Structure: grid = one CTA per SM (all co-resident), 320 threads.  GEMM phase: warp 0 = TMA producer, warp 1 = tcgen05 MMA issuer,
 // warps 2-9 = epilogue (transposed f32 partial store), work item = (128-row weight tile, K split), one per CTA (single wave by the
-// split rule).  Reduce phase: all 320 threads, CTA b reduces batch row b in the fixed split order (deterministic).  Pipeline state
+// split rule).  Reduce phase: all 320 threads, CTA b reduces batch rows b, b + grid, ... in the fixed split order (deterministic).  Pipeline state
 // (ring stage / parity, accumulator parity) lives in registers across phases.  Memory ordering at a phase boundary: every thread
 // fences its generic-proxy global writes towards the async proxy (the next GEMM phase reads activations with TMA), then
 // bar.sync + __threadfence + atomic arrive / acquire spin (the cooperative-groups grid.sync recipe).
@@ -322,7 +322,7 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
             if (warp == 0 && lane == 0 && ph + 1 < p.n_phases && p.ph[ph + 1].kind == 0) prefetch_weights(ph + 1);
             __syncwarp();
             if (P.kind == 1) {
-                if ((int)blockIdx.x < p.B) reduce_ln_row<T>(p, P, blockIdx.x, scratch);
+                for (int b = blockIdx.x; b < p.B; b += gridDim.x) reduce_ln_row<T>(p, P, b, scratch);   // rows beyond one per CTA (beam search: up to 256 rows)
             } else {
                 reduce_gelu_all<T>(p, P);
             }
@@ -374,7 +374,7 @@ wk_status decoder_chain(const ChainDesc& c, int num_sms, cudaStream_t stream) {
             if (last_gemm != i - 1) { set_error("decoder_chain: reduce phase %d must follow a GEMM phase", i); return WK_ERR_INVALID_ARGUMENT; }
             k.red_n = p.ph[i - 1].n; k.red_splits = p.ph[i - 1].splits;
             k.bias = s.bias; k.gamma = s.gamma; k.beta = s.beta; k.out16 = s.out16;
-            if (k.red_splits > kMaxSplitsR || (k.red_n & 3) || (s.kind == 1 && (k.red_n != c.d || c.d > 8 * kThreads)) || c.B > num_sms) {
+            if (k.red_splits > kMaxSplitsR || (k.red_n & 3) || (s.kind == 1 && (k.red_n != c.d || c.d > 8 * kThreads))) {
                 set_error("decoder_chain: unsupported reduce phase %d", i); return WK_ERR_INVALID_ARGUMENT;
             }
         }

@@ -119,6 +119,21 @@ struct DecodeState {
     const RowParams* rp;  // [Bmax]
 };
 
+// Beam search (semantics restated from openai/whisper BeamSearchDecoder in oracle/beam_ref.py - the reference's
+// BeamSearchTokenSampler is a fatalError stub, TokenSampler.swift:254-290).  Decode rows come in groups of `beam` consecutive rows per window.
+constexpr int kMaxBeam = 8;
+constexpr int kMaxCand = 8;        // maxCandidates = Int(Float(beamSize) * patience) (TokenSampler.swift:266)
+struct BeamState {
+    int beam;                      // rows per window; <= 1 = greedy / sampling, every field below unused
+    int max_candidates;
+    float* sum_lp;                 // [rows] cumulative log-prob of the sampled tokens of the beam
+    int32_t* cand_tok; float* cand_lp;   // [rows][kMaxBeam + 1] best tokens of the step's filtered log-softmax, best first (-1 = none)
+    int32_t* anc;                  // [rows][224] physical cache row that holds position t of this beam's self K/V
+    int32_t* fin_tokens; float* fin_lps;   // [groups][kMaxCand][224] finished sequences (EOT included), per-token log-probs (EOT -> 0)
+    int32_t* fin_len; float* fin_score;    // [groups][kMaxCand]
+    int32_t* n_fin;                // [groups]
+};
+
 struct SamplerParams {
     wk_special_tokens st;
     int vocab;
@@ -127,6 +142,7 @@ struct SamplerParams {
     const int32_t* suppress; // loop mode: the pool RowParams.suppress_off indexes; stateless: the list itself
     const int32_t* language_tokens; int n_language_tokens; int language_sample_begin;
     int max_ctx;             // 224
+    BeamState beam;          // loop mode with beam.beam > 1: the kernel only ranks candidates; beam_update() does the bookkeeping
     // stateless mode only
     int sample_begin_ts, sample_begin_blank, n_suppress;
     float temperature; int top_k; uint64_t seed;
@@ -143,15 +159,18 @@ wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, con
                                    int dtype, cudaStream_t stream);
 // self attention for one new token per sequence; reduces qkv partials [S][Bp][3d], appends K/V at pos[b].  done != nullptr: rows with
 // done[b] != 0 are skipped (their window has ended: no cache traffic)
+// anc != nullptr (beam search): position t of row b is read from cache row anc[b][t]; the new row is written to row b itself
 wk_status decoder_self_attention(const float* partial, int splits, int Bp, const float* bq, const float* bv, void* kcache,
                                  void* vcache, const int32_t* pos, const int32_t* done, void* out, int B, int H,
-                                 int max_len, int dtype, cudaStream_t stream);
+                                 int max_len, int dtype, cudaStream_t stream, const int32_t* anc = nullptr);
 // cross attention over T encoder positions; reduces q partials [S][Bp][d]; K/V [B][H][T][64]
 // align_scratch != nullptr: heads h with bit h of align_mask set also write their softmax row (f32, [slot][B][T], slot = rank of h in
 // the mask) - the alignment heads behind the reference decoder's `alignment_heads_weights` output (TextDecoder.swift:310,414)
 wk_status decoder_cross_attention(const float* partial, int splits, int Bp, const float* bq, const void* kcross,
                                   const void* vcross, void* out, int B, int H, int T, int dtype, cudaStream_t stream,
-                                  const int32_t* done = nullptr, float* align_scratch = nullptr, uint32_t align_mask = 0);
+                                  const int32_t* done = nullptr, float* align_scratch = nullptr, uint32_t align_mask = 0, int kv_div = 1);
+// kv_div > 1 (beam search): row b reads the K/V block of window b / kv_div; the CTAs of one (window, head) are adjacent in the grid so that
+// their K/V stream is shared through L2
 // alignment row of the step just sampled (run AFTER the sampler advanced steps[b] to tokenIndex + 1): out[b][steps[b]][t] =
 // Float16(mean over n_slots of scratch[slot][b][t]) unless done[b] (TextDecoder.updateAlignmentWeights, TextDecoder.swift:272-296:
 // the slice of step tokenIndex lands in row tokenIndex + 1; a completed segment breaks out before the update, :668-674)
@@ -162,7 +181,10 @@ wk_status sampler_filter_sample(const float* logits, int64_t ld_logits, SamplerP
                                 float* filtered_out, int B, cudaStream_t stream);
 // (re)starts the decode of n slots: slot_ids[i] gets prompt row i of prompts [n][224] (length rp[i].prompt_len) and RowParams rp[i]
 wk_status decode_slots_init(DecodeState st, RowParams* rp_dev, const int32_t* slot_ids, const int32_t* prompts, const RowParams* rp_new,
-                            int n, cudaStream_t stream);
+                            int n, cudaStream_t stream, BeamState beam = BeamState());
+// the beam-search step after the sampler ranked every row's candidates: per window, merge the beams' candidates, move finished sequences
+// to the finished list, permute token / log-prob histories and cache ancestry to the surviving beams, advance the loop state
+wk_status beam_update(DecodeState st, BeamState beam, wk_special_tokens sp, int max_ctx, int groups, cudaStream_t stream);
 
 // ---- a chain of decoder GEMM / split-K reduce phases in ONE persistent kernel with grid-wide barriers between the phases instead of
 // kernel boundaries (fused_chain.cu)

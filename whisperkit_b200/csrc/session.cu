@@ -27,7 +27,8 @@ using namespace wk;
 struct wk_session {
     wk_model* m = nullptr;
     int max_batch = 0;        // decode slots
-    int batch = 0;            // rows the step runs over: slots [0, batch)
+    int batch = 0;            // rows the step runs over: slots [0, batch) (x beam rows per slot with beam search)
+    int bound_windows = 0;    // windows bound by wk_session_set_encoder_output (cross K/V blocks 0 .. bound_windows - 1)
     int bp = 16;              // batch padded to the UMMA N granule
     cudaStream_t stream = nullptr;      // decode stream
     cudaStream_t enc_stream = nullptr;  // mel + encoder of the batched entry
@@ -60,6 +61,10 @@ struct wk_session {
     unsigned int* chain_counters = nullptr;
     cudaEvent_t ev_enc = nullptr, ev_adm = nullptr, ev_stage = nullptr, ev_t[10];
     bool knob_fused = true, knob_graph = true;
+    // beam search (allocated on the first call that asks for it)
+    BeamState bs = BeamState(); int bs_cap_rows = 0;
+    int32_t *h_n_fin = nullptr, *h_fin_len = nullptr, *h_fin_tokens = nullptr; float *h_fin_score = nullptr, *h_fin_lps = nullptr, *h_sum_lp = nullptr;
+    int graph_beam = 1;
     std::vector<int> slot_window, slot_try;
     int64_t stats[4] = {0, 0, 0, 0};   // of the last batched call: step launches, sum of live rows over them, admissions, ladder re-admissions
 };
@@ -86,7 +91,7 @@ static wk_status dec_gemm(wk_session* s, const void* w, int N, int K, const void
 
 // The fused phase chains hold every SM with a CTA that waits on grid-wide barriers.  Two such grids from different sessions could each
 // take half of the machine and wait for the other half forever, so a session only uses them while it is the model's sole live session.
-static bool use_fused(const wk_session* s) { return s->knob_fused && s->m->live_sessions.load(std::memory_order_relaxed) == 1 && s->batch <= s->m->num_sms; }
+static bool use_fused(const wk_session* s) { return s->knob_fused && s->m->live_sessions.load(std::memory_order_relaxed) == 1; }
 
 // one decoder forward for every row of the step.  explicit_pos == nullptr: loop mode (token / position from DecodeState, ended rows skipped)
 static wk_status decoder_forward(wk_session* s, int ts_begin, const int32_t* explicit_pos, bool fused) {
@@ -98,18 +103,20 @@ static wk_status decoder_forward(wk_session* s, int ts_begin, const int32_t* exp
     const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;          // bytes per (layer, k|v)
     const int32_t* pos = explicit_pos ? explicit_pos : s->st.steps;
     const int32_t* done = explicit_pos ? nullptr : s->st.done;
+    const bool beam_rows = !explicit_pos && s->bs.beam > 1;   // rows are beams: cache ancestry + one cross K/V block per `beam` rows
     const int n_layers = c.dec_layers;
     int sp = 1;
     WK_CHECK(decoder_embed_ln(m->emb, m->dec_pos, m->dec[0].ln1.g, m->dec[0].ln1.b, s->st, c.vocab, ts_begin, s->x, s->xn, B, d, dt, explicit_pos, st));
     auto self_attn = [&](int li, const DecLayer& l) {
         return decoder_self_attention(s->partial, sp, Bp, l.bq, l.bv, (char*)s->self_k + li * self_layer, (char*)s->self_v + li * self_layer, pos, done,
-                                      s->attn, B, H, kKvMaxLen, dt, st);
+                                      s->attn, B, H, kKvMaxLen, dt, st, beam_rows ? s->bs.anc : nullptr);
     };
     auto cross_attn = [&](int li, const DecLayer& l) {
         const bool align = s->align_on && !explicit_pos && m->align_mask[li] != 0;
         return decoder_cross_attention(s->partial, sp, Bp, l.bcq, (char*)s->cross_kv + (size_t)(2 * li) * cross_block,
                                        (char*)s->cross_kv + (size_t)(2 * li + 1) * cross_block, s->attn, B, H, T, dt, st, done,
-                                       align ? s->align_scratch + (size_t)m->align_base[li] * B * T : nullptr, align ? m->align_mask[li] : 0u);
+                                       align ? s->align_scratch + (size_t)m->align_base[li] * B * T : nullptr, align ? m->align_mask[li] : 0u,
+                                       beam_rows ? s->bs.beam : 1);
     };
     if (fused) {
         // per layer: self-attention -> chain B (out-proj, reduce+LN, cross-Q) -> cross-attention -> chain C (cross-out, reduce+LN, FC1,
@@ -197,6 +204,7 @@ static SamplerParams loop_sampler_params(wk_session* s, const wk_special_tokens*
     p.loop_mode = 1;
     p.suppress = s->suppress_dev;
     p.max_ctx = kKvMaxLen;
+    p.beam = s->bs;
     return p;
 }
 
@@ -289,6 +297,7 @@ static wk_status enqueue_step(wk_session* s, const wk_special_tokens* st, bool f
     wk_model* m = s->m;
     WK_CHECK(decoder_forward(s, st->time_token_begin, nullptr, fused));
     WK_CHECK(sampler_filter_sample(s->logits, m->cfg.vocab, loop_sampler_params(s, st), s->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, s->batch, s->stream));
+    if (s->bs.beam > 1) WK_CHECK(beam_update(s->st, s->bs, *st, kKvMaxLen, s->batch / s->bs.beam, s->stream));
     if (s->align_on)
         WK_CHECK(decoder_align_mean(s->align_scratch, m->n_align_slots, s->st.steps, s->st.done, s->align_w, s->batch, m->cfg.n_audio_ctx, kKvMaxLen, s->stream));
     return WK_OK;
@@ -306,7 +315,7 @@ static wk_status run_steps(wk_session* s, const wk_special_tokens* st, int n) {
     }
     if (done >= n) return WK_OK;
     const bool stale = !s->graph_exec || s->graph_batch != s->batch || s->graph_align != s->align_on || s->graph_fused != fused ||
-                       memcmp(&s->graph_st, st, sizeof(*st)) != 0;
+                       s->graph_beam != std::max(1, s->bs.beam) * 16 + s->bs.max_candidates || memcmp(&s->graph_st, st, sizeof(*st)) != 0;
     if (stale) {
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
@@ -332,6 +341,7 @@ static wk_status run_steps(wk_session* s, const wk_special_tokens* st, int n) {
             return WK_ERR_CUDA;
         }
         s->graph_batch = s->batch; s->graph_align = s->align_on; s->graph_fused = fused; s->graph_st = *st;
+        s->graph_beam = std::max(1, s->bs.beam) * 16 + s->bs.max_candidates;
     }
     for (; done < n; ++done) {
         WK_CUDA_CHECK(cudaGraphLaunch(s->graph_exec, s->stream));
@@ -368,6 +378,33 @@ static wk_status ensure_align(wk_session* s, int64_t n_windows) {
     return WK_OK;
 }
 
+static wk_status ensure_beam(wk_session* s) {
+    if (s->bs_cap_rows >= s->max_batch) return WK_OK;
+    const int S = s->max_batch, G = S / 2 + 1;
+    WK_CHECK(dmalloc(&s->bs.sum_lp, S));
+    WK_CHECK(dmalloc(&s->bs.cand_tok, (size_t)S * (kMaxBeam + 1)));
+    WK_CHECK(dmalloc(&s->bs.cand_lp, (size_t)S * (kMaxBeam + 1)));
+    WK_CHECK(dmalloc(&s->bs.anc, (size_t)S * kKvMaxLen));
+    WK_CHECK(dmalloc(&s->bs.fin_tokens, (size_t)G * kMaxCand * kKvMaxLen));
+    WK_CHECK(dmalloc(&s->bs.fin_lps, (size_t)G * kMaxCand * kKvMaxLen));
+    WK_CHECK(dmalloc(&s->bs.fin_len, (size_t)G * kMaxCand));
+    WK_CHECK(dmalloc(&s->bs.fin_score, (size_t)G * kMaxCand));
+    WK_CHECK(dmalloc(&s->bs.n_fin, G));
+    auto pinned = [&](void** p, size_t bytes) -> wk_status {
+        cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return WK_ERR_CUDA; }
+        return WK_OK;
+    };
+    WK_CHECK(pinned((void**)&s->h_n_fin, (size_t)G * 4));
+    WK_CHECK(pinned((void**)&s->h_fin_len, (size_t)G * kMaxCand * 4));
+    WK_CHECK(pinned((void**)&s->h_fin_score, (size_t)G * kMaxCand * 4));
+    WK_CHECK(pinned((void**)&s->h_fin_tokens, (size_t)G * kMaxCand * kKvMaxLen * 4));
+    WK_CHECK(pinned((void**)&s->h_fin_lps, (size_t)G * kMaxCand * kKvMaxLen * 4));
+    WK_CHECK(pinned((void**)&s->h_sum_lp, (size_t)S * 4));
+    s->bs_cap_rows = S;
+    return WK_OK;
+}
+
 static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
     wk_model* m = s->m;
     const wk_model_config& c = m->cfg;
@@ -375,8 +412,29 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
     const wk_special_tokens* st = a.st;
     const bool bound = a.pcm == nullptr;
     const int64_t n = a.n;
-    const int S = s->max_batch, d = c.d_model, T = c.n_audio_ctx;
+    const int d = c.d_model, T = c.n_audio_ctx;
     const int poll = bo->progress_every > 0 ? bo->progress_every : 16;
+    // beam search: every window takes `beam` consecutive decode rows; one setting per call (it shapes the step graph)
+    const int beam = bo->opts[0].beam_size > 1 ? bo->opts[0].beam_size : 1;
+    for (int i = 0; i < bo->n_opts; ++i)
+        if ((bo->opts[i].beam_size > 1 ? bo->opts[i].beam_size : 1) != beam || (beam > 1 && bo->opts[i].beam_patience != bo->opts[0].beam_patience)) {
+            set_error("beam size / patience must be the same for every window of a call"); return WK_ERR_INVALID_ARGUMENT;
+        }
+    int max_cand = 0;
+    if (beam > 1) {
+        const float patience = bo->opts[0].beam_patience > 0.f ? bo->opts[0].beam_patience : 1.f;
+        max_cand = (int)((float)beam * patience);                                  // TokenSampler.swift:266
+        if (beam > kMaxBeam || max_cand < 1 || max_cand > kMaxCand || s->max_batch < beam) {
+            set_error("beam size %d / patience %.2f unsupported (beam <= %d, candidates in [1, %d], session rows %d)", beam, patience, kMaxBeam, kMaxCand, s->max_batch);
+            return WK_ERR_INVALID_ARGUMENT;
+        }
+        for (int i = 0; i < bo->n_opts; ++i)
+            if (bo->opts[i].word_timestamps) { set_error("wordTimestamps with beam search is not supported"); return WK_ERR_INVALID_ARGUMENT; }
+        WK_CHECK(ensure_beam(s));
+    }
+    s->bs.beam = beam; s->bs.max_candidates = max_cand;
+    const int S = s->max_batch / beam;     // decode slots (windows in flight)
+    if (bound && n > S) { set_error("wk_decode_text: %lld bound windows x beam %d exceed the session's %d rows", (long long)n, beam, s->max_batch); return WK_ERR_PREPARE_DECODER_INPUTS; }
     std::vector<wk_status> st_local((size_t)n, WK_OK);
     wk_status* status = bo->status ? bo->status : st_local.data();
     for (int64_t w = 0; w < n; ++w) status[w] = WK_OK;
@@ -439,13 +497,15 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
     if (any_words) WK_CHECK(ensure_align(s, n));
 
     // ---- slots
-    if (!bound) { s->batch = (int)std::min<int64_t>(S, n); s->bp = round_up(s->batch, 16); }
-    const int Brun = s->batch;
+    const int Brun = (int)std::min<int64_t>(S, n);     // slots in use; the step covers Brun * beam rows
+    s->batch = Brun * beam;
+    s->bp = round_up(s->batch, 16);
+    const int rows = s->batch;
     s->slot_window.assign(S, -1);
     s->slot_try.assign(S, 0);
-    {   // every slot starts free: done = 1 keeps its row out of the step until a window is admitted
-        std::vector<int32_t> ones(S, 1);
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->st.done, ones.data(), S * 4, cudaMemcpyHostToDevice, s->stream));
+    {   // every slot starts free: done = 1 keeps its rows out of the step until a window is admitted
+        std::vector<int32_t> ones(s->max_batch, 1);
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->st.done, ones.data(), s->max_batch * 4, cudaMemcpyHostToDevice, s->stream));
         WK_CUDA_CHECK(cudaStreamSynchronize(s->stream));
     }
     // temperature of ladder rung i, computed in Float16 like the reference (TranscribeTask.swift:327)
@@ -473,14 +533,17 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
         R.seed = o.seed + (uint64_t)rung;
         R.suppress_off = sup_off[oi]; R.n_suppress = sup_n[oi];
         if (n_adm == 0) cudaEventSynchronize(s->ev_stage);   // the previous round's copies out of the pinned staging have landed
-        s->h_adm_slots[n_adm] = slot;
-        memset(s->h_adm_prompts + (size_t)n_adm * kKvMaxLen, 0, kKvMaxLen * 4);
-        memcpy(s->h_adm_prompts + (size_t)n_adm * kKvMaxLen, p, (size_t)np * 4);
-        s->h_adm_rp[n_adm] = R;
-        ++n_adm;
+        for (int j = 0; j < beam; ++j) {                     // beam search: `beam` identical rows start the window
+            s->h_adm_slots[n_adm] = slot * beam + j;
+            memset(s->h_adm_prompts + (size_t)n_adm * kKvMaxLen, 0, kKvMaxLen * 4);
+            memcpy(s->h_adm_prompts + (size_t)n_adm * kKvMaxLen, p, (size_t)np * 4);
+            s->h_adm_rp[n_adm] = R;
+            ++n_adm;
+        }
         s->slot_window[slot] = (int)w;
         s->slot_try[slot] = rung;
     };
+    auto prompt_len_of = [&](int64_t w) -> int { const int32_t* p; int np; prompt_of(w, &p, &np); return np; };
     auto flush_admissions = [&]() -> wk_status {
         if (n_adm == 0) return WK_OK;
         WK_CUDA_CHECK(cudaMemcpyAsync(s->d_adm_slots, s->h_adm_slots, (size_t)n_adm * 4, cudaMemcpyHostToDevice, s->stream));
@@ -489,7 +552,7 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
         if (s->align_on)
             for (int i = 0; i < n_adm; ++i)   // row 0 and unreached rows of alignmentWeights stay 0
                 WK_CUDA_CHECK(cudaMemsetAsync((char*)s->align_w + (size_t)s->h_adm_slots[i] * kKvMaxLen * T * 2, 0, (size_t)kKvMaxLen * T * 2, s->stream));
-        WK_CHECK(decode_slots_init(s->st, s->rp_dev, s->d_adm_slots, s->d_adm_prompts, s->d_adm_rp, n_adm, s->stream));
+        WK_CHECK(decode_slots_init(s->st, s->rp_dev, s->d_adm_slots, s->d_adm_prompts, s->d_adm_rp, n_adm, s->stream, s->bs));
         WK_CUDA_CHECK(cudaEventRecord(s->ev_stage, s->stream));
         n_adm = 0;
         return WK_OK;
@@ -610,13 +673,21 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
         WK_CHECK(run_steps(s, st, poll));
         s->stats[0] += poll; s->stats[1] += (int64_t)poll * live;
         WK_CUDA_CHECK(cudaEventRecord(s->ev_t[7], s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_done, s->st.done, Brun * 4, cudaMemcpyDeviceToHost, s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_n_tokens, s->st.n_tokens, Brun * 4, cudaMemcpyDeviceToHost, s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_steps, s->st.steps, Brun * 4, cudaMemcpyDeviceToHost, s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_first_low, s->st.first_low, Brun * 4, cudaMemcpyDeviceToHost, s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_error, s->st.error, Brun * 4, cudaMemcpyDeviceToHost, s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_tokens, s->st.tokens, (size_t)Brun * kKvMaxLen * 4, cudaMemcpyDeviceToHost, s->stream));
-        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_logprobs, s->st.logprobs, (size_t)Brun * kKvMaxLen * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_done, s->st.done, rows * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_n_tokens, s->st.n_tokens, rows * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_steps, s->st.steps, rows * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_first_low, s->st.first_low, rows * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_error, s->st.error, rows * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_tokens, s->st.tokens, (size_t)rows * kKvMaxLen * 4, cudaMemcpyDeviceToHost, s->stream));
+        WK_CUDA_CHECK(cudaMemcpyAsync(s->h_logprobs, s->st.logprobs, (size_t)rows * kKvMaxLen * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (beam > 1) {
+            WK_CUDA_CHECK(cudaMemcpyAsync(s->h_sum_lp, s->bs.sum_lp, rows * 4, cudaMemcpyDeviceToHost, s->stream));
+            WK_CUDA_CHECK(cudaMemcpyAsync(s->h_n_fin, s->bs.n_fin, Brun * 4, cudaMemcpyDeviceToHost, s->stream));
+            WK_CUDA_CHECK(cudaMemcpyAsync(s->h_fin_len, s->bs.fin_len, (size_t)Brun * kMaxCand * 4, cudaMemcpyDeviceToHost, s->stream));
+            WK_CUDA_CHECK(cudaMemcpyAsync(s->h_fin_score, s->bs.fin_score, (size_t)Brun * kMaxCand * 4, cudaMemcpyDeviceToHost, s->stream));
+            WK_CUDA_CHECK(cudaMemcpyAsync(s->h_fin_tokens, s->bs.fin_tokens, (size_t)Brun * kMaxCand * kKvMaxLen * 4, cudaMemcpyDeviceToHost, s->stream));
+            WK_CUDA_CHECK(cudaMemcpyAsync(s->h_fin_lps, s->bs.fin_lps, (size_t)Brun * kMaxCand * kKvMaxLen * 4, cudaMemcpyDeviceToHost, s->stream));
+        }
         {
             cudaError_t e = cudaStreamSynchronize(s->stream);
             if (e != cudaSuccess) { set_error("decode loop: %s", cudaGetErrorString(e)); return WK_ERR_DECODING_FAILED; }
@@ -631,16 +702,17 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
         for (int q = 0; q < Brun; ++q) {
             const int w = s->slot_window[q];
             if (w < 0) continue;
+            const int r0 = q * beam;                  // first decode row of the slot (the only one without beam search)
             const wk_decode_opts& o = opts_of(bo, w);
-            bool ended = s->h_done[q] != 0, stopped = false;
+            bool ended = s->h_done[r0] != 0, stopped = false;
             if (!ended && bo->progress) {
-                const int nt = s->h_n_tokens[q];
+                const int nt = s->h_n_tokens[r0];
                 float sum = 0.f;
-                for (int i = 0; i < nt; ++i) sum += s->h_logprobs[(size_t)q * kKvMaxLen + i];
-                if (!bo->progress(bo->progress_user, w, s->h_tokens + (size_t)q * kKvMaxLen, nt, nt > 0 ? sum / nt : 0.f)) {
+                for (int i = 0; i < nt; ++i) sum += s->h_logprobs[(size_t)r0 * kKvMaxLen + i];
+                if (!bo->progress(bo->progress_user, w, s->h_tokens + (size_t)r0 * kKvMaxLen, nt, nt > 0 ? sum / nt : 0.f)) {
                     // callback -> false: the reference's early-stop flag ends the loop at the next token (TextDecoder.swift:733-762)
-                    const int32_t one = 1;
-                    WK_CUDA_CHECK(cudaMemcpyAsync(s->st.done + q, &one, 4, cudaMemcpyHostToDevice, s->stream));
+                    std::vector<int32_t> ones(beam, 1);
+                    WK_CUDA_CHECK(cudaMemcpyAsync(s->st.done + r0, ones.data(), beam * 4, cudaMemcpyHostToDevice, s->stream));
                     WK_CUDA_CHECK(cudaStreamSynchronize(s->stream));
                     stopped = true;              // an early-stopped window does not walk the ladder
                     ended = true;
@@ -649,12 +721,46 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
             if (!ended) continue;
             wk_decode_result r;
             const int rung = s->slot_try[q];
-            finalize_result(r, s->h_tokens + (size_t)q * kKvMaxLen, s->h_logprobs + (size_t)q * kKvMaxLen, s->h_n_tokens[q], s->h_steps[q], s->h_first_low[q],
-                            st, &o, rung_temperature(o, rung));
-            if (s->h_error[q]) {
-                set_error("window %d: no finite logit at decoder step %d", w, s->h_steps[q] - 1);
+            const int32_t* seq_tok = s->h_tokens + (size_t)r0 * kKvMaxLen;
+            const float* seq_lp = s->h_logprobs + (size_t)r0 * kKvMaxLen;
+            int seq_n = s->h_n_tokens[r0];
+            std::vector<int32_t> btok; std::vector<float> blp;
+            if (beam > 1) {
+                // BeamSearchDecoder.finalize + MaximumLikelihoodRanker (oracle/beam_ref.py): the finished list, topped up with the live beams
+                // (best sum first) to `beam` entries; the winner maximises sum_logprob / sampled tokens
+                struct Cand { const int32_t* tok; const float* lp; int len; float score; bool live; };
+                std::vector<Cand> cands;
+                const int nf = std::min(s->h_n_fin[q], kMaxCand);
+                for (int f = 0; f < nf; ++f) {
+                    const size_t slot = (size_t)q * kMaxCand + f;
+                    cands.push_back(Cand{s->h_fin_tokens + slot * kKvMaxLen, s->h_fin_lps + slot * kKvMaxLen, s->h_fin_len[slot], s->h_fin_score[slot], false});
+                }
+                if ((int)cands.size() < beam) {
+                    std::vector<int> order(beam);
+                    for (int j = 0; j < beam; ++j) order[j] = j;
+                    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return s->h_sum_lp[r0 + x] > s->h_sum_lp[r0 + y]; });
+                    for (int j : order) {
+                        const int rr = r0 + j;
+                        cands.push_back(Cand{s->h_tokens + (size_t)rr * kKvMaxLen, s->h_logprobs + (size_t)rr * kKvMaxLen, s->h_n_tokens[rr] + 1, s->h_sum_lp[rr], true});
+                        if ((int)cands.size() >= beam) break;
+                    }
+                }
+                const int P = prompt_len_of(w);
+                int best = 0; float best_rank = -INFINITY;
+                for (size_t i = 0; i < cands.size(); ++i) {
+                    const float rk = cands[i].score / (float)std::max(cands[i].len - P - 1, 1);
+                    if (i == 0 || rk > best_rank) { best = (int)i; best_rank = rk; }
+                }
+                const Cand& cd = cands[best];
+                const int body = cd.live ? cd.len - 1 : cd.len;      // live beams carry no EOT yet: finalize_result appends it
+                btok.assign(cd.tok, cd.tok + body); blp.assign(cd.lp, cd.lp + body);
+                seq_tok = btok.data(); seq_lp = blp.data(); seq_n = body;
+            }
+            finalize_result(r, seq_tok, seq_lp, seq_n, s->h_steps[r0], s->h_first_low[r0], st, &o, rung_temperature(o, rung));
+            if (s->h_error[r0]) {
+                set_error("window %d: no finite logit at decoder step %d", w, s->h_steps[r0] - 1);
                 fail_window(w, WK_ERR_DECODING_LOGITS_FAILED);
-            } else if (a.ladder && !stopped && r.needs_fallback && s->slot_try[q] < o.temperature_fallback_count) {
+            } else if (a.ladder && beam == 1 && !stopped && r.needs_fallback && s->slot_try[q] < o.temperature_fallback_count) {
                 // decodeWithFallback (TranscribeTask.swift:316-411): same encoder output (the slot keeps its cross K/V), next temperature
                 stage_admission(q, w, s->slot_try[q] + 1);
                 ++s->stats[3];
@@ -811,6 +917,8 @@ wk_status wk_session_set_encoder_output(wk_session* s, const wk_tensor* enc) {
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, T = c.n_audio_ctx;
     s->batch = (int)enc->batch;
+    s->bound_windows = s->batch;
+    s->bs.beam = 1;
     s->bp = round_up(s->batch, 16);
     // the encoder ran on the model stream; the projection reads its output on the session stream and the tensor remembers the reader
     std::lock_guard<std::mutex> lock(m->api_mu);
@@ -901,10 +1009,10 @@ wk_status wk_detect_language(wk_session* s, const wk_special_tokens* st, const i
 
 wk_status wk_decode_text_ex(wk_session* s, const wk_special_tokens* st, const wk_batch_opts* bo, wk_decode_result* results) {
     if (!s || !st || !bo || !bo->opts || bo->n_opts < 1 || !results) { set_error("wk_decode_text: null argument"); return WK_ERR_INVALID_ARGUMENT; }
-    if (s->batch < 1) { set_error("wk_decode_text: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
-    if (bo->n_opts != 1 && bo->n_opts != s->batch) { set_error("wk_decode_text: %d option sets for %d windows", bo->n_opts, s->batch); return WK_ERR_INVALID_ARGUMENT; }
+    if (s->bound_windows < 1) { set_error("wk_decode_text: no encoder output bound"); return WK_ERR_PREPARE_DECODER_INPUTS; }
+    if (bo->n_opts != 1 && bo->n_opts != s->bound_windows) { set_error("wk_decode_text: %d option sets for %d windows", bo->n_opts, s->bound_windows); return WK_ERR_INVALID_ARGUMENT; }
     WK_CUDA_CHECK(cudaSetDevice(s->m->device));
-    CoreArgs a{nullptr, s->batch, 0, nullptr, st, bo, results, false};
+    CoreArgs a{nullptr, s->bound_windows, 0, nullptr, st, bo, results, false};
     return transcribe_core(s, a);
 }
 
