@@ -63,6 +63,14 @@ def parse_args():
                     help="windows end at their own length: per-window sampleLength drawn (seeded) from a speech-like distribution instead of "
                          "the worst-case 223 steps for every window; with --windows > --batch the freed slots take the next windows")
     ap.add_argument("--encoder-chunk", type=int, default=0, help="windows per mel+encoder pass (default: the model's max_batch)")
+    ap.add_argument("--enc-batch", type=int, default=0, help="mel/encoder workspace size in windows (default: min(--batch, windows, 64))")
+    ap.add_argument("--beam", type=int, default=1, help="beam search width (BASELINE configs[2]: 5); --batch counts decode ROWS, windows in flight = batch / beam")
+    ap.add_argument("--longform", action="store_true",
+                    help="BASELINE configs[4] shape: long audio streams through wk_transcribe_streams (seek loop per stream, all streams share the "
+                         "GPU batches), word timestamps on; --streams per GPU, --stream-seconds each")
+    ap.add_argument("--streams", type=int, default=16)
+    ap.add_argument("--stream-seconds", type=float, default=300.0)
+    ap.add_argument("--no-word-timestamps", action="store_true")
     return ap.parse_args()
 
 
@@ -290,8 +298,10 @@ def run_own_arm(args):
     torch.cuda.set_device(local_rank)
     B = args.batch                       # decode slots per GPU
     W = args.windows or B                # windows per GPU per step
-    log(f"rank {rank}/{world}: creating model {args.variant} max_batch {B}")
-    model = wk.Model(args.variant, device=local_rank, max_batch=B, dtype=args.dtype)
+    beam = max(1, args.beam)
+    enc_batch = args.enc_batch or min(B, W, 64)
+    log(f"rank {rank}/{world}: creating model {args.variant}: encoder workspace {enc_batch} windows, {B} decode rows" + (f", beam {beam}" if beam > 1 else ""))
+    model = wk.Model(args.variant, device=local_rank, max_batch=enc_batch, dtype=args.dtype)
     model.init_random(seed=1234)
     dec = wk.TextDecoder(model, B)
     log("model + session ready; generating synthetic PCM")
@@ -300,7 +310,7 @@ def run_own_arm(args):
     st = special_tokens_for(info.vocab)
     # one greedy pass per window: with random-init weights avgLogProb is always below logProbThreshold, so the temperature
     # fallback ladder (retries, not part of the metric) is switched off; the CPU arm decodes one pass as well
-    base = dict(firstTokenLogProbThreshold=None, temperatureFallbackCount=0)
+    base = dict(firstTokenLogProbThreshold=None, temperatureFallbackCount=0, beamSize=beam)
     if args.eot_profile:
         lens = eot_profile_lengths(world * W)[rank * W:(rank + 1) * W]
         opts = [wk.DecodingOptions(sampleLength=int(v), **base) for v in lens]
@@ -333,24 +343,30 @@ def run_own_arm(args):
     # to its GPU, NCCL scatters shards over NVLink, every rank transcribes, NCCL gathers token IDs back to rank 0.
     e2e_stages = {}
     if world > 1:
+        # the edges run inside libwkb200 (csrc/comm.cu: ncclSend / ncclRecv); torch.distributed only carried the NCCL id
         from whisperkit_b200 import distributed as WD
+        comm = WD.Comm(lib, rank, world, local_rank)
         all_host = torch.from_numpy(synthetic_windows(0, world * W)).pin_memory() if rank == 0 else None
-        dev = torch.device("cuda", local_rank)
+        shard_dev = torch.empty(W, 480000, dtype=torch.float32, device=torch.device("cuda", local_rank))
+        all_res = (wk_decode_result * (world * W))() if rank == 0 else None
     d2h_bytes = W * (224 * 8 + 16)
 
     def step_e2e():
         if world == 1:
             transcribe(pcm_host.data_ptr(), W, res, bo)
             return
-
-        def local(shard):
-            torch.cuda.synchronize()  # NCCL ran on torch's stream; the library has its own
-            transcribe(shard.data_ptr(), shard.shape[0], res, bo)
-            return res
-
-        toks = WD.transcribe_sharded(all_host, world * W, 480000, dev, local, stages=e2e_stages)
+        t0 = time.perf_counter()
+        comm.scatter_windows(all_host.data_ptr() if rank == 0 else None, world * W, 480000, shard_dev.data_ptr())
+        t1 = time.perf_counter()
+        transcribe(shard_dev.data_ptr(), W, res, bo)
+        t2 = time.perf_counter()
+        comm.gather_results(res, W, world * W, all_res)
+        t3 = time.perf_counter()
+        for k, v in (("scatter_h2d_send", t1 - t0), ("transcribe", t2 - t1), ("gather_d2h", t3 - t2)):
+            e2e_stages[k] = e2e_stages.get(k, 0.0) + v * 1000.0
+        e2e_stages["_calls"] = e2e_stages.get("_calls", 0) + 1
         if rank == 0:
-            assert len(toks) == world * W
+            assert all_res[world * W - 1].n_tokens > 0
 
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
@@ -426,12 +442,17 @@ def run_own_arm(args):
         "e2e": {"value": e2e_value, "unit": "audio-sec/s", "h2d_bytes_per_step": world * W * 480000 * 4,
                 "d2h_bytes_per_step": world * d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                 "wall_ms_per_step": wall_e2e / args.steps,
-                "path": "wk_transcribe_windows_ex(host pinned PCM)" + (" + NCCL scatter/gather" if world > 1 else "")},
+                "path": "wk_transcribe_windows_ex(host pinned PCM)" if world == 1 else
+                        "wk_comm_scatter_windows (pinned host PCM on rank 0 -> ncclSend/ncclRecv) + wk_transcribe_windows_ex + wk_comm_gather_results"},
         "gpu_launches": launches,
         "clocks": clocks,
     }
-    if world > 1 and rank == 0 and e2e_stages:
-        line["e2e"]["stage_ms_rank0"] = {k: round(v / max(1, e2e_stages.get("_calls", 1)), 2) for k, v in e2e_stages.items() if k != "_calls"}
+    if world > 1 and e2e_stages:
+        mine = torch.tensor([e2e_stages.get(k, 0.0) / max(1, e2e_stages.get("_calls", 1)) for k in ("scatter_h2d_send", "transcribe", "gather_d2h")], device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        if rank == 0:   # host wall clock per stage and rank (warm-up call included): where the end-to-end time goes
+            line["e2e"]["stage_ms_per_rank"] = {k: [round(float(a[i]), 2) for a in allr] for i, k in enumerate(("scatter_h2d_send", "transcribe", "gather_d2h"))}
     assert sum(steps_run) <= expected_steps
 
     if rank == 0 and not args.no_roofline:
@@ -522,6 +543,140 @@ def run_own_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ long-form arm
+def synthetic_tokenizer(vocab: int, st):
+    """A byte-level vocabulary of Whisper's size for the word-timestamp path (splitToWordTokens needs token strings; no tokenizer files are
+    available offline): ids 0..255 the GPT-2 byte alphabet, then two-letter merges up to specialTokenBegin, then <|...|> specials."""
+    from whisperkit_b200.tokenizer import WhisperTokenizer
+    bs = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b); cs.append(256 + n); n += 1
+    alphabet = {b: chr(c) for b, c in zip(bs, cs)}
+    sb = st.specialTokenBegin
+    toks, ids, flags = [], [], []
+    for b in range(256):
+        toks.append(alphabet[b]); ids.append(b); flags.append(0)
+    letters = " etaoinshrdlucmfwypvbgkqjxz"
+    for i in range(256, sb):
+        a, c, e = letters[(i * 7) % len(letters)], letters[(i * 3 + 1) % len(letters)], letters[(i // 27) % len(letters)]
+        toks.append("".join(alphabet[ord(ch)] for ch in (a + c + e if i % 3 else a + c))); ids.append(i); flags.append(0)
+    names = {st.endToken: "<|endoftext|>", st.startOfTranscriptToken: "<|startoftranscript|>", st.englishToken: "<|en|>", st.translateToken: "<|translate|>",
+             st.transcribeToken: "<|transcribe|>", st.startOfPreviousToken: "<|startofprev|>", st.noSpeechToken: "<|nospeech|>",
+             st.noTimestampsToken: "<|notimestamps|>"}
+    for i in range(sb, vocab):
+        toks.append(names.get(i, f"<|{(i - st.timeTokenBegin) * 0.02:.2f}|>" if i >= st.timeTokenBegin else f"<|lang{i}|>")); ids.append(i); flags.append(3)
+    return WhisperTokenizer(tokens=toks, ids=ids, flags=flags)
+
+
+def run_longform_arm(args):
+    """BASELINE configs[4] shape on this rank's share: `--streams` long audio streams, each run through TranscribeTask.run's seek loop
+    (windows of one stream are sequentially dependent; the streams share the GPU batches), word timestamps on (alignment heads -> DTW ->
+    word timings on host threads).  One step = every stream transcribed once.  RTFx = audio seconds / time."""
+    import torch
+    import whisperkit_b200 as wk
+    from whisperkit_b200._lib import check, wk_segment
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    B = args.batch
+    model = wk.Model(args.variant, device=local_rank, max_batch=min(B, 64), dtype=args.dtype)
+    model.init_random(seed=1234)
+    dec = wk.TextDecoder(model, B)
+    lib, info = model.lib, model.info
+    st = special_tokens_for(info.vocab)
+    words = not args.no_word_timestamps
+    opts = wk.DecodingOptions(firstTokenLogProbThreshold=None, temperatureFallbackCount=0, sampleLength=args.sample_length, wordTimestamps=words,
+                              logProbThreshold=None, compressionRatioThreshold=None, noSpeechThreshold=None)
+    prompt = dec.prefillDecoderInputs(opts, st)
+    tok = synthetic_tokenizer(info.vocab, st) if words else None
+    hooks = tok.hooks() if words else None
+    n_samples = int(args.stream_seconds * 16000)
+    log(f"rank {rank}: generating {args.streams} synthetic streams of {args.stream_seconds:.0f} s")
+    base = synthetic_windows(rank * 8, 8).reshape(-1)
+    streams = []
+    for i in range(args.streams):
+        off = (i * 123457) % (len(base) - 16000)
+        x = np.concatenate([base[off:], base[:off]])
+        reps = int(np.ceil((n_samples + i * 8000) / len(x)))          # streams of slightly different lengths
+        streams.append(np.ascontiguousarray(np.tile(x, reps)[: n_samples + i * 8000], dtype=np.float32))
+    ptrs = (C.c_void_p * len(streams))(*[a.ctypes.data for a in streams])
+    lens = (C.c_int64 * len(streams))(*[len(a) for a in streams])
+    st_c = st.to_c()
+    o_c, keep = opts.to_c()
+    p_c = (C.c_int32 * len(prompt))(*prompt)
+    ext = torch.cuda.ExternalStream(model.stream, device=torch.device("cuda", local_rank))
+    stats = {}
+
+    def step():
+        h = C.c_void_p()
+        check(lib.wk_transcribe_streams(model.handle, dec.handle, ptrs, lens, len(streams), C.byref(st_c), C.byref(o_c), p_c, len(prompt), None, 0,
+                                        1.0, -1, 0, C.byref(hooks) if hooks is not None else None, C.byref(h)))
+        stats["windows"] = lib.wk_transcription_window_count(h)
+        stats["segments"] = lib.wk_transcription_segment_count(h)
+        stats["words"] = lib.wk_transcription_word_count(h)
+        lib.wk_transcription_free(h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    log("first (untimed) pass")
+    t0 = time.perf_counter()
+    step()
+    log(f"first pass {time.perf_counter() - t0:.2f} s: {stats}")
+    for _ in range(max(args.warmup, 3) - 1):
+        step()
+    barrier()
+    lib.wk_kernel_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as sampler:
+        e0.record(ext)
+        for _ in range(args.steps):
+            step()
+        e1.record(ext)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.wk_kernel_launch_count(0))
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    audio_s = world * sum(len(a) for a in streams) / 16000.0 * args.steps
+    value = audio_s / (ms / 1000.0)
+    name = "whisper-large-v3" if args.variant == "large-v3" else f"whisper-{args.variant}"
+    line = {
+        "metric": f"RTFx (audio-sec/s) {name} long-form" + (" word-timestamps" if words else ""),
+        "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": f"synthetic 16 kHz PCM streams, seeded random weights of the {args.variant} architecture, synthetic byte-level vocabulary of Whisper's size",
+        "config": {"workload": f"{name} long-form (BASELINE configs[4] shape, one GPU's share): {args.streams} streams x ~{args.stream_seconds:.0f} s per GPU through "
+                               f"wk_transcribe_streams (seek loop per stream, {B} decode slots shared by all streams), wordTimestamps={words}, "
+                               f"sampleLength={args.sample_length}, greedy, no temperature fallback; host PCM in, segments"
+                               + (" + word timings" if words else "") + " out (this IS the end-to-end path)",
+                   "streams_per_gpu": args.streams, "stream_seconds": args.stream_seconds, "decode_slots": B,
+                   "windows_decoded_per_step": stats["windows"], "segments": stats["segments"], "words": stats["words"],
+                   "l2": "inputs_larger_than_L2", "parallelism": f"dp{world} (streams sharded, weights replicated)"},
+        "e2e": {"value": value, "unit": "audio-sec/s", "h2d_bytes_per_step": int(stats["windows"]) * 480000 * 4 * world,
+                "d2h_bytes_per_step": int(stats["windows"]) * (224 * 8 + 16 + (224 * 1500 * 2 if words else 0)) * world, "ms_per_step": ms / args.steps,
+                "path": "wk_transcribe_streams(host PCM) - the long-form entry has no device-resident variant"},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+    }
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 _JSON_OUT = None
 
 
@@ -541,6 +696,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.longform:
+        run_longform_arm(args)
     else:
         run_own_arm(args)
 

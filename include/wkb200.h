@@ -330,6 +330,9 @@ void wk_transcription_free(wk_transcription* t);
 wk_status wk_model_set_alignment_heads(wk_model* m, const int32_t* layer_head_pairs, int32_t n_pairs);
 /* DecodingResult.cache.alignmentWeights of one window of the last wk_decode_text, first `rows` rows, as f32 [rows][n_audio_ctx]. */
 wk_status wk_session_alignment_weights(wk_session* s, int32_t window, int32_t rows, float* out);
+/* The same rows as stored, Float16 (FloatType): an asynchronous device-to-host copy on the session stream into out (pinned memory for it
+ * to be truly asynchronous); sync != 0 waits for it and for every copy queued before it. */
+wk_status wk_session_alignment_weights_f16(wk_session* s, int32_t window, int32_t rows, uint16_t* out, int32_t sync);
 
 struct wk_word {                   /* WordTiming (Models.swift:617-633) */
     const char* word;              /* UTF-8, NUL-terminated */

@@ -4,6 +4,7 @@
 out=gpurun_out/${1:-stage}
 mkdir -p $out
 export PYTHONUNBUFFERED=1
+python -m whisperkit_b200.build > $out/build.log 2>&1   # no-op when the shipped .so matches the sources
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $out/gpu.txt 2>&1
 (time WKB200_FUSED=0 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -s) > $out/pytest_unfused.log 2>&1
 echo "unfused rc $?" >> $out/summary.txt

@@ -173,6 +173,7 @@ SYMBOLS = [
     ("wk_transcription_free", None, [P]),
     ("wk_model_set_alignment_heads", I32, [P, PI32, I32]),
     ("wk_session_alignment_weights", I32, [P, I32, I32, P]),
+    ("wk_session_alignment_weights_f16", I32, [P, I32, I32, P, I32]),
     ("wk_words_count", I32, [P]),
     ("wk_words_get", I32, [P, I32, C.POINTER(wk_word)]),
     ("wk_words_free", None, [P]),

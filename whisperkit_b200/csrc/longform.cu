@@ -9,6 +9,10 @@
 
 #include <algorithm>
 #include <string>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -252,6 +256,63 @@ struct Unit {                 // one independently advancing cursor: a stream, o
 };
 }  // namespace
 
+namespace {
+constexpr int kRoundCap = 256;   // windows per round of the stream loop (host staging: 256 x 1.92 MB pinned)
+
+// pinned host staging, kept for the life of the thread that transcribes (allocation of half a gigabyte of pinned memory costs ~0.1 s)
+struct HostStage {
+    float* pcm = nullptr; size_t pcm_bytes = 0;
+    uint16_t* align = nullptr; size_t align_bytes = 0;
+    wk_status ensure(size_t need_pcm, size_t need_align) {
+        if (need_pcm > pcm_bytes) {
+            if (pcm) cudaFreeHost(pcm);
+            pcm = nullptr; pcm_bytes = 0;
+            if (cudaHostAlloc((void**)&pcm, need_pcm, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("pinned staging of %zu bytes failed", need_pcm); return WK_ERR_CUDA; }
+            pcm_bytes = need_pcm;
+        }
+        if (need_align > align_bytes) {
+            if (align) cudaFreeHost(align);
+            align = nullptr; align_bytes = 0;
+            if (cudaHostAlloc((void**)&align, need_align, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("pinned staging of %zu bytes failed", need_align); return WK_ERR_CUDA; }
+            align_bytes = need_align;
+        }
+        return WK_OK;
+    }
+    ~HostStage() { if (pcm) cudaFreeHost(pcm); if (align) cudaFreeHost(align); }
+};
+HostStage& host_stage() { static thread_local HostStage hs; return hs; }
+
+// fn(i) for i in [0, n) on up to n_threads host threads; the first failing status wins, its thread-local message is handed back
+template <typename F>
+wk_status parallel_for(int n, int n_threads, F fn, std::string* err) {
+    if (n <= 0) return WK_OK;
+    const int nt = std::max(1, std::min(n_threads, n));
+    if (nt == 1) {
+        for (int i = 0; i < n; ++i) { wk_status r = fn(i); if (r != WK_OK) { if (err) *err = wk_last_error(); return r; } }
+        return WK_OK;
+    }
+    std::atomic<int> next{0};
+    std::atomic<int> status{WK_OK};
+    std::mutex mu;
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n || status.load() != WK_OK) return;
+            const wk_status r = fn(i);
+            if (r != WK_OK) {
+                std::lock_guard<std::mutex> lock(mu);
+                if (status.load() == WK_OK) { status.store(r); if (err) *err = wk_last_error(); }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    return (wk_status)status.load();
+}
+}  // namespace
+
 extern "C" {
 
 wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* audio, const int64_t* n_samples, int32_t n_streams,
@@ -297,54 +358,77 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
         }
     }
     wk_transcription* T = new wk_transcription();
-    std::vector<float> batch((size_t)max_batch * kWindow);
-    std::vector<int32_t> valid(max_batch);
-    std::vector<wk_decode_result> res(max_batch);
+    // One round = the next window of EVERY unfinished unit (up to kRoundCap): the window scheduler behind wk_transcribe_windows keeps the
+    // session's decode slots full and runs the mel + encoder pass of the following windows under the running decode, so a round is not
+    // limited to one slot-load.  Host staging is pinned and kept across calls; the per-window host work that follows a round (segment
+    // search, DTW, word timing) runs on a pool of host threads.
+    const int round_cap = std::max(max_batch, kRoundCap);
+    HostStage& hs = host_stage();
+    rc = hs.ensure((size_t)round_cap * kWindow * sizeof(float), o->word_timestamps ? (size_t)round_cap * info.kv_max_len * info.n_audio_ctx * 2 : 0);
+    if (rc != WK_OK) { delete T; return rc; }
+    float* batch = hs.pcm;
+    std::vector<int32_t> valid(round_cap);
+    std::vector<wk_decode_result> res(round_cap);
     std::vector<int> active;
     std::vector<std::vector<int32_t>> unit_tokens(units.size());
     std::vector<std::vector<float>> unit_lps(units.size());
+    const int n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     for (;;) {
         active.clear();
-        for (size_t i = 0; i < units.size() && (int)active.size() < max_batch; ++i)
+        for (size_t i = 0; i < units.size() && (int)active.size() < round_cap; ++i)
             if (!units[i].done) active.push_back((int)i);
         if (active.empty()) break;
         std::vector<int64_t> seg_size(active.size());
-        for (size_t k = 0; k < active.size(); ++k) {
+        parallel_for((int)active.size(), n_threads, [&](int k) {
             Unit& u = units[active[k]];
             const int64_t clip_end = u.clips[2 * u.clip + 1];
             const int64_t sz = std::min<int64_t>({kWindow, u.n - u.seek, clip_end - u.seek});   // TranscribeTask.swift:121
             seg_size[k] = sz;
             valid[k] = (int32_t)sz;
-            float* dst = batch.data() + k * kWindow;
-            memcpy(dst, u.audio + u.seek, (size_t)sz * sizeof(float));   // padOrTrim (zero fill happens in the mel kernel via `valid`)
-        }
-        rc = wk_transcribe_windows(m, s, batch.data(), (int64_t)active.size(), kWindow, valid.data(), st, o, prompt, n_prompt, res.data());
+            memcpy(batch + (size_t)k * kWindow, u.audio + u.seek, (size_t)sz * sizeof(float));   // padOrTrim (zero fill happens in the mel kernel via `valid`)
+            return WK_OK;
+        }, nullptr);
+        rc = wk_transcribe_windows(m, s, batch, (int64_t)active.size(), kWindow, valid.data(), st, o, prompt, n_prompt, res.data());
         if (rc != WK_OK) { delete T; return rc; }
         T->windows += (int)active.size();
-        for (size_t k = 0; k < active.size(); ++k) {
+        const int cols = info.n_audio_ctx;
+        if (o->word_timestamps) {   // every window's alignment rows back in one burst (Float16, as the reference's alignmentWeights)
+            for (size_t k = 0; k < active.size(); ++k) {
+                const int have = std::min(res[k].n_tokens, info.kv_max_len);
+                rc = wk_session_alignment_weights_f16(s, (int32_t)k, have, hs.align + (size_t)k * info.kv_max_len * cols, k + 1 == active.size() ? 1 : 0);
+                if (rc != WK_OK) { delete T; return rc; }
+            }
+        }
+        std::string worker_error;
+        rc = parallel_for((int)active.size(), n_threads, [&](int k) -> wk_status {
             Unit& u = units[active[k]];
             const wk_decode_result& r = res[k];
+            wk_status rc2;
             wk_segment segs[128];
             int nseg = 0;
             int64_t new_seek = u.seek;
-            rc = wk_find_seek_point_and_segments(r.tokens, r.token_logprobs, r.n_tokens, 0.f, r.avg_logprob, r.compression_ratio, r.temperature, o,
-                                                 (int32_t)u.segs.size(), u.seek, seg_size[k], kSampleRate, st->time_token_begin, &new_seek, segs, 128, &nseg);
-            if (rc != WK_OK) { delete T; return rc; }
+            rc2 = wk_find_seek_point_and_segments(r.tokens, r.token_logprobs, r.n_tokens, 0.f, r.avg_logprob, r.compression_ratio, r.temperature, o,
+                                                  (int32_t)u.segs.size(), u.seek, seg_size[k], kSampleRate, st->time_token_begin, &new_seek, segs, 128, &nseg);
+            if (rc2 != WK_OK) return rc2;
             const int64_t prev = u.seek;
             u.seek = std::max(u.seek, new_seek);
             if (max_window_seek >= 0) u.seek = std::min(u.seek, prev + max_window_seek);
             std::vector<OutWord> new_words;
             if (o->word_timestamps) {
                 // addWordTimestamps on this window (TranscribeTask.swift:197-239): rows = window tokens, zero rows past the tensor's 224
-                const int cols = info.n_audio_ctx, n_tok = r.n_tokens, have = std::min(n_tok, info.kv_max_len);
-                std::vector<float> align((size_t)std::max(n_tok, 1) * cols, 0.f);
-                rc = wk_session_alignment_weights(s, (int32_t)k, have, align.data());
-                if (rc != WK_OK) { delete T; return rc; }
+                const int n_tok = r.n_tokens, have = std::min(n_tok, info.kv_max_len);
+                const uint16_t* rows16 = hs.align + (size_t)k * info.kv_max_len * cols;
+                std::vector<uint16_t> padded;
+                if (n_tok > have || n_tok < 1) {   // (226-token results: the rows past the tensor read as zeros)
+                    padded.assign((size_t)std::max(n_tok, 1) * cols, 0);
+                    memcpy(padded.data(), rows16, (size_t)have * cols * 2);
+                    rows16 = padded.data();
+                }
                 wk_words* wh = nullptr;
                 const int n_in = std::max(nseg, 0);
-                rc = wk_add_word_timestamps(segs, n_in, r.tokens, r.token_logprobs, align.data(), WK_DTYPE_F32, std::max(n_tok, 1), cols, cols, hooks, prev,
-                                            (float)((double)prev / (double)kSampleRate), st->special_token_begin, nullptr, nullptr, &wh);
-                if (rc != WK_OK) { delete T; return rc; }
+                rc2 = wk_add_word_timestamps(segs, n_in, r.tokens, r.token_logprobs, rows16, WK_DTYPE_F16, std::max(n_tok, 1), cols, cols, hooks, prev,
+                                             (float)((double)prev / (double)kSampleRate), st->special_token_begin, nullptr, nullptr, &wh);
+                if (rc2 != WK_OK) return rc2;
                 // drop zero-length segments (:214), remap the words' segment index, and let the last word end pull the seek forward (:217-219)
                 std::vector<int> remap((size_t)n_in, -1);
                 int kept = 0;
@@ -384,7 +468,9 @@ wk_status wk_transcribe_streams(wk_model* m, wk_session* s, const float* const* 
                 ++u.clip;
                 u.seek = u.clips[2 * u.clip];
             }
-        }
+            return WK_OK;
+        }, &worker_error);
+        if (rc != WK_OK) { set_error("%s", worker_error.c_str()); delete T; return rc; }
     }
     // flatten: streams in order, units (chunks) in order, chunk offsets applied (updateSegmentTimings, AudioChunker.swift:14-39)
     std::vector<int> next_id(n_streams, 0);

@@ -1066,6 +1066,17 @@ wk_status wk_session_alignment_weights(wk_session* s, int32_t window, int32_t ro
     return WK_OK;
 }
 
+wk_status wk_session_alignment_weights_f16(wk_session* s, int32_t window, int32_t rows, uint16_t* out, int32_t sync) {
+    if (!s || !out || window < 0 || rows < 0 || rows > kKvMaxLen) { set_error("wk_session_alignment_weights_f16: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    if (!s->align_on || !s->align_store || window >= s->align_store_n) { set_error("wk_session_alignment_weights_f16: the last decode did not ask for word timestamps (or window %d is outside it)", window); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(s->m->device));
+    const size_t T = s->m->cfg.n_audio_ctx;
+    if (rows > 0)
+        WK_CUDA_CHECK(cudaMemcpyAsync(out, (const __half*)s->align_store + (size_t)window * kKvMaxLen * T, (size_t)rows * T * 2, cudaMemcpyDeviceToHost, s->stream));
+    if (sync) WK_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    return WK_OK;
+}
+
 // Average device time (ms) of one launch of a named hot kernel on the session's buffers (CUDA events on the stream the kernel runs on;
 // decoder-side kernels are replayed `iters` times as one CUDA graph so that host launch cost stays out, as in the real step):
 //   0 decoder cross-attention (one layer, `batch` live rows)      1 encoder FC1+GELU GEMM (M = batch*1500)   2 log-mel

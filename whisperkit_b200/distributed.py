@@ -184,3 +184,43 @@ def transcribe_streams_sharded(audio_arrays: list, device, transcribe_local: Cal
     for b in bufs:
         merged.update(unpack_segments(b))
     return [merged.get(i, []) for i in range(len(audio_arrays))]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# The same edges through the library's own C ABI (csrc/comm.cu: ncclSend / ncclRecv issued by libwkb200, no torch tensors in the data
+# path) - what a Swift host would call.  torch.distributed is only the rendezvous that carries the 128-byte NCCL id to the other ranks.
+# ---------------------------------------------------------------------------------------------------------------------------------
+class Comm:
+    def __init__(self, lib, rank: int, world: int, device_index: int):
+        import ctypes as C
+        self.lib, self.rank, self.world = lib, rank, world
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            from ._lib import check
+            check(lib.wk_comm_unique_id(ident))
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=torch.device("cuda", device_index))
+        dist.broadcast(t, src=0)
+        ident = (C.c_uint8 * 128)(*[int(v) for v in t.cpu()])
+        self.handle = C.c_void_p()
+        from ._lib import check
+        check(lib.wk_comm_create(ident, rank, world, device_index, C.byref(self.handle)))
+
+    def shard_bounds(self, n_windows: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        return shard_bounds(n_windows, self.world, self.rank if rank is None else rank)
+
+    def scatter_windows(self, all_pcm_ptr: Optional[int], n_windows: int, stride: int, shard_ptr: int, root: int = 0) -> int:
+        """all_pcm_ptr: address of [n_windows][stride] f32 on the root (host pinned or device), ignored elsewhere; shard_ptr: device buffer."""
+        import ctypes as C
+        from ._lib import check
+        n_local = C.c_int64()
+        check(self.lib.wk_comm_scatter_windows(self.handle, C.c_void_p(all_pcm_ptr or 0), n_windows, stride, root, C.c_void_p(shard_ptr), C.byref(n_local)))
+        return int(n_local.value)
+
+    def gather_results(self, local_results, n_local: int, n_windows: int, all_results=None, root: int = 0) -> None:
+        from ._lib import check
+        check(self.lib.wk_comm_gather_results(self.handle, local_results, n_local, n_windows, root, all_results))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.wk_comm_free(self.handle)
+            self.handle = None

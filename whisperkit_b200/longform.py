@@ -141,7 +141,7 @@ class VADAudioChunker:
 
 def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional[DecodingOptions] = None,
                        clipTimestamps: Sequence[float] = (), windowClipTime: float = 1.0, maxWindowSeek: Optional[int] = None,
-                       chunkingStrategy: Optional[str] = None, split_to_word_tokens=None, decode=None):
+                       chunkingStrategy: Optional[str] = None, split_to_word_tokens=None, decode=None, hooks=None):
     """TranscribeTask.run's seek loop for many audio arrays at once (TranscribeTask.swift:98-279; `chunkingStrategy="vad"`
     = WhisperKit.swift:878-911).  Returns (segments per stream, number of 30 s windows decoded)."""
     opts = kit.resolveLanguage(options or DecodingOptions())   # DecodingOptions.language -> <|xx|> through the tokenizer
@@ -157,10 +157,12 @@ def transcribe_streams(kit, audioArrays: Sequence[np.ndarray], options: Optional
     ts = (C.c_float * max(1, n))(*[float(v) for v in clipTimestamps])
     h = C.c_void_p()
     from .wordtiming import WordTiming, make_hooks
-    hooks, keep_hooks = make_hooks(split_to_word_tokens, decode)
+    native = hooks                      # a wk_tokenizer_hooks struct (WhisperTokenizer.hooks()): the library's own tokenizer, no host callbacks
+    if native is None:
+        hooks, keep_hooks = make_hooks(split_to_word_tokens, decode)
     check(lib.wk_transcribe_streams(kit.model.handle, kit.textDecoder.handle, ptrs, lens, len(arrs), C.byref(st), C.byref(o), p, len(prompt),
                                     ts, n, windowClipTime, -1 if maxWindowSeek is None else maxWindowSeek,
-                                    1 if chunkingStrategy == "vad" else 0, C.byref(hooks) if split_to_word_tokens is not None else None,
+                                    1 if chunkingStrategy == "vad" else 0, C.byref(hooks) if (split_to_word_tokens is not None or native is not None) else None,
                                     C.byref(h)))
     try:
         ns, nt = lib.wk_transcription_segment_count(h), lib.wk_transcription_token_count(h)
@@ -200,13 +202,12 @@ def transcribe_audio(kit, audioArrays: Sequence[np.ndarray], options: Optional[D
     filled the way the reference does it (segment text: SegmentSeeker.swift:118-121,160-165 - all tokens unless skipSpecialTokens;
     result text: TranscribeTask.finalizeTranscriptionResult, :299-311 - text tokens only, trimmed) and word timestamps need no callbacks."""
     opts = options or DecodingOptions()
-    split = decode = None
-    if tokenizer is not None:
-        split, decode = tokenizer.splitToWordTokens, tokenizer.decode
-    elif opts.wordTimestamps:
+    if tokenizer is None and opts.wordTimestamps:
         raise _lib.WhisperError(-1, "wordTimestamps needs a tokenizer")
+    native = tokenizer.hooks() if (tokenizer is not None and opts.wordTimestamps and hasattr(tokenizer, "hooks")) else None
+    split = tokenizer.splitToWordTokens if (tokenizer is not None and opts.wordTimestamps and native is None) else None
     per_stream, windows = transcribe_streams(kit, audioArrays, opts, clipTimestamps=clipTimestamps, chunkingStrategy=chunkingStrategy,
-                                             split_to_word_tokens=split if opts.wordTimestamps else None, decode=decode)
+                                             split_to_word_tokens=split, decode=tokenizer.decode if split is not None else None, hooks=native)
     sb = kit.specialTokens.specialTokenBegin
     out = []
     for segs in per_stream:
