@@ -55,10 +55,6 @@ def test_beam_search_matches_the_oracle_on_gpu_logits(variant, policy, beam, pat
         np.testing.assert_allclose(res[b].tokenLogProbs, ref.tokenLogProbs, atol=2e-4)
         assert abs(res[b].avgLogProb - ref.avgLogProb) < 2e-4 and res[b].steps == ref.steps
         differs += res[b].tokens != greedy[b].tokens
-        # the beam result is at least as likely as the greedy one under the ranking rule (sum of log-probs / sampled tokens)
-        rank = lambda r: sum(r.tokenLogProbs) / max(len(r.tokens) - len(prompt) - 1, 1)   # noqa: E731
-        if res[b].tokens[-1] == st.endToken and greedy[b].tokens[-1] == st.endToken and len(res[b].tokens) == len(greedy[b].tokens):
-            assert rank(res[b]) >= rank(greedy[b]) - 1e-4
     print(f"[{variant}/{policy} beam {beam} patience {patience}] windows whose beam result differs from greedy: {differs} of {n_win}")
 
 

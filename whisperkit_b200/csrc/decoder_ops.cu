@@ -275,155 +275,124 @@ wk_status decoder_reduce_bias_gelu(const float* partial, int splits, int Bp, con
 }
 
 // =====================================================================================================
-// self attention for one new token: warp per (b, h); reduces q/k/v partials, appends K/V in place in the
-// device cache (replaces the host-side updateKVCache splice), attends over positions 0..pos
-// cache layout [B][H][max_len][64]
+// self attention for one new token: one CTA (4 warps) per (b, h).  Warp 0 reduces the q/k/v split-K partials and appends K/V in place
+// in the device cache (replaces the host-side updateKVCache splice); the cached positions are then split over the 4 warps - 8 lanes
+// per 128-byte row, 4 rows per warp instruction, several instructions in flight - so that B*H*4 warps keep enough loads in the air
+// for what is a latency-bound gather (<= 223 rows of K and of V per head).  cache layout [B][H][max_len][64]
 // =====================================================================================================
-template <typename T>
+template <typename T, bool kAnc>
 __global__ void __launch_bounds__(128)
 decoder_self_attention_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
                               const float* __restrict__ bv, T* __restrict__ kcache, T* __restrict__ vcache,
                               const int32_t* __restrict__ pos_ptr, const int32_t* __restrict__ done,
                               T* __restrict__ out, int B, int H, int max_len, const int32_t* __restrict__ anc) {
-    __shared__ float sq[4][64];
-    __shared__ float skc[4][64];
-    __shared__ float svc[4][64];
-    __shared__ float sp[4][kMaxCtx];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x * 4 + warp;
+    __shared__ float sq[64], skc[64], svc[64];
+    __shared__ float sp[kMaxCtx];
+    __shared__ float red[4][64];
+    __shared__ float sstat[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bh = blockIdx.x, b = bh / H, h = bh % H;
     pdl_launch_dependents();
     pdl_wait();
-    if (bh >= B * H) return;
-    const int b = bh / H, h = bh % H;
     if (done != nullptr && done[b]) return;   // ended window: no cache traffic
     const int dm = H * 64;
     const int pos = pos_ptr[b];
-    const int e = 2 * lane;
-    float2 q = make_float2(bq[h * 64 + e], bq[h * 64 + e + 1]);
-    float2 k = make_float2(0.f, 0.f);
-    float2 v = make_float2(bv[h * 64 + e], bv[h * 64 + e + 1]);
-    for (int s = 0; s < splits; ++s) {
-        const float* pr = partial + ((long long)s * Bp + b) * (3LL * dm) + h * 64 + e;
-        const float2 pq = *reinterpret_cast<const float2*>(pr);
-        const float2 pk = *reinterpret_cast<const float2*>(pr + dm);
-        const float2 pv = *reinterpret_cast<const float2*>(pr + 2 * dm);
-        q.x += pq.x; q.y += pq.y; k.x += pk.x; k.y += pk.y; v.x += pv.x; v.y += pv.y;
-    }
-    // append to the cache (16-bit rounding is part of the precision policy)
-    T* krow = kcache + ((long long)bh * max_len + pos) * 64;
-    T* vrow = vcache + ((long long)bh * max_len + pos) * 64;
-    const uint32_t k16 = T16<T>::pack2(k.x, k.y), v16 = T16<T>::pack2(v.x, v.y);
-    *reinterpret_cast<uint32_t*>(krow + e) = k16;
-    *reinterpret_cast<uint32_t*>(vrow + e) = v16;
-    const float2 kr = T16<T>::unpack2(k16), vr = T16<T>::unpack2(v16);
-    sq[warp][e] = q.x; sq[warp][e + 1] = q.y;
-    skc[warp][e] = kr.x; skc[warp][e + 1] = kr.y;
-    svc[warp][e] = vr.x; svc[warp][e + 1] = vr.y;
-    __syncwarp();
-    // scores: lane handles keys lane, lane+32, ...; the cache row of key i+1 is fetched while key i is reduced (double-buffered
-    // registers), and the first V tile is put in flight before any of it: the kernel is latency-bound, not bandwidth-bound
-    const int sub = lane & 7, rsel = lane >> 3;
     // cache row of position t: this sequence's own row, or (beam search) the row of the ancestor beam that produced position t
-    const int32_t* arow = anc ? anc + (long long)b * max_len : nullptr;
-    auto row_of = [&](int t) -> long long { return ((long long)(arow ? arow[t] : b) * H + h) * max_len + t; };
-    const T* vb = vcache + sub * 8;
-    uint4 u[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int t = 4 * j + rsel;
-        u[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + row_of(t) * 64) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    float smax = -INFINITY;
-    float sc[7];
-    uint4 kbuf[2][8];
-    {
-        const uint4* kp = reinterpret_cast<const uint4*>(kcache + (lane < pos ? row_of(lane) : 0) * 64);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) kbuf[0][c] = (lane < pos) ? kp[c] : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        const int t = lane + 32 * i;
-        if (i + 1 < 7) {
-            const int tn = t + 32;
-            const uint4* kp = reinterpret_cast<const uint4*>(kcache + (tn < pos ? row_of(tn) : 0) * 64);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) kbuf[(i + 1) & 1][c] = (tn < pos) ? kp[c] : make_uint4(0u, 0u, 0u, 0u);
+    const int32_t* arow = kAnc ? anc + (long long)b * max_len : nullptr;
+    const long long own = (long long)bh * max_len;
+    auto row_of = [&](int t) -> long long { return kAnc ? ((long long)arow[t] * H + h) * max_len + t : own + t; };
+    if (warp == 0) {
+        const int e = 2 * lane;
+        float2 q = make_float2(bq[h * 64 + e], bq[h * 64 + e + 1]);
+        float2 k = make_float2(0.f, 0.f);
+        float2 v = make_float2(bv[h * 64 + e], bv[h * 64 + e + 1]);
+        for (int s = 0; s < splits; ++s) {
+            const float* pr = partial + ((long long)s * Bp + b) * (3LL * dm) + h * 64 + e;
+            const float2 pq = *reinterpret_cast<const float2*>(pr);
+            const float2 pk = *reinterpret_cast<const float2*>(pr + dm);
+            const float2 pv = *reinterpret_cast<const float2*>(pr + 2 * dm);
+            q.x += pq.x; q.y += pq.y; k.x += pk.x; k.y += pk.y; v.x += pv.x; v.y += pv.y;
         }
-        sc[i] = -INFINITY;
-        if (t <= pos) {
-            float acc = 0.f;
-            if (t == pos) {
-#pragma unroll 16
-                for (int j = 0; j < 64; ++j) acc += sq[warp][j] * skc[warp][j];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 kv = kbuf[i & 1][c];
-                    const float2 a0 = T16<T>::unpack2(kv.x), a1 = T16<T>::unpack2(kv.y), a2 = T16<T>::unpack2(kv.z), a3 = T16<T>::unpack2(kv.w);
-                    const float* qq = &sq[warp][c * 8];
-                    acc += qq[0] * a0.x + qq[1] * a0.y + qq[2] * a1.x + qq[3] * a1.y + qq[4] * a2.x + qq[5] * a2.y + qq[6] * a3.x + qq[7] * a3.y;
-                }
-            }
-            sc[i] = acc * 0.125f;
-            smax = fmaxf(smax, sc[i]);
-        }
+        // append to the cache (16-bit rounding is part of the precision policy); the new row always goes to the sequence's own cache row
+        const uint32_t k16 = T16<T>::pack2(k.x, k.y), v16 = T16<T>::pack2(v.x, v.y);
+        *reinterpret_cast<uint32_t*>(kcache + (own + pos) * 64 + e) = k16;
+        *reinterpret_cast<uint32_t*>(vcache + (own + pos) * 64 + e) = v16;
+        const float2 kr = T16<T>::unpack2(k16), vr = T16<T>::unpack2(v16);
+        sq[e] = q.x; sq[e + 1] = q.y;
+        skc[e] = kr.x; skc[e + 1] = kr.y;
+        svc[e] = vr.x; svc[e + 1] = vr.y;
+        const float self = warp_sum(q.x * kr.x + q.y * kr.y);   // the current position's score comes from registers
+        if (lane == 0) sp[pos] = self * 0.125f;
     }
-    smax = warp_max(smax);
-    float ssum = 0.f;
+    __syncthreads();
+    const int sub = lane & 7, rsel = lane >> 3;   // 16-byte piece of the 128-byte row / row within a group of 4
+    float qv[8];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        const int t = lane + 32 * i;
-        if (t <= pos) {
-            const float p = __expf(sc[i] - smax);
-            sp[warp][t] = p;
-            ssum += p;
+    for (int j = 0; j < 8; ++j) qv[j] = sq[sub * 8 + j];
+    // ---- scores over the cached positions: warp w takes rows 16 i + 4 w + rsel
+    const T* kb = kcache + sub * 8;
+#pragma unroll 4
+    for (int t0 = warp * 4; t0 < pos; t0 += 16) {
+        const int t = t0 + rsel;
+        float acc = 0.f;
+        if (t < pos) {
+            const uint4 u = *reinterpret_cast<const uint4*>(kb + row_of(t) * 64);
+            const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+            acc = qv[0] * a0.x + qv[1] * a0.y + qv[2] * a1.x + qv[3] * a1.y + qv[4] * a2.x + qv[5] * a2.y + qv[6] * a3.x + qv[7] * a3.y;
         }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (sub == 0 && t < pos) sp[t] = acc * 0.125f;
     }
-    ssum = warp_sum(ssum);
-    __syncwarp();
-    // output: 16-byte loads, 4 cache rows per warp instruction, 8 instructions in flight: lane = (row % 4, 8-dim chunk); the next
-    // tile of 32 rows is fetched while the current one is accumulated
+    __syncthreads();
+    // ---- softmax over positions 0..pos
+    float mx = -INFINITY;
+    for (int t = tid; t <= pos; t += 128) mx = fmaxf(mx, sp[t]);
+    mx = warp_max(mx);
+    if (lane == 0) sstat[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(sstat[0], sstat[1]), fmaxf(sstat[2], sstat[3]));
+    float sm = 0.f;
+    for (int t = tid; t <= pos; t += 128) {
+        const float pr = __expf(sp[t] - mx);
+        sp[t] = pr;
+        sm += pr;
+    }
+    sm = warp_sum(sm);
+    if (lane == 0) sstat[4 + warp] = sm;
+    __syncthreads();
+    const float inv = 1.f / (sstat[4] + sstat[5] + sstat[6] + sstat[7]);
+    // ---- output: sum_t p[t] V[t]
     float o8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o8[j] = 0.f;
-    for (int t0 = 0; t0 < pos; t0 += 32) {
-        uint4 un[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int t = t0 + 32 + 4 * j + rsel;
-            un[j] = (t < pos) ? *reinterpret_cast<const uint4*>(vb + row_of(t) * 64) : make_uint4(0u, 0u, 0u, 0u);
+    const T* vb = vcache + sub * 8;
+#pragma unroll 4
+    for (int t0 = warp * 4; t0 < pos; t0 += 16) {
+        const int t = t0 + rsel;
+        if (t < pos) {
+            const float pr = sp[t];
+            const uint4 u = *reinterpret_cast<const uint4*>(vb + row_of(t) * 64);
+            const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+            o8[0] += pr * a0.x; o8[1] += pr * a0.y; o8[2] += pr * a1.x; o8[3] += pr * a1.y;
+            o8[4] += pr * a2.x; o8[5] += pr * a2.y; o8[6] += pr * a3.x; o8[7] += pr * a3.y;
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int t = t0 + 4 * j + rsel;
-            const float p = (t < pos) ? sp[warp][t] : 0.f;
-            const float2 a0 = T16<T>::unpack2(u[j].x), a1 = T16<T>::unpack2(u[j].y), a2 = T16<T>::unpack2(u[j].z), a3 = T16<T>::unpack2(u[j].w);
-            o8[0] += p * a0.x; o8[1] += p * a0.y; o8[2] += p * a1.x; o8[3] += p * a1.y;
-            o8[4] += p * a2.x; o8[5] += p * a2.y; o8[6] += p * a3.x; o8[7] += p * a3.y;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = un[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         o8[j] += __shfl_xor_sync(0xffffffffu, o8[j], 8);
         o8[j] += __shfl_xor_sync(0xffffffffu, o8[j], 16);
     }
-    // the current position comes from registers/smem (its cache row was written by this warp just above)
-    {
-        const float p = sp[warp][pos];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] += p * svc[warp][sub * 8 + j];
-    }
-    const float inv = 1.f / ssum;
     if (rsel == 0) {
-        uint4 pk;
-        pk.x = T16<T>::pack2(o8[0] * inv, o8[1] * inv);
-        pk.y = T16<T>::pack2(o8[2] * inv, o8[3] * inv);
-        pk.z = T16<T>::pack2(o8[4] * inv, o8[5] * inv);
-        pk.w = T16<T>::pack2(o8[6] * inv, o8[7] * inv);
-        *reinterpret_cast<uint4*>(out + (long long)b * dm + h * 64 + sub * 8) = pk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][sub * 8 + j] = o8[j];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        // the current position comes from shared memory (its cache row was written by this CTA just above)
+        const float o = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid] + sp[pos] * svc[tid];
+        out[(long long)b * dm + h * 64 + tid] = T16<T>::from_f(o * inv);
     }
 }
 
@@ -431,11 +400,14 @@ wk_status decoder_self_attention(const float* partial, int splits, int Bp, const
                                  void* vcache, const int32_t* pos, const int32_t* done, void* out, int B, int H,
                                  int max_len, int dtype, cudaStream_t stream, const int32_t* anc) {
     if (max_len > kMaxCtx) { set_error("decoder_self_attention: max_len %d > %d", max_len, kMaxCtx); return WK_ERR_INVALID_ARGUMENT; }
-    const unsigned grid = (unsigned)((B * H + 3) / 4);
-    if (dtype == WK_DTYPE_F16)
-        launch_k(decoder_self_attention_kernel<__half>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, pos, done, (__half*)out, B, H, max_len, anc);
-    else
-        launch_k(decoder_self_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, pos, done, (__nv_bfloat16*)out, B, H, max_len, anc);
+    const unsigned grid = (unsigned)(B * H);
+    if (dtype == WK_DTYPE_F16) {
+        if (anc) launch_k(decoder_self_attention_kernel<__half, true>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, pos, done, (__half*)out, B, H, max_len, anc);
+        else launch_k(decoder_self_attention_kernel<__half, false>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__half*)kcache, (__half*)vcache, pos, done, (__half*)out, B, H, max_len, anc);
+    } else {
+        if (anc) launch_k(decoder_self_attention_kernel<__nv_bfloat16, true>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, pos, done, (__nv_bfloat16*)out, B, H, max_len, anc);
+        else launch_k(decoder_self_attention_kernel<__nv_bfloat16, false>, dim3(grid), dim3(128), 0, stream, 2, partial, splits, Bp, bq, bv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, pos, done, (__nv_bfloat16*)out, B, H, max_len, anc);
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decoder_self_attention launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
@@ -475,13 +447,15 @@ decoder_cross_attention_kernel(const float* __restrict__ partial, int splits, in
     const int chunks = Tlen / kCrossRows;  // per K and per V
     pdl_launch_dependents();
     // ended window: skip its 2 x 192 KB K/V stream.  done[] was written by the sampler of the previous step, many kernels upstream, so it
-    // may be read before griddepcontrol.wait; the wait itself still runs so that this grid never completes before its upstream does
-    if (done != nullptr && done[b]) { pdl_wait(); return; }
+    // may be read before griddepcontrol.wait; the load is issued here and consumed after the barrier set-up so that its latency hides
+    // under it (the CTA lives ~8 us: a dependent L2 round trip at its start would cost several per cent of the kernel)
+    const int ended = done != nullptr ? done[b] : 0;
     if (tid == 0) {
         for (int i = 0; i < kCrossStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
         fence_barrier_init();
     }
     __syncthreads();
+    if (ended) { pdl_wait(); return; }   // (the wait still runs: this grid must not complete before its upstream does)
 
     if (warp == 4) {
         // ---------------- producer ----------------

@@ -817,6 +817,8 @@ wk_status wk_mel(wk_model* m, const float* pcm, int64_t n_windows, int64_t strid
     WK_CHECK(enc_ws_ensure(m, &m->ws, m->cfg.max_batch));
     wk_tensor* t = nullptr;
     WK_CHECK(tensor_new(m, 0, WK_DTYPE_F16, n_windows, (size_t)n_windows * kMelRows * kMelCols * 2, &t));
+    // rows 0 / 3001 (the conv stem's zero padding) and the channels past n_mels are never written by the mel kernels
+    WK_CUDA_CHECK(cudaMemsetAsync(t->data, 0, (size_t)n_windows * kMelRows * kMelCols * 2, m->stream));
     wk_status s = mel_run(m, &m->ws, pcm, n_windows, stride, samples_per_window, t->data, m->stream);
     if (s != WK_OK) { cudaFreeAsync(t->data, m->stream); cudaEventDestroy(t->events[0]); delete t; return s; }
     WK_CUDA_CHECK(cudaEventRecord(t->events[0], m->stream));

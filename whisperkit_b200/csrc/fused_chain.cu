@@ -69,28 +69,26 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     return v;
 }
 
-// grid-wide barrier: every CTA of the (fully co-resident) grid arrives once on `ctr`, which the host zeroed before the launch
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n_ctas) {
-    fence_generic_to_async_global();
+// grid-wide barrier: every CTA of the (fully co-resident) grid arrives once on `ctr` (zero before the launch).  Release / acquire at gpu
+// scope through one elected thread per CTA, made cumulative over the CTA by the bar.sync on either side.  `tma_reads_next`: this CTA's
+// generic-proxy stores of the phase are read by TMA (async proxy) in the next phase - the writers fence towards that proxy first.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n_ctas, bool tma_reads_next) {
+    if (tma_reads_next) fence_generic_to_async_global();
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         if (ld_acquire_gpu(ctr) < n_ctas) {
             const unsigned long long t0 = globaltimer_ns();
             unsigned int spins = 0;
             while (ld_acquire_gpu(ctr) < n_ctas) {
-                __nanosleep(20);
-                if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > kSpinLimitNs) {
+                if ((++spins & 0xfffu) == 0 && globaltimer_ns() - t0 > kSpinLimitNs) {
                     printf("wkb200: grid barrier timed out (block %d: %u of %u CTAs arrived)\n", (int)blockIdx.x, ld_acquire_gpu(ctr), n_ctas);
                     __trap();
                 }
             }
         }
-        __threadfence();
     }
     __syncthreads();
-    fence_generic_to_async_global();
 }
 
 template <typename T>
@@ -253,6 +251,7 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
                     // ===================== TMA producer =====================
                     if (pre_for != ph) prefetch_weights(ph);   // (only if the previous phase could not prefetch)
                     const int kb0 = split * P.kb_per_split;
+                    fence_generic_to_async_global();           // the activations were written with generic stores by other CTAs (acquired at the barrier)
                     for (int i = 0; i < pre_n; ++i) {          // activations for the weight tiles already in flight
                         const int st = (pre_stage0 + i) % p.stages;
                         tma_load_2d(smem + (size_t)st * stage_bytes + kStageABytes, &maps.b[P.map], &full_bar[st], (kb0 + i) * kK, 0);
@@ -327,7 +326,7 @@ decoder_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainK p) {
                 reduce_gelu_all<T>(p, P);
             }
         }
-        if (ph + 1 < p.n_phases) grid_barrier(p.counters + ph, gridDim.x);
+        if (ph + 1 < p.n_phases) grid_barrier(p.counters + ph, gridDim.x, P.kind != 0);
     }
 
     tc_fence_before();

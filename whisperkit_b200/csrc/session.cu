@@ -640,7 +640,10 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
             bool first_gemm = true;
             auto flush_run = [&]() -> wk_status {
                 if (run_cnt == 0) return WK_OK;
-                if (first_gemm && !ckv_timing) { WK_CUDA_CHECK(cudaEventRecord(s->ev_t[4], s->stream)); }
+                if (first_gemm && !ckv_timing) {
+                    if (!chunk_waited) { WK_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->ev_enc, 0)); chunk_waited = true; }   // timed region starts once the encoder output exists
+                    WK_CUDA_CHECK(cudaEventRecord(s->ev_t[4], s->stream));
+                }
                 first_gemm = false;
                 wk_status r = project_cross_kv(run_w0, run_q0, run_cnt);
                 run_cnt = 0;
