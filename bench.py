@@ -71,6 +71,9 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=16)
     ap.add_argument("--stream-seconds", type=float, default=300.0)
     ap.add_argument("--no-word-timestamps", action="store_true")
+    ap.add_argument("--chunking", default="vad", choices=["vad", "none"],
+                    help="long-form: 'vad' = chunkingStrategy .vad (every stream is cut into independent <= 30 s chunks, WhisperKit.swift:878-911: the "
+                         "'chunked to 30 s windows' of BASELINE configs[4]); 'none' = one sequential seek loop per stream")
     return ap.parse_args()
 
 
@@ -618,7 +621,7 @@ def run_longform_arm(args):
     def step():
         h = C.c_void_p()
         check(lib.wk_transcribe_streams(model.handle, dec.handle, ptrs, lens, len(streams), C.byref(st_c), C.byref(o_c), p_c, len(prompt), None, 0,
-                                        1.0, -1, 0, C.byref(hooks) if hooks is not None else None, C.byref(h)))
+                                        1.0, -1, 1 if args.chunking == "vad" else 0, C.byref(hooks) if hooks is not None else None, C.byref(h)))
         stats["windows"] = lib.wk_transcription_window_count(h)
         stats["segments"] = lib.wk_transcription_segment_count(h)
         stats["words"] = lib.wk_transcription_word_count(h)
@@ -659,7 +662,8 @@ def run_longform_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": f"synthetic 16 kHz PCM streams, seeded random weights of the {args.variant} architecture, synthetic byte-level vocabulary of Whisper's size",
         "config": {"workload": f"{name} long-form (BASELINE configs[4] shape, one GPU's share): {args.streams} streams x ~{args.stream_seconds:.0f} s per GPU through "
-                               f"wk_transcribe_streams (seek loop per stream, {B} decode slots shared by all streams), wordTimestamps={words}, "
+                               f"wk_transcribe_streams (chunking={args.chunking}: " + ("streams cut into independent <= 30 s VAD chunks" if args.chunking == "vad" else "one sequential seek loop per stream")
+                               + f", {B} decode slots shared by all streams), wordTimestamps={words}, "
                                f"sampleLength={args.sample_length}, greedy, no temperature fallback; host PCM in, segments"
                                + (" + word timings" if words else "") + " out (this IS the end-to-end path)",
                    "streams_per_gpu": args.streams, "stream_seconds": args.stream_seconds, "decode_slots": B,

@@ -23,6 +23,7 @@ run bench_eot_fixed --windows 256 --steps 1 --warmup 3 --no-cpu-baseline --no-ro
 run bench_beam --beam 5 --batch 160 --windows 32 --steps 3 --warmup 3 --no-cpu-baseline --no-roofline
 run bench_longform --longform --variant distil-large-v3 --batch 64 --streams 16 --stream-seconds 300 --steps 2 --warmup 3
 run bench_longform_nowords --longform --variant distil-large-v3 --batch 64 --streams 16 --stream-seconds 300 --steps 2 --warmup 3 --no-word-timestamps
+run bench_longform_seq --longform --variant distil-large-v3 --batch 64 --streams 16 --stream-seconds 300 --steps 2 --warmup 3 --chunking none
 cat $out/summary.txt
 tail -15 $out/pytest.log
 tail -12 $out/microbench.log
