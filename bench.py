@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--sample-length", type=int, default=224, help="DecodingOptions.sampleLength (reference default 224)")
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-second-dtype", action="store_true", help="skip the extra timed passes under the other 16-bit storage policy")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-windows", type=int, default=1)
     ap.add_argument("--profile-pass", action="store_true", help="one untimed pass of the hot path and exit (for ncu)")
@@ -477,11 +478,17 @@ def run_own_arm(args):
             4: (f"gemm_tcgen05_kernel[dec QKV swap-AB N={3 * d},K={d},split-K] (L2-warm)", "hbm", 0),
             5: (f"gemm_tcgen05_kernel[enc QKV M=B*1500,N={3 * d},K={d}]", "tensor", L * (W / B)),
             9: ("decoder_self_attention_kernel[pos 100]", "hbm", Ld * nsteps),
-            18: ("decoder_chain_kernel[B: out-proj > reduce+LN > cross-Q]", "hbm", Ld * nsteps),
-            19: ("decoder_chain_kernel[C: cross-out > LN > FC1 > GELU > FC2 > LN > QKV]", "hbm", Ld * nsteps),
+            14: (f"gemm_tcgen05_kernel[dec d x d swap-AB split-K, HBM-cold] (x3 per layer)", "hbm", 3 * Ld * nsteps),
+            15: (f"gemm_tcgen05_kernel[dec FC1 swap-AB split-K, HBM-cold]", "hbm", Ld * nsteps),
+            16: (f"gemm_tcgen05_kernel[dec FC2 swap-AB split-K, HBM-cold]", "hbm", Ld * nsteps),
+            17: (f"gemm_tcgen05_kernel[dec QKV swap-AB split-K, HBM-cold]", "hbm", Ld * nsteps),
+            8: ("decoder_reduce_resid_ln_kernel (x3 per layer)", "hbm", 3 * Ld * nsteps),
         }
         for which, (kname, bound, per_step) in table.items():
-            check(lib.wk_bench_kernel(model.handle, dec.handle, which, B, 20 if which != 2 else 5, C.byref(f), C.byref(wk_)))
+            kb = min(B, enc_batch) if which in (1, 2, 3, 5) else B      # encoder-side kernels run on one encoder chunk
+            if which in (1, 2, 3, 5):
+                per_step = per_step * B / kb
+            check(lib.wk_bench_kernel(model.handle, dec.handle, which, kb, 20 if which != 2 else 5, C.byref(f), C.byref(wk_)))
             t_ms, work = float(f.value), float(wk_.value)
             if bound == "hbm":
                 ach, peak, unit = work / (t_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
@@ -528,6 +535,35 @@ def run_own_arm(args):
                                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s"}
         if line["roofline_encoder"]["achieved"]:
             line["roofline_encoder"]["frac"] = line["roofline_encoder"]["achieved"] / peaks["bf16_tflops_sustained"]
+
+    if world == 1 and not args.no_second_dtype and not args.eot_profile and beam == 1 and args.dtype in ("bf16", "f16"):
+        # the same workload under the other storage policy.  BASELINE names bf16; the reference itself is Float16 end to end
+        # (ArgmaxCore/FloatType.swift:9-13) and only f16 meets north_star's 1e-3 logits tolerance (tests/test_gpu_large.py: 7.1e-4 vs
+        # 5.2e-3 for bf16 at 32 decoder layers), so both are timed here, device-resident PCM, same steps
+        other = "f16" if args.dtype == "bf16" else "bf16"
+        dec.close(); model.close()
+        model2 = wk.Model(args.variant, device=local_rank, max_batch=enc_batch, dtype=other)
+        model2.init_random(seed=1234)
+        dec2 = wk.TextDecoder(model2, B)
+        ext2 = torch.cuda.ExternalStream(model2.stream, device=torch.device("cuda", local_rank))
+
+        def step2():
+            check(lib.wk_transcribe_windows_ex(model2.handle, dec2.handle, C.c_void_p(pcm_dev.data_ptr()), W, 480000, None, C.byref(st_c), C.byref(bo), res))
+        for _ in range(4):
+            step2()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(ext2)
+        for _ in range(args.steps):
+            step2()
+        a1.record(ext2)
+        torch.cuda.synchronize()
+        ms2 = a0.elapsed_time(a1) / args.steps
+        line["other_dtype"] = {"dtype": other, "value": W * AUDIO_SECONDS_PER_WINDOW / (ms2 / 1000.0), "unit": "audio-sec/s", "ms_per_step": ms2,
+                               "steps": args.steps, "logits_rel_err_vs_oracle": {"f16": "7.1e-4 (meets 1e-3)", "bf16": "5.2e-3 (does not meet 1e-3)"},
+                               "note": "same workload, device-resident PCM; parity figures from tests/test_gpu_large.py on B200"}
+        log(f"{other}: {ms2:.1f} ms/step")
+        dec2.close(); model2.close()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

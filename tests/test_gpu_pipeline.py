@@ -205,10 +205,13 @@ def test_model_load_from_safetensors_checkpoint(tmp_path):
     cfg = dict(num_mel_bins=dims.n_mels, d_model=dims.d_model, encoder_attention_heads=dims.n_heads, encoder_layers=dims.enc_layers,
                decoder_layers=dims.dec_layers, vocab_size=dims.vocab, max_source_positions=1500, max_target_positions=448)
     (tmp_path / "config.json").write_text(json.dumps(cfg))
+    # the checkpoint's own word-timestamp heads (openai-whisper's alignment_heads, shipped by HF in generation_config.json)
+    (tmp_path / "generation_config.json").write_text(json.dumps({"alignment_heads": [[1, 0], [1, 1]], "max_length": 448}))
     m1 = wk.Model.from_pretrained(str(tmp_path), max_batch=2, dtype="bf16")
     m2 = wk.Model("toy", max_batch=2, dtype="bf16")
     m2.load_state_dict(w)
     assert m1.info.d_model == dims.d_model and m1.info.vocab == dims.vocab
+    assert m1.info.has_alignment_heads == 1 and m2.info.has_alignment_heads == 0     # supportsWordTimestamps (TextDecoder.swift:309-311)
     pcm = np.stack([mel_ref.synthetic_pcm(1), mel_ref.synthetic_pcm(2)])
     outs = []
     for m in (m1, m2):
@@ -375,6 +378,23 @@ def test_transcribe_streams_seek_loop_matches_oracle_loop():
     assert [g.seek for g in got[0]] == [r.seek for r in ref_all]
     np.testing.assert_allclose([g.start for g in got[0]], [r.start for r in ref_all], atol=1e-4)
     np.testing.assert_allclose([g.end for g in got[0]], [r.end for r in ref_all], atol=1e-4)
+
+
+def test_vad_strategy_on_short_audio_keeps_clip_timestamps():
+    """chunkingStrategy .vad only applies to audio longer than one window (isChunkable, WhisperKit.swift:876-878): shorter audio goes through
+    runTranscribeTask with the caller's options, clipTimestamps included."""
+    from whisperkit_b200 import longform as L
+    st_o = D.SpecialTokens.toy(1024)
+    kit = wk.WhisperKit(wk.WhisperKitConfig(model="toy", maxBatch=2, seed=9, specialTokens=wk.SpecialTokens.from_any(st_o)))
+    o = wk.DecodingOptions(firstTokenLogProbThreshold=None, logProbThreshold=None, compressionRatioThreshold=None, sampleLength=16,
+                           temperatureFallbackCount=0)
+    x = mel_ref.synthetic_pcm(321)[:400000].astype(np.float32)          # 25 s: not chunkable
+    clips = (2.0, 9.0, 12.5)
+    plain, w_plain = L.transcribe_streams(kit, [x], o, clipTimestamps=clips)
+    vad, w_vad = L.transcribe_streams(kit, [x], o, clipTimestamps=clips, chunkingStrategy="vad")
+    whole, _ = L.transcribe_streams(kit, [x], o, chunkingStrategy="vad")
+    assert [(g.seek, g.tokens) for g in vad[0]] == [(g.seek, g.tokens) for g in plain[0]] and w_vad == w_plain == 2
+    assert vad[0][0].seek == 32000 and [g.seek for g in whole[0]][0] == 0   # the clips were honoured (and do change the result)
 
 
 def _toy_split(tokens, special_begin):
@@ -568,8 +588,9 @@ def test_transcribe_audio_text_and_words_with_library_tokenizer():
 
 
 def test_fused_decoder_chains_match_the_launch_per_phase_path():
-    """csrc/fused_chain.cu (the default decode schedule) keeps the arithmetic and its order: tokens and logits must be bit-identical to
-    the launch-per-phase schedule (WKB200_FUSED=0), at toy widths and at d = 1280 / H = 20 / V = 51866."""
+    """csrc/fused_chain.cu (WKB200_FUSED=1: persistent phase chains with grid barriers; measured slower than the default on B200, kept as
+    an opt-in) keeps the arithmetic and its order: tokens and logits must be bit-identical to the launch-per-phase schedule, at toy widths
+    and at d = 1280 / H = 20 / V = 51866."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

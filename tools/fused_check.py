@@ -1,5 +1,5 @@
-"""Bit-identity check of the two decode schedules: the fused phase chains (csrc/fused_chain.cu, default) against one launch per phase
-(WKB200_FUSED=0).  The arithmetic and its order are the same, only the launch structure differs, so tokens and logits must match bit
+"""Bit-identity check of the two decode schedules: the fused phase chains (csrc/fused_chain.cu, WKB200_FUSED=1) against one launch per
+phase (the default).  The arithmetic and its order are the same, only the launch structure differs, so tokens and logits must match bit
 for bit - at toy widths and at large-v3 width (d 1280, 20 heads, vocabulary 51866; 3 decoder layers to keep it short).
 
     timeout 600 python tools/fused_check.py            # exits 0 on a match

@@ -4,7 +4,7 @@
 //   warp 0      TMA producer: Q tile once, then K / V tiles of 128 keys through 3-deep smem rings (128B swizzle)
 //   warp 1      MMA issuer:   S_j = Q K_j^T   (tcgen05.mma 128x128x16 x4, accumulator S in TMEM, double buffered)
 //                             PV_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P_j from smem, B = V_j MN-major from smem)
-//   warps 2..9  softmax:      two threads per query row (warps w and w+4 share a TMEM lane quarter): each takes 64
+//   warps 2..   softmax:      P (2, or 4) threads per query row (warps w, w+4, ... share a TMEM lane quarter); for P = 2 each takes 64
 //                             of the tile's 128 keys and 32 of the 64 output columns.  tcgen05.ld S_j -> max / exp2 /
 //                             row sum in registers (only the row max is exchanged, through smem, once per tile),
 //                             P_j (16-bit) -> swizzled smem for the second MMA; PV_j is read back from TMEM and
@@ -21,14 +21,14 @@
 
 namespace wk {
 
-static constexpr int kFaThreads = 320;      // TMA warp + MMA warp + 8 softmax warps
+static constexpr int kFaThreadsFor(int parts) { return 64 + 128 * parts; }   // TMA warp + MMA warp + 4 * parts softmax warps
 static constexpr int kFaBM = 128;          // queries per CTA
 static constexpr int kFaBN = 128;          // keys per tile
 static constexpr int kFaD = 64;
 static constexpr int kFaTile = kFaBN * kFaD * 2;   // 16 KiB: one K or V or Q tile, 128-byte rows
 static constexpr int kFaStages = 3;
 static constexpr int kFaPBytes = kFaBM * kFaBN * 2;  // 32 KiB: P tile = two 64-key chunks of 16 KiB
-static constexpr int kFaSmem = kFaTile /*Q*/ + 2 * kFaStages * kFaTile /*K,V rings*/ + 2 * kFaPBytes + 1024 /*align*/ + 512 /*barriers*/ + 4096 /*row-max / row-sum exchange*/;
+static constexpr int kFaSmem = kFaTile /*Q*/ + 2 * kFaStages * kFaTile /*K,V rings*/ + 2 * kFaPBytes + 1024 /*align*/ + 512 /*barriers*/ + 8192 /*row-max / row-sum exchange*/;
 static constexpr int kFaTmemCols = 512;    // S0 @0, S1 @128, O0 @256, O1 @320
 
 struct FaParams {
@@ -55,8 +55,20 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
     return d;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kFaThreads, 1)
+// 32 lanes x 16 columns of 32-bit
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// P = softmax threads per query row: each takes 128 / P of the tile's keys and 64 / P of the output columns
+template <typename T, int P>
+__global__ void __launch_bounds__(kFaThreadsFor(P), 1)
 encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, const FaParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,7 +89,7 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
     uint64_t* o_full = p_empty + 2;               // 2
     uint64_t* o_empty = o_full + 2;               // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
-    float* xch = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parity][2 halves][128 rows] row-max exchange (+ final sums)
+    float* xch = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parity][P parts][128 rows] row-max exchange, then [P][128] final sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, bh = blockIdx.y;
@@ -93,9 +105,9 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-            mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4 * P);
+            mbar_init(&p_full[i], 4 * P); mbar_init(&p_empty[i], 1);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4 * P);
         }
         fence_barrier_init();
     }
@@ -176,32 +188,36 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
         }
     } else {
         // ============================ softmax / accumulate / epilogue ============================
+        constexpr int KT = kFaBN / P;                 // keys of the tile per thread (64 or 32)
+        constexpr int OC = kFaD / P;                  // output columns per thread (32 or 16)
+        constexpr int NCH = KT / 32;                  // 32-column TMEM loads per tile
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int half = (warp - 2) >> 2;             // 0: keys 0..63 / out cols 0..31, 1: keys 64..127 / out cols 32..63
+        const int part = (warp - 2) >> 2;             // which slice of the keys / output columns
         const int row = quarter * 32 + lane;          // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t pair_bar = 1 + quarter;        // named barrier shared by the two warps of this lane quarter
-        float o[32];
+        const uint32_t pair_bar = 1 + quarter;        // named barrier shared by the P warps of this lane quarter
+        float o[OC];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
-        float m_run = -INFINITY;      // running max of raw scores (identical in both threads of a row)
+        for (int i = 0; i < OC; ++i) o[i] = 0.f;
+        float m_run = -INFINITY;      // running max of raw scores (identical in all threads of a row)
         float m_acc = -INFINITY;      // max the register accumulator o[] is currently scaled to
         float l_run = 0.f;            // this thread's share of the row sum
         float m_tile_prev = -INFINITY;
         const float c = p.scale_log2e;
         const int sw = row & 7;
 
-        auto accumulate = [&](int i, float m_i) {   // o += PV_i[:, half*32 .. +32], PV_i is relative to max m_i
+        auto accumulate = [&](int i, float m_i) {   // o += PV_i[:, part*OC .. +OC], PV_i is relative to max m_i
             const int sb = i & 1;
             mbar_wait(&o_full[sb], (i >> 1) & 1);
             tc_fence_after();
             const float corr = ex2_approx((m_acc - m_i) * c);   // m_acc = -inf on first use -> 0
             m_acc = m_i;
-            uint32_t r[32];
-            tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + half * 32, r);
+            uint32_t r[OC];
+            if constexpr (OC == 32) tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + part * OC, r);
+            else tmem_ld_32x16(tmem + lane_addr + 256 + sb * 64 + part * OC, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 32; ++t) o[t] = fmaf(o[t], corr, __uint_as_float(r[t]));
+            for (int t = 0; t < OC; ++t) o[t] = fmaf(o[t], corr, __uint_as_float(r[t]));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[sb]);
@@ -212,42 +228,48 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             const uint32_t ph = (j >> 1) & 1;
             mbar_wait(&s_full[sb], ph);
             tc_fence_after();
-            // this thread's 64 scores into registers (both TMEM loads in flight), then release the S buffer
-            uint32_t sr[2][32];
-            tmem_ld_32x32(tmem + lane_addr + sb * 128 + half * 64, sr[0]);
-            tmem_ld_32x32(tmem + lane_addr + sb * 128 + half * 64 + 32, sr[1]);
+            // this thread's KT scores into registers (all TMEM loads in flight), then release the S buffer
+            uint32_t sr[NCH][32];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32(tmem + lane_addr + sb * 128 + part * KT + ch * 32, sr[ch]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[sb]);
-            const int valid = p.T - j * kFaBN - half * 64;   // keys of this thread's half that exist (>= 64 except at the end)
-            if (valid < 64) {
+            const int valid = p.T - j * kFaBN - part * KT;   // keys of this thread's slice that exist (>= KT except at the end)
+            if (valid < KT) {
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch)
+                for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
                     for (int t = 0; t < 32; ++t)
                         if (ch * 32 + t >= valid) sr[ch][t] = 0xff800000u;   // -inf: key does not exist
             }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                mx0 = fmaxf(mx0, __uint_as_float(sr[0][t]));
-                mx1 = fmaxf(mx1, __uint_as_float(sr[1][t]));
-            }
-            // exchange the half-row max with the partner thread (same row, other 64 keys)
-            float* slot = xch + (j & 1) * 256;
-            slot[half * 128 + row] = fmaxf(mx0, mx1);
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            const float mx = fmaxf(m_run, fmaxf(slot[row], slot[128 + row]));
+            for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[ch][t]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[ch][t + 1]));
+                }
+            // exchange the slice max with the partner threads (same row, other keys)
+            float* slot = xch + (j & 1) * (P * 128);
+            slot[part * 128 + row] = fmaxf(mx0, mx1);
+            asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * P) : "memory");
+            float mx = m_run;
+#pragma unroll
+            for (int q = 0; q < P; ++q) mx = fmaxf(mx, slot[q * 128 + row]);
             const float l_corr = ex2_approx((m_run - mx) * c);
             const float msc = mx * c;
             m_run = mx;
             // P buffer free?  (PV of tile j-2 has consumed it)
             mbar_wait(&p_empty[sb], ph ^ 1);
             float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-            uint8_t* prow = sP + sb * kFaPBytes + half * (kFaPBytes / 2) + row * 128;   // this half = one 64-key chunk block
+            // P tile in smem = two 64-key chunk blocks of 16 KiB (128-byte rows, 128B swizzle); this thread's keys part*KT .. +KT
+            uint8_t* prow = sP + sb * kFaPBytes + ((part * KT) >> 6) * (kFaPBytes / 2) + row * 128;
+            const int chunk0 = ((part * KT) & 63) >> 3;   // first 16-byte chunk of the slice inside the 128-byte row
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NCH; ++ch) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {
@@ -261,7 +283,7 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int chunk = ch * 4 + q;   // 16-byte chunk inside the 128-byte row
+                    const int chunk = chunk0 + ch * 4 + q;   // 16-byte chunk inside the 128-byte row
                     *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
@@ -274,16 +296,19 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             m_tile_prev = mx;
         }
         accumulate(n - 1, m_tile_prev);
-        // ---- epilogue: total row sum = both halves; normalise and store this thread's 32 columns (64 contiguous bytes)
-        float* fin = xch + 512;   // [2][128]
-        fin[half * 128 + row] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        // ---- epilogue: total row sum = all slices; normalise and store this thread's OC columns
+        float* fin = xch + 2 * P * 128;   // [P][128]
+        fin[part * 128 + row] = l_run;
+        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * P) : "memory");
         const int q = q0 + row;
         if (q < p.T) {
-            const float inv = 1.f / (fin[row] + fin[128 + row]);
-            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kFaD + half * 32);
+            float tot = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < P; ++i) tot += fin[i * 128 + row];
+            const float inv = 1.f / tot;
+            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kFaD + part * OC);
+#pragma unroll
+            for (int i = 0; i < OC / 8; ++i) {
                 uint4 v;
                 v.x = T16<T>::pack2(o[8 * i] * inv, o[8 * i + 1] * inv);
                 v.y = T16<T>::pack2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
@@ -337,16 +362,22 @@ wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, in
                  ((uint32_t)(kFaBM >> 4) << 24);
     p.v_lbo = 1; p.v_sbo = 64; p.v_kstep = 2048;
     dim3 grid((T + kFaBM - 1) / kFaBM, B * n_heads);
-    cudaError_t e;
+    // softmax threads per query row: 2 (8 softmax warps) or 4 (16 warps: more warps per scheduler to hide the exp2 / pack latencies).
+    // WKB200_ATTN_PARTS (read once) keeps the other variant reachable for A/B timing.
+    static const int parts = (getenv("WKB200_ATTN_PARTS") && atoi(getenv("WKB200_ATTN_PARTS")) == 4) ? 4 : 2;
+    cudaError_t e = cudaSuccess;
     if (dtype == WK_DTYPE_F16) {
-        static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fa): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; } set = true; }
-        encoder_attention_tcgen05_kernel<__half><<<grid, kFaThreads, kFaSmem, stream>>>(tm, (__half*)out, p);
+        if (parts == 4) { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+                          if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, 4><<<grid, kFaThreadsFor(4), kFaSmem, stream>>>(tm, (__half*)out, p); }
+        else { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+               if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__half*)out, p); }
     } else {
-        static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fa): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; } set = true; }
-        encoder_attention_tcgen05_kernel<__nv_bfloat16><<<grid, kFaThreads, kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p);
+        if (parts == 4) { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+                          if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, 4><<<grid, kFaThreadsFor(4), kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p); }
+        else { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+               if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p); }
     }
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fa): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("encoder_attention_tcgen05 launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }

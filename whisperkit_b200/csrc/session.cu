@@ -51,7 +51,7 @@ struct wk_session {
     float* h_logprobs = nullptr;
     // step graph, cached across calls: the step depends on the call only through the rows it covers, the alignment export and the
     // special-token ids baked into the sampler's parameters
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec = nullptr, graph_exec_live = nullptr;   // the step with / without the ended-row checks in the attention kernels
     int graph_batch = 0; bool graph_align = false, graph_fused = false; wk_special_tokens graph_st; long long launches_per_step = 0;
     bool warmed = false;
     // word timestamps: per-head softmax rows of the current step, the [S][224][T] Float16 alignmentWeights of the slots, and the per-window
@@ -60,7 +60,7 @@ struct wk_session {
     void* align_store = nullptr; int64_t align_store_cap = 0, align_store_n = 0;
     unsigned int* chain_counters = nullptr;
     cudaEvent_t ev_enc = nullptr, ev_adm = nullptr, ev_stage = nullptr, ev_t[10];
-    bool knob_fused = true, knob_graph = true;
+    bool knob_fused = false, knob_graph = true;
     // beam search (allocated on the first call that asks for it)
     BeamState bs = BeamState(); int bs_cap_rows = 0;
     int32_t *h_n_fin = nullptr, *h_fin_len = nullptr, *h_fin_tokens = nullptr; float *h_fin_score = nullptr, *h_fin_lps = nullptr, *h_sum_lp = nullptr;
@@ -94,7 +94,7 @@ static wk_status dec_gemm(wk_session* s, const void* w, int N, int K, const void
 static bool use_fused(const wk_session* s) { return s->knob_fused && s->m->live_sessions.load(std::memory_order_relaxed) == 1; }
 
 // one decoder forward for every row of the step.  explicit_pos == nullptr: loop mode (token / position from DecodeState, ended rows skipped)
-static wk_status decoder_forward(wk_session* s, int ts_begin, const int32_t* explicit_pos, bool fused) {
+static wk_status decoder_forward(wk_session* s, int ts_begin, const int32_t* explicit_pos, bool fused, bool check_done = true) {
     wk_model* m = s->m;
     const wk_model_config& c = m->cfg;
     const int d = c.d_model, H = c.n_heads, dt = c.dtype, B = s->batch, Bp = s->bp, T = c.n_audio_ctx;
@@ -102,7 +102,9 @@ static wk_status decoder_forward(wk_session* s, int ts_begin, const int32_t* exp
     const size_t self_layer = (size_t)s->max_batch * H * kKvMaxLen * 64 * 2;   // bytes per layer
     const size_t cross_block = (size_t)s->max_batch * H * T * 64 * 2;          // bytes per (layer, k|v)
     const int32_t* pos = explicit_pos ? explicit_pos : s->st.steps;
-    const int32_t* done = explicit_pos ? nullptr : s->st.done;
+    // ended rows are skipped by the attention kernels; a burst that starts with every slot live runs the variant without the checks (a
+    // row that ends inside it just keeps computing until the next poll, as harmlessly as before it ended)
+    const int32_t* done = (explicit_pos || !check_done) ? nullptr : s->st.done;
     const bool beam_rows = !explicit_pos && s->bs.beam > 1;   // rows are beams: cache ancestry + one cross K/V block per `beam` rows
     const int n_layers = c.dec_layers;
     int sp = 1;
@@ -293,9 +295,9 @@ static wk_status build_prompt(const wk_model* m, const wk_special_tokens* st, co
 }
 
 // ---------------------------------------------------------------------------------------------- the step and its graph
-static wk_status enqueue_step(wk_session* s, const wk_special_tokens* st, bool fused) {
+static wk_status enqueue_step(wk_session* s, const wk_special_tokens* st, bool fused, bool check_done) {
     wk_model* m = s->m;
-    WK_CHECK(decoder_forward(s, st->time_token_begin, nullptr, fused));
+    WK_CHECK(decoder_forward(s, st->time_token_begin, nullptr, fused, check_done));
     WK_CHECK(sampler_filter_sample(s->logits, m->cfg.vocab, loop_sampler_params(s, st), s->st, nullptr, 0, nullptr, nullptr, nullptr, nullptr, s->batch, s->stream));
     if (s->bs.beam > 1) WK_CHECK(beam_update(s->st, s->bs, *st, kKvMaxLen, s->batch / s->bs.beam, s->stream));
     if (s->align_on)
@@ -305,33 +307,40 @@ static wk_status enqueue_step(wk_session* s, const wk_special_tokens* st, bool f
 
 // runs `n` decode steps on the session stream (CUDA graph replay; the first step of a session runs eagerly so that lazily loaded
 // kernels and function attributes exist before a capture)
-static wk_status run_steps(wk_session* s, const wk_special_tokens* st, int n) {
+static wk_status run_steps(wk_session* s, const wk_special_tokens* st, int n, bool all_live) {
     const bool fused = use_fused(s);
+    const bool check_done = !all_live;
     int done = 0;
     if (!s->knob_graph || !s->warmed) {
         const int eager = s->knob_graph ? 1 : n;
-        for (; done < eager && done < n; ++done) WK_CHECK(enqueue_step(s, st, fused));
+        for (; done < eager && done < n; ++done) WK_CHECK(enqueue_step(s, st, fused, check_done));
         s->warmed = true;
     }
     if (done >= n) return WK_OK;
-    const bool stale = !s->graph_exec || s->graph_batch != s->batch || s->graph_align != s->align_on || s->graph_fused != fused ||
-                       s->graph_beam != std::max(1, s->bs.beam) * 16 + s->bs.max_candidates || memcmp(&s->graph_st, st, sizeof(*st)) != 0;
+    const int beam_key = std::max(1, s->bs.beam) * 16 + s->bs.max_candidates;
+    const bool stale = s->graph_batch != s->batch || s->graph_align != s->align_on || s->graph_fused != fused || s->graph_beam != beam_key ||
+                       memcmp(&s->graph_st, st, sizeof(*st)) != 0;
     if (stale) {
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+        if (s->graph_exec_live) { cudaGraphExecDestroy(s->graph_exec_live); s->graph_exec_live = nullptr; }
+        s->graph_batch = s->batch; s->graph_align = s->align_on; s->graph_fused = fused; s->graph_st = *st; s->graph_beam = beam_key;
+    }
+    cudaGraphExec_t& exec = check_done ? s->graph_exec : s->graph_exec_live;
+    if (!exec) {
         for (int attempt = 0; attempt < 2; ++attempt) {
-            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;
             const long long before = launch_counter_load();
             WK_CUDA_CHECK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-            wk_status r = enqueue_step(s, st, fused);
+            wk_status r = enqueue_step(s, st, fused, check_done);
             cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
             s->launches_per_step = launch_counter_load() - before;
             launch_counter_sub(s->launches_per_step);  // captured, not executed
             if (r != WK_OK) { if (graph) cudaGraphDestroy(graph); return r; }
             if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-            e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+            e = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e == cudaSuccess) break;
-            s->graph_exec = nullptr;
+            exec = nullptr;
             if (attempt == 0 && pdl_enabled()) {   // programmatic edges rejected by this driver: plain serialisation, capture again
                 cudaGetLastError();
                 pdl_disable();
@@ -340,11 +349,9 @@ static wk_status run_steps(wk_session* s, const wk_special_tokens* st, int n) {
             set_error("graph instantiate failed: %s", cudaGetErrorString(e));
             return WK_ERR_CUDA;
         }
-        s->graph_batch = s->batch; s->graph_align = s->align_on; s->graph_fused = fused; s->graph_st = *st;
-        s->graph_beam = std::max(1, s->bs.beam) * 16 + s->bs.max_candidates;
     }
     for (; done < n; ++done) {
-        WK_CUDA_CHECK(cudaGraphLaunch(s->graph_exec, s->stream));
+        WK_CUDA_CHECK(cudaGraphLaunch(exec, s->stream));
         count_launch((int)s->launches_per_step);
     }
     return WK_OK;
@@ -367,7 +374,8 @@ static wk_status ensure_align(wk_session* s, int64_t n_windows) {
         if (s->align_scratch) { WK_CUDA_CHECK(cudaStreamSynchronize(s->stream)); cudaFree(s->align_scratch); s->align_scratch = nullptr; }
         WK_CUDA_CHECK(cudaMalloc((void**)&s->align_scratch, (size_t)std::max(1, m->n_align_slots) * s->max_batch * T * 4));
         s->align_slots = m->n_align_slots;
-        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // the scratch pointer is baked into the graph
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // the scratch pointer is baked into the graphs
+        if (s->graph_exec_live) { cudaGraphExecDestroy(s->graph_exec_live); s->graph_exec_live = nullptr; }
     }
     if (s->align_store_cap < n_windows) {
         if (s->align_store) { WK_CUDA_CHECK(cudaStreamSynchronize(s->stream)); cudaFree(s->align_store); s->align_store = nullptr; }
@@ -489,7 +497,8 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
         if (s->suppress_dev) cudaFree(s->suppress_dev);
         s->suppress_cap = std::max<size_t>(4096, sup_pool.size() * 2);
         WK_CHECK(dmalloc(&s->suppress_dev, s->suppress_cap));
-        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // pool pointer is baked into the graph
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // pool pointer is baked into the graphs
+        if (s->graph_exec_live) { cudaGraphExecDestroy(s->graph_exec_live); s->graph_exec_live = nullptr; }
     }
     if (!sup_pool.empty()) WK_CUDA_CHECK(cudaMemcpyAsync(s->suppress_dev, sup_pool.data(), sup_pool.size() * 4, cudaMemcpyHostToDevice, s->stream));
     WK_CUDA_CHECK(cudaStreamSynchronize(s->stream));   // sup_pool is pageable: the copy must land before it goes out of scope paths below reuse it
@@ -673,7 +682,7 @@ static wk_status transcribe_core(wk_session* s, const CoreArgs& a) {
         }
         // (C) a burst of decode steps, then the state comes back in one go
         WK_CUDA_CHECK(cudaEventRecord(s->ev_t[6], s->stream));
-        WK_CHECK(run_steps(s, st, poll));
+        WK_CHECK(run_steps(s, st, poll, live == Brun));
         s->stats[0] += poll; s->stats[1] += (int64_t)poll * live;
         WK_CUDA_CHECK(cudaEventRecord(s->ev_t[7], s->stream));
         WK_CUDA_CHECK(cudaMemcpyAsync(s->h_done, s->st.done, rows * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -806,8 +815,10 @@ wk_status wk_session_create(wk_model* m, int32_t max_batch, wk_session** out) {
     wk_session* s = new wk_session();
     s->m = m;
     s->max_batch = S;
-    // A/B switches, read once per session (never on the step path): WKB200_FUSED=0 launches every decoder phase as its own kernel,
-    // WKB200_NO_GRAPH=1 replays nothing
+    // A/B switches, read once per session (never on the step path).  WKB200_FUSED=1 runs the decoder's GEMM / reduce phases as persistent
+    // chains with grid barriers (fused_chain.cu): bit-identical, but measured SLOWER on B200 than one PDL-chained launch per phase
+    // (64 windows: 1252 vs 1198 ms per pass; a phase costs ~4.5 us of dependent L2 round trips either way and a grid barrier is no
+    // cheaper than a programmatic kernel boundary), so it is off by default.  WKB200_NO_GRAPH=1 replays nothing.
     if (const char* e = getenv("WKB200_FUSED")) s->knob_fused = atoi(e) != 0;
     s->knob_graph = getenv("WKB200_NO_GRAPH") == nullptr;
     WK_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -886,6 +897,7 @@ void wk_session_free(wk_session* s) {
     cudaStreamSynchronize(s->enc_stream);
     s->m->live_sessions.fetch_sub(1);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->graph_exec_live) cudaGraphExecDestroy(s->graph_exec_live);
     void* ptrs[] = {s->cross_kv, s->self_k, s->self_v, s->partial, s->x, s->xn, s->attn, s->ffn, s->logits, s->st.tokens, s->st.n_tokens,
                     s->st.logprobs, s->st.next_token, s->st.done, s->st.first_low, s->st.steps, s->st.input_ids, s->st.error, s->rp_dev,
                     s->pos_dev, s->lang_dev, s->suppress_dev, s->d_adm_slots, s->d_adm_prompts, s->d_adm_rp, s->align_scratch, s->align_w,
