@@ -394,7 +394,7 @@ def test_vad_strategy_on_short_audio_keeps_clip_timestamps():
     vad, w_vad = L.transcribe_streams(kit, [x], o, clipTimestamps=clips, chunkingStrategy="vad")
     whole, _ = L.transcribe_streams(kit, [x], o, chunkingStrategy="vad")
     assert [(g.seek, g.tokens) for g in vad[0]] == [(g.seek, g.tokens) for g in plain[0]] and w_vad == w_plain == 2
-    assert vad[0][0].seek == 32000 and [g.seek for g in whole[0]][0] == 0   # the clips were honoured (and do change the result)
+    assert all(g.seek >= 32000 for g in vad[0]) and any(g.seek < 32000 for g in whole[0])   # the clips were honoured (and do change the result)
 
 
 def _toy_split(tokens, special_begin):
