@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--vad", action="store_true", help="chunkingStrategy .vad: split long audio at silences into independent units")
     ap.add_argument("--word-timestamps", action="store_true")
+    ap.add_argument("--write", default=None, metavar="DIR", help="also write <audio>.srt / .vtt / .json there (ResultWriter.swift)")
     args = ap.parse_args()
 
     import whisperkit_b200 as wk
@@ -50,6 +51,11 @@ def main():
             print(f"  [{g.start:7.2f} -> {g.end:7.2f}] {g.text if tokenizer else g.tokens[:12]}")
             for w in (g.words or []):
                 print(f"      {w.start:7.2f} {w.end:7.2f} {w.probability:4.2f} {w.word!r}")
+        if args.write:
+            from whisperkit_b200 import writers
+            stem = os.path.splitext(os.path.basename(path))[0]
+            for cls in (writers.WriteSRT, writers.WriteVTT, writers.WriteJSON):
+                print("   wrote", cls(args.write).write(r, stem))
 
 
 if __name__ == "__main__":
