@@ -38,7 +38,7 @@ def p(t):
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
 @pytest.mark.parametrize("M,N,K,gelu,out32", [
     (128, 256, 64, 0, 1), (256, 256, 128, 0, 0), (1000, 384, 128, 1, 0), (3000, 1280, 1280, 1, 0),
-    (4500, 3840, 1280, 0, 0), (777, 1280, 5120, 0, 1), (130, 128, 64, 0, 1),
+    (4500, 3840, 1280, 0, 0), (777, 1280, 5120, 0, 1), (130, 128, 64, 0, 1), (4200, 1280, 256, 1, 0), (8200, 512, 1280, 0, 1),
 ])
 def test_gemm_tcgen05_vs_torch(toy, dt, M, N, K, gelu, out32):
     tdt, wdt = TD[dt]

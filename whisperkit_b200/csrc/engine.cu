@@ -224,6 +224,7 @@ static bool resolve_name(wk_model* m, const std::string& name, Dest* out) {
 }
 
 // ---------------------------------------------------------------------------------------------- mel + encoder schedule
+bool gemm_pair_enabled();
 GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int dtype, int mode, void* out, int64_t ld_out,
                     const float* bias, int gelu) {
     GemmDesc g;
@@ -233,7 +234,14 @@ GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int d
     g.m_rows_per_batch = (int)M; g.n = N; g.k = K; g.taps = 1;
     g.bn = N >= 256 ? 256 : round_up(N, 16);
     g.splits = 1; g.mode = mode; g.gelu = gelu; g.out = out; g.ld_out = ld_out; g.out_rows_per_batch = M; g.bias = bias;
+    g.pair = gemm_pair_enabled() && M >= 4096;   // encoder-sized products: CTA pairs with the weight tile multicast
     return g;
+}
+
+bool gemm_pair_enabled() {
+    // A/B switch, read once per process (WKB200_GEMM_PAIR=1): the 2-CTA multicast variant of the encoder GEMMs
+    static const bool on = getenv("WKB200_GEMM_PAIR") && atoi(getenv("WKB200_GEMM_PAIR")) == 1;
+    return on;
 }
 
 wk_status mel_run(wk_model* m, EncWorkspace* ws, const float* pcm, int64_t n, int64_t stride, const int32_t* samples_per_window,

@@ -56,6 +56,86 @@ struct GemmKParams {
     int a_static;     // see GemmDesc::a_static
 };
 
+// fused epilogue of one 32-column chunk of the accumulator row held by this thread (shared by the single-CTA and the CTA-pair kernels)
+template <typename T>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32], int split, long long grow, int row_in_batch,
+                                                    bool row_ok, int col_base, int c) {
+    const int col0 = col_base + c;
+    if (p.mode == GEMM_OUT_PARTIAL_T) {
+        if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                if (c + j < p.bn && col < p.partial_cols)
+                    o[((long long)split * p.partial_cols + col) * p.ld_out + grow] = __uint_as_float(r[j]);
+            }
+        }
+        return;
+    }
+    if (!row_ok || col0 >= p.n) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+    }
+    if (p.gelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (p.mode == GEMM_OUT_T16 || p.mode == GEMM_OUT_T16_HEADS) {
+        T* o;
+        if (p.mode == GEMM_OUT_T16) {
+            o = reinterpret_cast<T*>(p.out) + grow * p.ld_out + col0;
+        } else {
+            const int b = (int)(grow / p.heads_T);
+            const int tt = (int)(grow - (long long)b * p.heads_T);
+            const int which = col0 / p.heads_dmodel;
+            const int rem = col0 - which * p.heads_dmodel;
+            const int h = rem >> 6;
+            const int dd = rem & 63;
+            o = reinterpret_cast<T*>(p.out) +
+                ((((long long)which * p.heads_B + b) * p.heads_H + h) * p.heads_T + tt) * 64 + dd;
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = T16<T>::pack2(v[8 * j], v[8 * j + 1]);
+            pk.y = T16<T>::pack2(v[8 * j + 2], v[8 * j + 3]);
+            pk.z = T16<T>::pack2(v[8 * j + 4], v[8 * j + 5]);
+            pk.w = T16<T>::pack2(v[8 * j + 6], v[8 * j + 7]);
+            o4[j] = pk;
+        }
+    } else {
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ld_out + col0);
+        if (p.mode == GEMM_OUT_F32_ADD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 x = o4[j];
+                x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
+                o4[j] = x;
+            }
+        } else if (p.mode == GEMM_OUT_F32_GELU_POS) {
+            const float4* p4 = reinterpret_cast<const float4*>(p.pos + (long long)row_in_batch * p.ld_pos + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 pp = __ldg(p4 + j);
+                o4[j] = make_float4(v[4 * j] + pp.x, v[4 * j + 1] + pp.y, v[4 * j + 2] + pp.z, v[4 * j + 3] + pp.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -206,80 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent tails below
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
-                const int col0 = col_base + c;
-                if (p.mode == GEMM_OUT_PARTIAL_T) {
-                    if (row_ok) {
-                        float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = col0 + j;
-                            if (c + j < p.bn && col < p.partial_cols)
-                                o[((long long)split * p.partial_cols + col) * p.ld_out + grow] = __uint_as_float(r[j]);
-                        }
-                    }
-                    continue;
-                }
-                if (!row_ok || col0 >= p.n) continue;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 bb = __ldg(b4 + j);
-                        v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-                    }
-                }
-                if (p.gelu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                }
-                if (p.mode == GEMM_OUT_T16 || p.mode == GEMM_OUT_T16_HEADS) {
-                    T* o;
-                    if (p.mode == GEMM_OUT_T16) {
-                        o = reinterpret_cast<T*>(p.out) + grow * p.ld_out + col0;
-                    } else {
-                        const int b = (int)(grow / p.heads_T);
-                        const int tt = (int)(grow - (long long)b * p.heads_T);
-                        const int which = col0 / p.heads_dmodel;
-                        const int rem = col0 - which * p.heads_dmodel;
-                        const int h = rem >> 6;
-                        const int dd = rem & 63;
-                        o = reinterpret_cast<T*>(p.out) +
-                            ((((long long)which * p.heads_B + b) * p.heads_H + h) * p.heads_T + tt) * 64 + dd;
-                    }
-                    uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 pk;
-                        pk.x = T16<T>::pack2(v[8 * j], v[8 * j + 1]);
-                        pk.y = T16<T>::pack2(v[8 * j + 2], v[8 * j + 3]);
-                        pk.z = T16<T>::pack2(v[8 * j + 4], v[8 * j + 5]);
-                        pk.w = T16<T>::pack2(v[8 * j + 6], v[8 * j + 7]);
-                        o4[j] = pk;
-                    }
-                } else {
-                    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ld_out + col0);
-                    if (p.mode == GEMM_OUT_F32_ADD) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 x = o4[j];
-                            x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
-                            o4[j] = x;
-                        }
-                    } else if (p.mode == GEMM_OUT_F32_GELU_POS) {
-                        const float4* p4 = reinterpret_cast<const float4*>(p.pos + (long long)row_in_batch * p.ld_pos + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 pp = __ldg(p4 + j);
-                            o4[j] = make_float4(v[4 * j] + pp.x, v[4 * j + 1] + pp.y, v[4 * j + 2] + pp.z, v[4 * j + 3] + pp.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                }
+                gemm_epilogue_chunk<T>(p, r, split, grow, row_in_batch, row_ok, col_base, c);
             }
             // release the accumulator stage back to the MMA warp
             tc_fence_before();
@@ -290,6 +297,158 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant for the big encoder GEMMs (plain 2-D operands, one split): a cluster of two CTAs works on two vertically adjacent
+// 128-row tiles of the SAME column block, so both need the same weight (B) tile.  Each CTA fetches half of it and TMA multicasts the
+// half into both CTAs' shared memory: per k-block a CTA pulls 16 KB (A) + BN/2 x 128 B (its half of B) through L2 instead of
+// 16 KB + BN x 128 B - at BN = 256 that is 32 KB instead of 48 KB, and L2 -> SM bandwidth is what bounds the single-CTA kernel
+// (48 KB per 4.2 MFLOP = 26 TB/s at tensor peak).  MMAs stay cta_group::1 (each CTA multiplies its own A tile by the full B tile in
+// its own shared memory); what crosses CTAs is the multicast load and the stage-release: a stage may be overwritten only when BOTH CTAs'
+// MMAs have read it, so tcgen05.commit multicasts its arrive to both CTAs' empty barriers (count 2).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhalf, const GemmKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = kStageA + p.stage_b_bytes;
+    uint8_t* smem_tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_tail);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 / 1: upper / lower tile of the pair, first / second half of B
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int half_bytes = p.stage_b_bytes / 2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmBhalf);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 2);   // this CTA's MMAs and the peer's (multicast commit)
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // the peer's barriers exist before anything is multicast at them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = pair; w < p.work; w += n_pairs) {
+                const int n_tile = w % p.tiles_n;
+                const int m_tile = 2 * (w / p.tiles_n) + (int)rank;
+                for (int kb = 0; kb < p.kb_per_split; ++kb) {
+                    mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);   // own A tile + both halves of B
+                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
+                    tma_load_2d_multicast(sa + kStageA + rank * half_bytes, &tmBhalf, &full_bar[stage], kb * kBlockK,
+                                          n_tile * p.bn + (int)rank * (p.bn / 2), (uint16_t)3);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int w = pair; w < p.work; w += n_pairs, ++it) {
+            const int acc = it & 1;
+            mbar_wait_bounded(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccStride;
+            for (int kb = 0; kb < p.kb_per_split; ++kb) {
+                mbar_wait_bounded(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageA);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    tc_commit_multicast(&empty_bar[stage], (uint16_t)3);   // releases the stage in both CTAs
+                    if (kb == p.kb_per_split - 1) tc_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;
+        const int csub = (warp - 2) >> 2;
+        int it = 0;
+        for (int w = pair; w < p.work; w += n_pairs, ++it) {
+            const int acc = it & 1;
+            const int n_tile = w % p.tiles_n;
+            const int m_tile = 2 * (w / p.tiles_n) + (int)rank;
+            const int row_in_batch = m_tile * kBlockM + quarter * 32 + lane;
+            const bool row_ok = row_in_batch < p.m_rows_per_batch;
+            const long long grow = row_in_batch;
+            mbar_wait_bounded(&tfull_bar[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
+            const int col_base = n_tile * p.bn;
+            for (int c = csub * 32; c < p.bn; c += 64) {
+                uint32_t r[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr + c, r);
+                tmem_ld_wait();
+                gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // neither CTA leaves while the peer may still multicast into it or arrive at its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -434,6 +593,40 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
         if (st != WK_OK) return st;
     }
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+    // CTA-pair path (two 128-row tiles of one column block per cluster, weight tile multicast): plain encoder-sized GEMMs only
+    if (d.pair && !d.a_3d && d.taps == 1 && p.splits == 1 && d.mode != GEMM_OUT_PARTIAL_T && d.bn % 16 == 0 && d.bn >= 32 && num_sms >= 2 &&
+        p.tiles_per_batch >= 2) {
+        CUtensorMap tmBh;
+        uint64_t dims[2] = {(uint64_t)d.k, (uint64_t)d.b_rows};
+        uint64_t str[1] = {(uint64_t)d.b_ld * 2};
+        uint32_t box[2] = {kBlockK, (uint32_t)d.bn / 2};
+        st = make_tmap(&tmBh, d.b, d.in_dtype, 2, dims, str, box);
+        if (st != WK_OK) return st;
+        p.work = ((p.tiles_per_batch + 1) / 2) * p.tiles_n;          // pair work items
+        p.tmem_cols = kTmemCols;
+        int pairs = std::min(p.work, num_sms / 2);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e;
+        if (d.in_dtype == WK_DTYPE_F16) {
+            static bool attr_set = false;
+            if (!attr_set) { e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; } attr_set = true; }
+            e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_pair_kernel<__half>, tmA, tmBh, p);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) { e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; } attr_set = true; }
+            e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_pair_kernel<__nv_bfloat16>, tmA, tmBh, p);
+        }
+        count_launch();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("gemm_tcgen05 (pair) launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
+        return WK_OK;
+    }
     int grid = p.work < num_sms ? p.work : num_sms;
     if (grid < 1) return WK_OK;
     cudaError_t e;

@@ -61,6 +61,7 @@ struct GemmDesc {
     int pdl;                 // launch with programmatic dependent launch (decode-step chain)
     int max_stages;          // 0 = as many smem stages as fit; >0 caps the ring (lets other kernels co-reside on the SM)
     int a_static;            // A operand (weights) does not depend on the upstream kernel: with PDL its first tiles are fetched before griddepcontrol.wait
+    int pair;                // run as 2-CTA clusters sharing the B (weight) tile by TMA multicast (plain 2-D, single-split GEMMs)
 };
 
 wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream);
