@@ -504,10 +504,13 @@ def run_own_arm(args):
             tj = json.load(open(traffic_file))
         except Exception:
             pass
+        roles = tj.get("by_bench_kernel_prefix", {})
         for kname, k in kernels.items():   # DRAM bytes per launch from the committed ncu --set full captures (tools/ncu_traffic.py)
-            short = kname.split("[")[0]
-            ent = tj.get(kname) or tj.get(short)
-            k["traffic"] = ent["bytes"] if ent and args.variant == "large-v3" and B == 64 else None
+            ent = next((v for pre, v in roles.items() if kname.startswith(pre)), None)
+            same_shape = args.variant in ("large-v3", "large-v3-turbo", "distil-large-v3") and (B == 64 or not kname.startswith("decoder"))
+            k["traffic"] = ent["bytes"] if ent and same_shape else None
+            if ent and same_shape and ent.get("tensor_pipe_pct") and k["bound"] == "tensor":
+                k["ncu_tensor_pipe_pct"] = ent["tensor_pipe_pct"]
         dom = max(kernels.items(), key=lambda kv: kv[1]["share_of_step"])
         line["roofline"] = {"kernel": dom[0], "bound": dom[1]["bound"], "achieved": dom[1]["achieved"], "peak": dom[1]["peak"],
                             "unit": dom[1]["unit"], "frac": dom[1]["frac"], "traffic": dom[1]["traffic"],
