@@ -362,20 +362,18 @@ wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, in
                  ((uint32_t)(kFaBM >> 4) << 24);
     p.v_lbo = 1; p.v_sbo = 64; p.v_kstep = 2048;
     dim3 grid((T + kFaBM - 1) / kFaBM, B * n_heads);
-    // softmax threads per query row: 2 (8 softmax warps) or 4 (16 warps: more warps per scheduler to hide the exp2 / pack latencies).
-    // WKB200_ATTN_PARTS (read once) keeps the other variant reachable for A/B timing.
-    static const int parts = (getenv("WKB200_ATTN_PARTS") && atoi(getenv("WKB200_ATTN_PARTS")) == 4) ? 4 : 2;
+    // P = 2 softmax threads per query row.  P = 4 (16 softmax warps, 32 keys and 16 output columns per thread) was built and measured on
+    // B200: correct, but slower (2.24 vs 2.05 ms per layer at 64 windows) - twice the row-max exchanges and named-barrier waits cost more
+    // than the extra warps hide - so only P = 2 is instantiated.
     cudaError_t e = cudaSuccess;
     if (dtype == WK_DTYPE_F16) {
-        if (parts == 4) { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
-                          if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, 4><<<grid, kFaThreadsFor(4), kFaSmem, stream>>>(tm, (__half*)out, p); }
-        else { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
-               if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__half*)out, p); }
+        static bool set = false;
+        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+        if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__half*)out, p);
     } else {
-        if (parts == 4) { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
-                          if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, 4><<<grid, kFaThreadsFor(4), kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p); }
-        else { static bool set = false; if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
-               if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p); }
+        static bool set = false;
+        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+        if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p);
     }
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fa): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     count_launch();
