@@ -375,6 +375,7 @@ def run_own_arm(args):
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
             fn()
+        e2e_stages.clear()      # per-stage wall clock of the timed calls only (the first call also builds the NCCL communicator's channels)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local_rank) if sample_clocks else None
@@ -455,7 +456,7 @@ def run_own_arm(args):
         mine = torch.tensor([e2e_stages.get(k, 0.0) / max(1, e2e_stages.get("_calls", 1)) for k in ("scatter_h2d_send", "transcribe", "gather_d2h")], device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        if rank == 0:   # host wall clock per stage and rank (warm-up call included): where the end-to-end time goes
+        if rank == 0:   # host wall clock per stage and rank, mean over the timed calls: where the end-to-end time goes
             line["e2e"]["stage_ms_per_rank"] = {k: [round(float(a[i]), 2) for a in allr] for i, k in enumerate(("scatter_h2d_send", "transcribe", "gather_d2h"))}
     assert sum(steps_run) <= expected_steps
 
