@@ -434,6 +434,9 @@ wk_status wk_test_attention(wk_model* m, const void* qkv, void* out, int32_t B, 
  * marks rows to skip. */
 wk_status wk_test_cross_attention(wk_model* m, const float* q, const void* kcross, const void* vcross, void* out, int32_t B, int32_t H,
                                   int32_t T, int32_t dtype, const int32_t* done);
+/* The beam-search form of the same kernel: groups of kv_div adjacent rows share one K/V block, K/V [B / kv_div][H][T][64]. */
+wk_status wk_test_cross_attention_shared(wk_model* m, const float* q, const void* kcross, const void* vcross, void* out, int32_t B, int32_t H,
+                                         int32_t T, int32_t dtype, const int32_t* done, int32_t kv_div);
 /* Decoder self-attention kernel alone: qkv [B][3*H*64] f32 of the new token, caches [B][H][224][64] 16-bit (positions < pos[b] valid;
  * row pos[b] is appended), pos [B] device -> out [B][H*64] 16-bit. */
 wk_status wk_test_self_attention(wk_model* m, const float* qkv, void* kcache, void* vcache, const int32_t* pos, void* out, int32_t B,

@@ -206,6 +206,7 @@ SYMBOLS = [
     ("wk_model_stream", P, [P]),
     ("wk_test_gemm", I32, [P, P, P, P, P, I32, I32, I32, I32, I32, I32]),
     ("wk_test_cross_attention", I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
+    ("wk_test_cross_attention_shared", I32, [P, P, P, P, P, I32, I32, I32, I32, P, I32]),
     ("wk_test_self_attention", I32, [P, P, P, P, P, P, I32, I32, I32, P]),
     ("wk_test_gemm_splitk", I32, [P, P, P, P, I32, I32, I32, I32, I32]),
     ("wk_test_attention", I32, [P, P, P, I32, I32, I32, I32]),

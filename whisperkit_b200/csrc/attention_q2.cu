@@ -25,6 +25,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -100,13 +102,36 @@ __device__ __forceinline__ uint64_t q2_sw128_desc(uint32_t smem_addr, uint32_t l
     d |= (uint64_t)2 << 61;
     return d;
 }
+// The tcgen05 instructions of the MMA warp are PREDICATED inside the asm on the lane `elect.sync` picks, instead of sitting in an
+// `if (lane == 0)` branch: UTCHMMA / UTCBAR take uniform-register operands, and inside a divergent branch (or under an ordinary per-thread
+// predicate) the compiler rebuilds every operand with an ELECT / R2UR.BROADCAST / BRA.U.ANY loop - ~125 clocks per MMA issued; that loop,
+// not the tensor pipe, bounded the first version of this kernel.  With elect.sync the issue path is straight-line code.  The warp must be
+// converged at every call (the callers __syncwarp() after their mbarrier spins).
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void q2_mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]: A is read from tensor memory (lane = row, two consecutive 16-bit K elements per 32-bit column)
 __device__ __forceinline__ void q2_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void q2_commit(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
         : "memory");
 }
 // 32 lanes x 32 columns of 32-bit: thread i of the warp writes lane (base+i), columns [c, c+32)
@@ -133,7 +158,7 @@ __device__ __forceinline__ void q2_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void q2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <typename T, int kPolyOf8>
+template <typename T, int kPolyOf8, bool kOrdered>
 __global__ void __launch_bounds__(kQ2Threads, 1)
 encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, const Q2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -180,7 +205,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
@@ -200,53 +225,60 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        auto mma_s = [&](int t, int j) {   // S_t = Q_t K_j^T (overwrites P_t(j-1): tcgen05.mma of one thread execute in issue order)
-            if (lane == 0) {
-                const uint64_t adesc = q2_sw128_desc(smem_u32(sQ + t * kQ2Tile), 1, 64);
-                const uint64_t bdesc = q2_sw128_desc(smem_u32(sK + (j % kQ2Stages) * kQ2Tile), 1, 64);
+        // every lane runs this code converged; only the tcgen05 instructions are predicated, on the lane elect.sync picks (see q2_mma_ss)
+        const uint64_t dbase = ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);   // see q2_sw128_desc(.., 1, 64)
+        const uint64_t qd0 = dbase | (uint64_t)((smem_u32(sQ) >> 4) & 0x3FFF);
+        const uint64_t kd0 = dbase | (uint64_t)((smem_u32(sK) >> 4) & 0x3FFF);
+        const uint64_t vd0 = dbase | (uint64_t)((smem_u32(sV) >> 4) & 0x3FFF);
+        constexpr uint64_t kTileStep = kQ2Tile >> 4;   // descriptor start-address units (16 B) per 16 KiB tile; all tiles sit below 256 KiB
+        const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
+        auto mma_s = [&](int t, int st) {   // S_t = Q_t K^T (overwrites P_t of the previous key tile: tcgen05.mma of one thread execute in issue order)
+            const uint64_t ad = qd0 + (uint64_t)t * kTileStep, bd = kd0 + (uint64_t)st * kTileStep;
+            const uint32_t d_addr = tmem + t * 128;
 #pragma unroll
-                for (int k = 0; k < kQ2D / 16; ++k)
-                    tc_mma_f16(tmem + t * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc_qk, k > 0 ? 1u : 0u);
-                tc_commit(&s_full[t]);
-                if (t == 1) tc_commit(&k_empty[j % kQ2Stages]);
-            }
-            __syncwarp();
+            for (int k = 0; k < kQ2D / 16; ++k) q2_mma_ss(d_addr, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+            q2_commit(&s_full[t]);
+            if (t == 1) q2_commit(&k_empty[st]);
         };
-        auto mma_pv = [&](int t, int j) {   // O_t (+)= P_t V_j
-            q2_wait(&p_full[t], j & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t vbase = smem_u32(sV + (j % kQ2Stages) * kQ2Tile);
-#pragma unroll
-                for (int k = 0; k < kQ2BN / 16; ++k) {
-                    // A = P_t: 16 keys = 8 TMEM columns per step.  B = V_j: MN-major (d contiguous, 128-byte rows), 16 keys = 16 rows = 2 KiB
-                    const uint64_t bdesc = q2_sw128_desc(vbase + k * 2048, 1, 64);
-                    q2_mma_ts(tmem + 256 + t * 64, tmem + t * 128 + k * 8, bdesc, p.idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-                }
-                if (t == 1) tc_commit(&v_empty[j % kQ2Stages]);
-                if (j + 1 == n) tc_commit(&o_full[t]);
-            }
+        auto mma_pv = [&](int t, int st, uint32_t par, bool first, bool last) {   // O_t (+)= P_t V
+            q2_wait(&p_full[t], par);
             __syncwarp();
+            tc_fence_after();
+            const uint64_t bd = vd0 + (uint64_t)st * kTileStep;
+            const uint32_t d_addr = tmem + 256 + t * 64, a_addr = tmem + t * 128;
+            // A = P_t: 16 keys = 8 TMEM columns per step.  B = V: MN-major (d contiguous, 128-byte rows), 16 keys = 16 rows = 2 KiB
+            q2_mma_ts(d_addr, a_addr, bd, idesc_pv, first ? 0u : 1u);
+#pragma unroll
+            for (int k = 1; k < kQ2BN / 16; ++k) q2_mma_ts(d_addr, a_addr + k * 8, bd + (uint64_t)(k * (2048 >> 4)), idesc_pv, 1u);
+            if (t == 1) q2_commit(&v_empty[st]);
+            if (last) q2_commit(&o_full[t]);
         };
         q2_wait(q_full, 0);
         q2_wait(&k_full[0], 0);
+        __syncwarp();
         tc_fence_after();
         mma_s(0, 0);
         mma_s(1, 0);
+        int st = 0, st_next = 1;
+        uint32_t ring_par = 0, ring_par_next = 0;   // parity of the ring slot st (st_next) for this (the next) key tile
         for (int j = 0; j < n; ++j) {
-            q2_wait(&v_full[j % kQ2Stages], (j / kQ2Stages) & 1);
-            mma_pv(0, j);
-            if (j + 1 < n) {
-                q2_wait(&k_full[(j + 1) % kQ2Stages], ((j + 1) / kQ2Stages) & 1);
+            const bool more = j + 1 < n;
+            q2_wait(&v_full[st], ring_par);
+            mma_pv(0, st, j & 1, j == 0, !more);
+            if (more) {
+                q2_wait(&k_full[st_next], ring_par_next);
+                __syncwarp();
                 tc_fence_after();
-                mma_s(0, j + 1);
+                mma_s(0, st_next);
             }
-            mma_pv(1, j);
-            if (j + 1 < n) mma_s(1, j + 1);
+            mma_pv(1, st, j & 1, j == 0, !more);
+            if (more) mma_s(1, st_next);
+            st = st_next; ring_par = ring_par_next;
+            if (++st_next == kQ2Stages) { st_next = 0; ring_par_next ^= 1; }
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ============================ softmax: one thread per query row ============================
         const int t = (warp - 4) >> 2;                // query tile
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
@@ -256,6 +288,11 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
         const uint32_t o_addr = tmem + lane_addr + 256 + t * 64;
         const float c = p.scale_log2e;
         const float2 c2 = make_float2(c, c);
+        // kOrdered: the A warp and the B warp of a scheduler take turns at the exponentials (64-thread named barriers 1..4 "A may go",
+        // 5..8 "B may go"): run together they would share the MUFU pipe and finish together, leaving the tensor core idle during the
+        // softmax and the MUFU pipe idle during the MMAs; in turns, one tile's MMAs hide under the other tile's exponentials
+        const uint32_t bar_own = 1 + t * 4 + quarter, bar_other = 1 + (t ^ 1) * 4 + quarter;
+        if (kOrdered && t == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
         float m_ref = -INFINITY;      // the maximum O_t and l are relative to
         float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
 
@@ -305,6 +342,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
             }
             const float nmsc = -m_ref * c;
             const float2 nm2 = make_float2(nmsc, nmsc);
+            if (kOrdered) asm volatile("bar.sync %0, 64;" ::"r"(bar_own) : "memory");
             // P_t(j): 128 probabilities per row -> 64 packed columns over the first half of S_t (all of S_t is in registers by now)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -328,6 +366,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
                 }
                 q2_tmem_st_32x32(s_addr + half * 32, pk);
             }
+            if (kOrdered && !(t == 1 && j + 1 == n)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
             q2_tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -400,29 +439,33 @@ wk_status encoder_attention_q2(const void* qkv, void* out, int B, int T, int n_h
     p.idesc_pv = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(kQ2D >> 3) << 17) |
                  ((uint32_t)(kQ2BM >> 4) << 24);
     dim3 grid((T + 2 * kQ2BM - 1) / (2 * kQ2BM), B * n_heads);
-    static const int poly = [] { const char* e = getenv("WKB200_ATTN_POLY"); return e ? atoi(e) : 0; }();   // bring-up switch
+    static const int poly = [] { const char* e = getenv("WKB200_ATTN_POLY"); return e ? atoi(e) : 0; }();      // bring-up switches
+    static const bool ordered = [] { const char* e = getenv("WKB200_ATTN_ORDER"); return !(e && e[0] == '0'); }();
     cudaError_t e = cudaSuccess;
     auto launch = [&](auto kern, auto* o) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2Smem);
         if (e == cudaSuccess) kern<<<grid, kQ2Threads, kQ2Smem, stream>>>(tm, o, p);
     };
-    if (dtype == WK_DTYPE_F16) {
-        __half* o = (__half*)out;
-        switch (poly) {
-            case 2: launch(encoder_attention_q2_kernel<__half, 2>, o); break;
-            case 3: launch(encoder_attention_q2_kernel<__half, 3>, o); break;
-            case 4: launch(encoder_attention_q2_kernel<__half, 4>, o); break;
-            default: launch(encoder_attention_q2_kernel<__half, 0>, o); break;
+    auto pick = [&](auto* o) {
+        using OT = std::remove_pointer_t<decltype(o)>;
+        if (ordered) {
+            switch (poly) {
+                case 2: launch(encoder_attention_q2_kernel<OT, 2, true>, o); break;
+                case 3: launch(encoder_attention_q2_kernel<OT, 3, true>, o); break;
+                case 4: launch(encoder_attention_q2_kernel<OT, 4, true>, o); break;
+                default: launch(encoder_attention_q2_kernel<OT, 0, true>, o); break;
+            }
+        } else {
+            switch (poly) {
+                case 2: launch(encoder_attention_q2_kernel<OT, 2, false>, o); break;
+                case 3: launch(encoder_attention_q2_kernel<OT, 3, false>, o); break;
+                case 4: launch(encoder_attention_q2_kernel<OT, 4, false>, o); break;
+                default: launch(encoder_attention_q2_kernel<OT, 0, false>, o); break;
+            }
         }
-    } else {
-        __nv_bfloat16* o = (__nv_bfloat16*)out;
-        switch (poly) {
-            case 2: launch(encoder_attention_q2_kernel<__nv_bfloat16, 2>, o); break;
-            case 3: launch(encoder_attention_q2_kernel<__nv_bfloat16, 3>, o); break;
-            case 4: launch(encoder_attention_q2_kernel<__nv_bfloat16, 4>, o); break;
-            default: launch(encoder_attention_q2_kernel<__nv_bfloat16, 0>, o); break;
-        }
-    }
+    };
+    if (dtype == WK_DTYPE_F16) pick((__half*)out);
+    else pick((__nv_bfloat16*)out);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fa q2): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     count_launch();
     e = cudaGetLastError();

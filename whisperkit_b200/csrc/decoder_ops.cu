@@ -8,6 +8,8 @@
 #include <curand_kernel.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <algorithm>
 #include "kernels.h"
@@ -793,6 +795,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
                                   const int32_t* done, float* align_scratch, uint32_t align_mask, int kv_div) {
     if (kv_div < 1 || B % kv_div != 0) { set_error("decoder_cross_attention: %d rows do not split into groups of %d", B, kv_div); return WK_ERR_INVALID_ARGUMENT; }
     if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
+    static const bool mq_tc = [] { const char* e = getenv("WKB200_MQ_TC"); return e && e[0] == '1'; }();   // bring-up switch
+    if (mq_tc && kv_div > 1 && kv_div <= 8 && align_scratch == nullptr)
+        return decoder_cross_attention_mq(partial, splits, Bp, bq, kcross, vcross, out, B, H, T, dtype, stream, done, kv_div);
     if (kv_div > 1 && kv_div <= 8 && align_scratch == nullptr) {
         // beam search: one CTA per (window, head) serves all beams from one pass over the K/V block
         wk_status r = WK_ERR_INVALID_ARGUMENT;

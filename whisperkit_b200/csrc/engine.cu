@@ -1027,6 +1027,21 @@ wk_status wk_test_cross_attention(wk_model* m, const float* q, const void* kcros
     return r;
 }
 
+// the beam-search form: B rows in groups of kv_div adjacent rows that share one K/V block ([B / kv_div][H][T][64])
+wk_status wk_test_cross_attention_shared(wk_model* m, const float* q, const void* kcross, const void* vcross, void* out, int32_t B, int32_t H,
+                                         int32_t T, int32_t dtype, const int32_t* done, int32_t kv_div) {
+    if (!m || !q || !kcross || !vcross || !out || B < 1 || H < 1 || H > 32 || kv_div < 1) { set_error("wk_test_cross_attention_shared: bad arguments"); return WK_ERR_INVALID_ARGUMENT; }
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    float* zero = nullptr;
+    WK_CHECK(dmalloc(&zero, (size_t)H * 64));
+    wk_status r = decoder_cross_attention(q, 1, B, zero, kcross, vcross, out, B, H, T, dtype, m->stream, done, nullptr, 0, kv_div);
+    cudaError_t e = cudaStreamSynchronize(m->stream);
+    cudaFree(zero);
+    if (r == WK_OK && e != cudaSuccess) { set_error("wk_test_cross_attention_shared: %s", cudaGetErrorString(e)); r = WK_ERR_CUDA; }
+    return r;
+}
+
 // decoder_self_attention_kernel alone: qkv [B][3*H*64] f32 (q | k | v of the new token, biases included), caches [B][H][224][64] 16-bit
 // holding positions < pos[b]; appends the new K/V row at pos[b] and writes out [B][H*64]
 wk_status wk_test_self_attention(wk_model* m, const float* qkv, void* kcache, void* vcache, const int32_t* pos, void* out, int32_t B,

@@ -183,7 +183,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // the whole warp runs this converged; the TMA / mbarrier instructions are predicated on the elect.sync lane (common.cuh)
+        {
             int stage = 0;
             uint32_t phase = 0;
             bool need_wait = early_a;
@@ -193,13 +194,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
                 uint8_t* sb = sa + kStageA;
                 if (do_a) {
-                    mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+                    mbar_expect_tx_elect(&full_bar[st], (uint32_t)stage_bytes);
                     const int ac0 = p.tap_col_off[tap] + kk * kBlockK;
                     const int ar = row0 + p.tap_row_shift[tap];
-                    if (p.a_is_3d) tma_load_3d(sa, &tmA, &full_bar[st], ac0, ar, batch);
-                    else tma_load_2d(sa, &tmA, &full_bar[st], ac0, ar);
+                    if (p.a_is_3d) tma_load_3d_elect(sa, &tmA, &full_bar[st], ac0, ar, batch);
+                    else tma_load_2d_elect(sa, &tmA, &full_bar[st], ac0, ar);
                 }
-                if (do_b) tma_load_2d(sb, &tmB, &full_bar[st], kb * kBlockK, n_tile * p.bn);
+                if (do_b) tma_load_2d_elect(sb, &tmB, &full_bar[st], kb * kBlockK, n_tile * p.bn);
             };
             for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
                 const int split = w % p.splits;
@@ -222,6 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 for (; kb < kb0 + p.kb_per_split; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    __syncwarp();
                     issue(kb, stage, row0, batch, n_tile, true, true);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -233,6 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        const uint32_t idesc = p.idesc;
         for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -241,21 +244,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t d_tmem = tmem_base + acc * kAccStride;
             for (int kb = 0; kb < p.kb_per_split; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
+                __syncwarp();   // converged from here: the tcgen05 instructions below are predicated on the elect.sync lane (common.cuh)
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageA);
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageA);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance the start address by k*32 bytes inside the swizzle atom (>>4 -> +2k)
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                   (kb > 0 || k > 0) ? 1u : 0u);
-                    }
-                    tc_commit(&empty_bar[stage]);
-                    if (kb == p.kb_per_split - 1) tc_commit(&tfull_bar[acc]);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    // advance the start address by k*32 bytes inside the swizzle atom (>>4 -> +2k)
+                    tc_mma_f16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
-                __syncwarp();
+                tc_commit_elect(&empty_bar[stage]);
+                if (kb == p.kb_per_split - 1) tc_commit_elect(&tfull_bar[acc]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -325,6 +325,21 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_multicast_elect(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast_elect(uint64_t* bar, uint16_t mask) {   // converged warp, see tc_mma_f16_elect
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
@@ -373,7 +388,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // the whole warp runs this converged; the TMA / mbarrier instructions are predicated on the elect.sync lane (common.cuh)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int w = pair; w < p.work; w += n_pairs) {
@@ -381,11 +397,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int m_tile = 2 * (w / p.tiles_n) + (int)rank;
                 for (int kb = 0; kb < p.kb_per_split; ++kb) {
                     mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+                    __syncwarp();
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);   // own A tile + both halves of B
-                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
-                    tma_load_2d_multicast(sa + kStageA + rank * half_bytes, &tmBhalf, &full_bar[stage], kb * kBlockK,
-                                          n_tile * p.bn + (int)rank * (p.bn / 2), (uint16_t)3);
+                    mbar_expect_tx_elect(&full_bar[stage], (uint32_t)stage_bytes);   // own A tile + both halves of B
+                    tma_load_2d_elect(sa, &tmA, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
+                    tma_load_2d_multicast_elect(sa + kStageA + rank * half_bytes, &tmBhalf, &full_bar[stage], kb * kBlockK,
+                                                n_tile * p.bn + (int)rank * (p.bn / 2), (uint16_t)3);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -395,6 +412,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        const uint32_t idesc = p.idesc;
         for (int w = pair; w < p.work; w += n_pairs, ++it) {
             const int acc = it & 1;
             mbar_wait_bounded(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
@@ -402,18 +420,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t d_tmem = tmem_base + acc * kAccStride;
             for (int kb = 0; kb < p.kb_per_split; ++kb) {
                 mbar_wait_bounded(&full_bar[stage], phase);
+                __syncwarp();   // converged from here: the tcgen05 instructions below are predicated on the elect.sync lane (common.cuh)
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageA);
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                const uint64_t bdesc = make_kmajor_sw128_desc(sa + kStageA);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    tc_commit_multicast(&empty_bar[stage], (uint16_t)3);   // releases the stage in both CTAs
-                    if (kb == p.kb_per_split - 1) tc_commit(&tfull_bar[acc]);
-                }
-                __syncwarp();
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                    tc_mma_f16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                tc_commit_multicast_elect(&empty_bar[stage], (uint16_t)3);   // releases the stage in both CTAs
+                if (kb == p.kb_per_split - 1) tc_commit_elect(&tfull_bar[acc]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }

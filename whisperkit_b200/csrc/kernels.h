@@ -174,6 +174,9 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
                                   const int32_t* done = nullptr, float* align_scratch = nullptr, uint32_t align_mask = 0, int kv_div = 1);
 // kv_div > 1 (beam search): row b reads the K/V block of window b / kv_div; the CTAs of one (window, head) are adjacent in the grid so that
 // their K/V stream is shared through L2
+// tensor-core variant for nq = 2..8 rows per K/V block (cross_attention_mq.cu): one K/V stream per (window, head) serves all nq beams
+wk_status decoder_cross_attention_mq(const float* partial, int splits, int Bp, const float* bq, const void* kcross, const void* vcross, void* out, int B, int H,
+                                     int Tlen, int dtype, cudaStream_t stream, const int32_t* done, int nq);
 // alignment row of the step just sampled (run AFTER the sampler advanced steps[b] to tokenIndex + 1): out[b][steps[b]][t] =
 // Float16(mean over n_slots of scratch[slot][b][t]) unless done[b] (TextDecoder.updateAlignmentWeights, TextDecoder.swift:272-296:
 // the slice of step tokenIndex lands in row tokenIndex + 1; a completed segment breaks out before the update, :668-674)
