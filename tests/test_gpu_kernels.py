@@ -111,6 +111,38 @@ def test_decoder_cross_attention_kernel_vs_torch(toy, dt, B, H):
 
 
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("W,NQ,H,T", [(32, 5, 20, 1500), (3, 2, 6, 1500), (2, 8, 2, 250), (1, 3, 1, 1500)])
+def test_decoder_cross_attention_shared_kv_vs_torch(toy, dt, W, NQ, H, T):
+    """The beam-search form of cross-attention: NQ adjacent decode rows (the beams of one window) read ONE K/V block.  Checked against
+    torch fp32 on the same 16-bit K/V at the benchmarked beam shape (32 windows x 5 beams, H = 20, T = 1500); a window flagged done (its
+    beams end together) must be left untouched; one peaked row exercises the max subtraction."""
+    tdt, wdt = TD[dt]
+    B, dm = W * NQ, H * 64
+    g = torch.Generator(device="cuda").manual_seed(W * 31 + NQ * 7 + H)
+    q = torch.randn(B, dm, device="cuda", generator=g)
+    k = (torch.randn(W, H, T, 64, device="cuda", generator=g) * 0.7).to(tdt)
+    v = torch.randn(W, H, T, 64, device="cuda", generator=g).to(tdt)
+    k[0, 0, T - 3] = (q[1, :64] * 3).to(tdt)
+    out = torch.full((B, dm), 7.0, device="cuda", dtype=tdt)
+    done = torch.zeros(B, dtype=torch.int32, device="cuda")
+    if W > 2:
+        done[2 * NQ:3 * NQ] = 1
+    _sync()
+    wk._lib.check(toy.lib.wk_test_cross_attention_shared(toy.handle, p(q), p(k), p(v), p(out), B, H, T, wdt, p(done), NQ))
+    torch.cuda.synchronize()
+    qh = q.view(W, NQ, H, 64).transpose(1, 2)                       # [W, H, NQ, 64]
+    ref = torch.softmax(qh @ k.float().transpose(-1, -2) * 0.125, dim=-1) @ v.float()   # [W, H, NQ, 64]
+    ref = ref.transpose(1, 2).reshape(B, dm)
+    got = out.float()
+    live = done == 0
+    err = (got[live] - ref[live]).abs().max().item()
+    tol = (8e-3 if dt == "bf16" else 1e-3) * max(1.0, ref.abs().max().item())
+    assert err <= tol, err
+    if W > 2:
+        assert torch.all(got[2 * NQ:3 * NQ] == 7.0)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
 @pytest.mark.parametrize("B,H", [(64, 20), (5, 6)])
 def test_decoder_self_attention_kernel_vs_torch(toy, dt, B, H):
     """decoder_self_attention_kernel alone at B = 64, H = 20 with per-row positions 0 / 1 / 100 / 222 (and everything between): reduces

@@ -5,8 +5,10 @@
 //   warp 0        TMA producer: Q_A, Q_B once, then K / V tiles of 128 keys through 4-deep smem rings (128B swizzle)
 //   warp 1        MMA issuer, per key tile j and query tile t:
 //                     S_t  = Q_t K_j^T          tcgen05.mma 128x128x16 x4, A and B from smem, accumulator S_t in TMEM
-//                     O_t += P_t V_j            tcgen05.mma 128x64x16  x8, A = P_t FROM TMEM (16-bit, written over S_t by the
-//                                               softmax warps), B = V_j MN-major from smem, accumulator O_t in TMEM
+//                     O_t += P_t V_j            tcgen05.mma 128x64x16  x8, A = P_t FROM TMEM (16-bit, written by the softmax warps
+//                                               into its own 64 columns), B = V_j MN-major from smem, accumulator O_t in TMEM
+//                 S_t(j+1) is issued as soon as the softmax warps have READ S_t(j) into registers (s_free), i.e. it runs under the
+//                 exponentials of tile j: the only serial chain left per query tile is load-S / max / exp / store-P
 //   warps 4..7    softmax of tile A, ONE thread per query row (warp w owns TMEM lane quarter w & 3)
 //   warps 8..11   softmax of tile B
 // (warps 2, 3 only fill warpgroup 0: setmaxnreg moves registers per warpgroup - 24 for warpgroup 0, 240 for the softmax warpgroups, whose
@@ -18,9 +20,9 @@
 // of the K / V traffic from L2.
 //
 // Online softmax with a lazy rescale: O_t and the row sum are relative to a reference maximum m_ref that only moves when some row
-// of the warp finds a score more than 2^8 above it (then the owning warp rescales its 32 rows of O_t in TMEM itself - the commit that
-// published S_t(j) also covers P_t V_(j-1), so O_t is quiescent between s_full and p_full).  Probabilities are therefore <= 2^8, exact
-// in f32 sums and inside bf16 / f16 range.
+// of the warp finds a score more than 2^8 above it (then the owning warp rescales its 32 rows of O_t in TMEM itself, after pv_done says
+// that P_t V_(j-1) has completed; P_t V_j cannot start before this warp publishes P_t(j), so O_t is quiescent meanwhile).  Probabilities
+// are therefore <= 2^8, exact in f32 sums and inside bf16 / f16 range.
 // Reference counterpart: inside AudioEncoder.mlmodelc (Sources/WhisperKit/Core/AudioEncoder.swift:59-62).
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,7 +41,7 @@ static constexpr int kQ2D = 64;
 static constexpr int kQ2Tile = kQ2BN * kQ2D * 2;   // 16 KiB: one K or V or Q tile, 128-byte rows
 static constexpr int kQ2Stages = 4;
 static constexpr int kQ2Smem = 2 * kQ2Tile /*Q_A, Q_B*/ + 2 * kQ2Stages * kQ2Tile /*K, V rings*/ + 1024 /*align*/ + 512 /*barriers*/;
-static constexpr int kQ2TmemCols = 512;    // S_A @0, S_B @128 (P_t over the first 64 columns of S_t), O_A @256, O_B @320
+static constexpr int kQ2TmemCols = 512;    // S_A @0, S_B @128, P_A @256, P_B @320 (16-bit: 64 columns each), O_A @384, O_B @448
 static constexpr float kQ2RescaleLog2 = 8.f;
 
 struct Q2Params {
@@ -172,10 +174,12 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
     uint64_t* k_empty = k_full + kQ2Stages;
     uint64_t* v_full = k_empty + kQ2Stages;
     uint64_t* v_empty = v_full + kQ2Stages;
-    uint64_t* s_full = v_empty + kQ2Stages;       // 2 (per query tile): S_t(j) complete, and with it P_t V_(j-1)
-    uint64_t* p_full = s_full + 2;                // 2: P_t(j) is in TMEM (and O_t rescaled if it had to be)
-    uint64_t* o_full = p_full + 2;                // 2: the last P_t V is complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    uint64_t* s_full = v_empty + kQ2Stages;       // 2 (per query tile): S_t(j) complete
+    uint64_t* s_free = s_full + 2;                // 2: the softmax warps hold S_t(j) in registers, S_t may be overwritten
+    uint64_t* p_full = s_free + 2;                // 2: P_t(j) is in TMEM (and O_t rescaled if it had to be)
+    uint64_t* pv_done = p_full + 2;               // 2: P_t V_j complete: P_t may be overwritten, O_t may be rescaled / read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    float* zero_slot = reinterpret_cast<float*>(tmem_slot + 1);   // holds 0.0f: see the turn barrier in the softmax loop
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y;
@@ -185,13 +189,14 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_qkv);
+        *zero_slot = 0.f;
         mbar_init(q_full, 1);
         for (int i = 0; i < kQ2Stages; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
         }
         fence_barrier_init();
     }
@@ -232,7 +237,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
         const uint64_t vd0 = dbase | (uint64_t)((smem_u32(sV) >> 4) & 0x3FFF);
         constexpr uint64_t kTileStep = kQ2Tile >> 4;   // descriptor start-address units (16 B) per 16 KiB tile; all tiles sit below 256 KiB
         const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
-        auto mma_s = [&](int t, int st) {   // S_t = Q_t K^T (overwrites P_t of the previous key tile: tcgen05.mma of one thread execute in issue order)
+        auto mma_s = [&](int t, int st) {   // S_t = Q_t K^T
             const uint64_t ad = qd0 + (uint64_t)t * kTileStep, bd = kd0 + (uint64_t)st * kTileStep;
             const uint32_t d_addr = tmem + t * 128;
 #pragma unroll
@@ -240,18 +245,18 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
             q2_commit(&s_full[t]);
             if (t == 1) q2_commit(&k_empty[st]);
         };
-        auto mma_pv = [&](int t, int st, uint32_t par, bool first, bool last) {   // O_t (+)= P_t V
+        auto mma_pv = [&](int t, int st, uint32_t par, bool first) {   // O_t (+)= P_t V
             q2_wait(&p_full[t], par);
             __syncwarp();
             tc_fence_after();
             const uint64_t bd = vd0 + (uint64_t)st * kTileStep;
-            const uint32_t d_addr = tmem + 256 + t * 64, a_addr = tmem + t * 128;
+            const uint32_t d_addr = tmem + 384 + t * 64, a_addr = tmem + 256 + t * 64;
             // A = P_t: 16 keys = 8 TMEM columns per step.  B = V: MN-major (d contiguous, 128-byte rows), 16 keys = 16 rows = 2 KiB
             q2_mma_ts(d_addr, a_addr, bd, idesc_pv, first ? 0u : 1u);
 #pragma unroll
             for (int k = 1; k < kQ2BN / 16; ++k) q2_mma_ts(d_addr, a_addr + k * 8, bd + (uint64_t)(k * (2048 >> 4)), idesc_pv, 1u);
+            q2_commit(&pv_done[t]);
             if (t == 1) q2_commit(&v_empty[st]);
-            if (last) q2_commit(&o_full[t]);
         };
         q2_wait(q_full, 0);
         q2_wait(&k_full[0], 0);
@@ -262,17 +267,20 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
         int st = 0, st_next = 1;
         uint32_t ring_par = 0, ring_par_next = 0;   // parity of the ring slot st (st_next) for this (the next) key tile
         for (int j = 0; j < n; ++j) {
-            const bool more = j + 1 < n;
-            q2_wait(&v_full[st], ring_par);
-            mma_pv(0, st, j & 1, j == 0, !more);
-            if (more) {
+            if (j + 1 < n) {   // S(j+1) of both tiles as soon as their S(j) has been read: runs under the exponentials of tile j
                 q2_wait(&k_full[st_next], ring_par_next);
+                q2_wait(&s_free[0], j & 1);
                 __syncwarp();
                 tc_fence_after();
                 mma_s(0, st_next);
+                q2_wait(&s_free[1], j & 1);
+                __syncwarp();
+                tc_fence_after();
+                mma_s(1, st_next);
             }
-            mma_pv(1, st, j & 1, j == 0, !more);
-            if (more) mma_s(1, st_next);
+            q2_wait(&v_full[st], ring_par);
+            mma_pv(0, st, j & 1, j == 0);
+            mma_pv(1, st, j & 1, j == 0);
             st = st_next; ring_par = ring_par_next;
             if (++st_next == kQ2Stages) { st_next = 0; ring_par_next ^= 1; }
         }
@@ -285,7 +293,8 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
         const int row = quarter * 32 + lane;          // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const uint32_t s_addr = tmem + lane_addr + t * 128;
-        const uint32_t o_addr = tmem + lane_addr + 256 + t * 64;
+        const uint32_t p_addr = tmem + lane_addr + 256 + t * 64;
+        const uint32_t o_addr = tmem + lane_addr + 384 + t * 64;
         const float c = p.scale_log2e;
         const float2 c2 = make_float2(c, c);
         // kOrdered: the A warp and the B warp of a scheduler take turns at the exponentials (64-thread named barriers 1..4 "A may go",
@@ -303,6 +312,9 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(s_addr + ch * 32, sr[ch]);
             tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t]);   // S_t(j) is in registers: the MMA warp may start S_t(j+1)
             const int valid = p.T - j * kQ2BN;   // keys of this tile that exist (>= 128 except at the end)
             if (valid < kQ2BN) {
 #pragma unroll
@@ -330,6 +342,8 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
                 const float corr = q2_ex2((m_ref - m_new) * c);
                 m_ref = m_new;
                 l2a.x *= corr; l2a.y *= corr; l2b.x *= corr; l2b.y *= corr;
+                q2_wait(&pv_done[t], (j - 1) & 1);   // P_t V_(j-1) has landed in O_t
+                tc_fence_after();
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t orr[32];
@@ -340,10 +354,16 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
                     q2_tmem_st_32x32(o_addr + half * 32, orr);
                 }
             }
-            const float nmsc = -m_ref * c;
+            float nmsc = -m_ref * c;
+            if (kOrdered) {
+                // my turn at the MUFU pipe.  The exponentials are pure register arithmetic, which ptxas schedules across a barrier as it
+                // likes; a volatile shared-memory load (of 0.0f) placed after the barrier and folded into their common operand pins them
+                float z;
+                asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(bar_own), "r"(smem_u32(zero_slot)) : "memory");
+                nmsc += z;
+            }
             const float2 nm2 = make_float2(nmsc, nmsc);
-            if (kOrdered) asm volatile("bar.sync %0, 64;" ::"r"(bar_own) : "memory");
-            // P_t(j): 128 probabilities per row -> 64 packed columns over the first half of S_t (all of S_t is in registers by now)
+            // P_t(j): 128 probabilities per row -> 64 packed 16-bit columns
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t pk[32];
@@ -364,7 +384,11 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
                         pk[cc * 16 + (i >> 1) + 1] = T16<T>::pack2(e1.x, e1.y);
                     }
                 }
-                q2_tmem_st_32x32(s_addr + half * 32, pk);
+                if (half == 0 && j > 0) {   // the P buffer is free once P_t V_(j-1) has completed (long ago, normally)
+                    q2_wait(&pv_done[t], (j - 1) & 1);
+                    tc_fence_after();
+                }
+                q2_tmem_st_32x32(p_addr + half * 32, pk);
             }
             if (kOrdered && !(t == 1 && j + 1 == n)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
             q2_tmem_st_wait();
@@ -373,7 +397,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
             if (lane == 0) mbar_arrive(&p_full[t]);
         }
         // ---- epilogue: O_t / l, 64 columns = one 128-byte row segment per thread
-        q2_wait(&o_full[t], 0);
+        q2_wait(&pv_done[t], (n - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
         const int q = q0 + t * kQ2BM + row;

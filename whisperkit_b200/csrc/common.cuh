@@ -52,6 +52,46 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// packed f32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): one issue slot for two lanes of work
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// gelu_erf on two values at once: the same formula, the FMA-pipe part packed (the FC1 epilogue is bound by its instruction issue)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 z = make_float2(fabsf(x.x) * 0.70710678118654752440f, fabsf(x.y) * 0.70710678118654752440f);
+    const float2 den = fma2(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+    float2 poly = fma2(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    poly = fma2(poly, t, make_float2(1.421413741f, 1.421413741f));
+    poly = fma2(poly, t, make_float2(-0.284496736f, -0.284496736f));
+    poly = fma2(poly, t, make_float2(0.254829592f, 0.254829592f));
+    const float2 nz2 = mul2(mul2(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));   // -z^2 * log2(e)
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(nz2.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(nz2.y));
+    const float2 pt = mul2(make_float2(-poly.x, -poly.y), t);
+    const float2 erf_abs = fma2(pt, e, make_float2(1.0f, 1.0f));
+    const float2 hx = mul2(make_float2(0.5f, 0.5f), x);
+    return fma2(hx, make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y)), hx);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

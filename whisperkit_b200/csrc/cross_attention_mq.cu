@@ -24,6 +24,7 @@ namespace wk {
 static constexpr int kMqThreads = 160;            // 4 consumer warps + 1 producer warp
 static constexpr int kMqRows = 128;               // keys per tile
 static constexpr int kMqStageBytes = kMqRows * 128;
+static constexpr float kMqPScale = 1024.f;         // probabilities are carried as p * 2^10 through the P V product
 
 __device__ __forceinline__ void mq_ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -147,12 +148,12 @@ decoder_cross_attention_mqt_kernel(const __grid_constant__ CUtensorMap tm_k, con
         float sm = 0.f;
         for (int t = lane; t < Tlen; t += 32) {
             const float pr = __expf(sc[t] - mx);
-            sc[t] = pr;
+            sc[t] = pr * kMqPScale;   // stored scaled: keeps the lo half of the 16-bit split out of the f16 subnormals (p ~ 1 / Tlen)
             sm += pr;
         }
         for (int t = Tlen + lane; t < Tp; t += 32) sc[t] = 0.f;
         sm = warp_sum(sm);
-        if (lane == 0) stat[j] = 1.f / sm;
+        if (lane == 0) stat[j] = 1.f / (sm * kMqPScale);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---- V phase: out_j[d] = sum_t p_j[t] V[t][d]; warp w takes k-steps 2w, 2w+1 (16 keys each) of every tile, all 64 output columns

@@ -87,7 +87,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const 
     }
     if (p.gelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 32; j += 2) {
+            const float2 g = gelu_erf2(make_float2(v[j], v[j + 1]));
+            v[j] = g.x; v[j + 1] = g.y;
+        }
     }
     if (p.mode == GEMM_OUT_T16 || p.mode == GEMM_OUT_T16_HEADS) {
         T* o;
