@@ -34,13 +34,13 @@
 
 namespace wk {
 
-static constexpr int kQ2Threads = 384;   // warpgroup 0: TMA warp, MMA warp, two idle warps; warpgroups 1 and 2: softmax of tile A / B
+static constexpr int kQ2Threads = 384;   // (kSplit = 1) warpgroup 0: TMA warp, MMA warp, two idle warps; warpgroups 1 and 2: softmax of tile A / B
 static constexpr int kQ2BM = 128;          // queries per tile (two tiles per CTA)
 static constexpr int kQ2BN = 128;          // keys per tile
 static constexpr int kQ2D = 64;
 static constexpr int kQ2Tile = kQ2BN * kQ2D * 2;   // 16 KiB: one K or V or Q tile, 128-byte rows
 static constexpr int kQ2Stages = 4;
-static constexpr int kQ2Smem = 2 * kQ2Tile /*Q_A, Q_B*/ + 2 * kQ2Stages * kQ2Tile /*K, V rings*/ + 1024 /*align*/ + 512 /*barriers*/;
+static constexpr int kQ2Smem = 2 * kQ2Tile /*Q_A, Q_B*/ + 2 * kQ2Stages * kQ2Tile /*K, V rings*/ + 1024 /*align*/ + 512 /*barriers*/ + 2048 /*exchange*/;
 static constexpr int kQ2TmemCols = 512;    // S_A @0, S_B @128, P_A @256, P_B @320 (16-bit: 64 columns each), O_A @384, O_B @448
 static constexpr float kQ2RescaleLog2 = 8.f;
 
@@ -160,8 +160,11 @@ __device__ __forceinline__ void q2_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void q2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <typename T, int kPolyOf8, bool kOrdered>
-__global__ void __launch_bounds__(kQ2Threads, 1)
+// kSplit = softmax threads per query row: 1 (a thread owns a whole 128-score row, 8 softmax warps) or 2 (each thread owns 64 of the
+// tile's keys and 32 of the output columns, 16 softmax warps - four per scheduler instead of two, which is what hides the MUFU / TMEM
+// latencies of the serial load-max-exp-store chain; the two threads of a row only meet in one OR-reducing named barrier per tile)
+template <typename T, int kPolyOf8, bool kOrdered, int kSplit>
+__global__ void __launch_bounds__(128 + 256 * kSplit, 1)
 encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, const Q2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -180,6 +183,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
     uint64_t* pv_done = p_full + 2;               // 2: P_t V_j complete: P_t may be overwritten, O_t may be rescaled / read
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
     float* zero_slot = reinterpret_cast<float*>(tmem_slot + 1);   // holds 0.0f: see the turn barrier in the softmax loop
+    float* xch = reinterpret_cast<float*>(bars + 64);             // kSplit = 2: [tile][half][128 rows] row-max / row-sum exchange (2 KiB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y;
@@ -196,7 +200,7 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4 * kSplit); mbar_init(&p_full[i], 4 * kSplit); mbar_init(&pv_done[i], 1);
         }
         fence_barrier_init();
     }
@@ -210,7 +214,8 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
@@ -285,6 +290,136 @@ encoder_attention_q2_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __res
             if (++st_next == kQ2Stages) { st_next = 0; ring_par_next ^= 1; }
         }
     }
+    } else if constexpr (kSplit == 2) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");   // 640 threads are launched at 96 registers; warpgroup 0 gave up 40 each
+        // ============================ softmax: two threads per query row ============================
+        const int sw = warp - 4;
+        const int t = sw >> 3;                        // query tile
+        const int hf = (sw >> 2) & 1;                 // which 64 of the tile's 128 keys, which 32 of the 64 output columns
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch (the four warps of a row quarter share a scheduler)
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t s_addr = tmem + lane_addr + t * 128 + hf * 64;
+        const uint32_t p_addr = tmem + lane_addr + 256 + t * 64 + hf * 32;
+        const uint32_t o_addr = tmem + lane_addr + 384 + t * 64 + hf * 32;
+        const uint32_t pair_bar = 1 + t * 4 + quarter;   // 64-thread named barrier of the two warps that share these 32 rows
+        float* x_mine = xch + (t * 2 + hf) * 128 + row;
+        const float* x_other = xch + (t * 2 + (hf ^ 1)) * 128 + row;
+        const float c = p.scale_log2e;
+        const float2 c2 = make_float2(c, c);
+        float m_ref = -INFINITY;      // identical in both threads of a row
+        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);   // this thread's share of the row sum
+
+        for (int j = 0; j < n; ++j) {
+            q2_wait(&s_full[t], j & 1);
+            tc_fence_after();
+            uint32_t sr[2][32];
+            tmem_ld_32x32(s_addr, sr[0]);
+            tmem_ld_32x32(s_addr + 32, sr[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t]);
+            const int valid = p.T - j * kQ2BN - hf * 64;   // keys of this thread's half that exist
+            if (valid < 64) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i >= valid) sr[ch][i] = 0xff800000u;
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[ch][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[ch][i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(sr[ch][i + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(sr[ch][i + 3]));
+                }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));   // -inf if this half holds no real key
+            // one OR-reducing barrier per tile: does any of the 64 threads (32 rows x 2 halves) need the reference maximum moved?
+            const uint32_t want = (j == 0 || (mx - m_ref) * c > kQ2RescaleLog2) ? 1u : 0u;
+            uint32_t any;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t"
+                "setp.ne.b32 p, %2, 0;\n\t"
+                "bar.red.or.pred q, %1, 64, p;\n\t"
+                "selp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(any) : "r"(pair_bar), "r"(want) : "memory");
+            if (any) {
+                *x_mine = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float row_mx = fmaxf(mx, *x_other);
+                if (j == 0) {
+                    m_ref = row_mx;           // tile 0 always holds real keys, so this is finite
+                } else {
+                    const float m_new = fmaxf(m_ref, row_mx);
+                    const float corr = q2_ex2((m_ref - m_new) * c);
+                    m_ref = m_new;
+                    l2a.x *= corr; l2a.y *= corr; l2b.x *= corr; l2b.y *= corr;
+                    q2_wait(&pv_done[t], (j - 1) & 1);   // P_t V_(j-1) has landed in O_t
+                    tc_fence_after();
+                    uint32_t orr[32];
+                    tmem_ld_32x32(o_addr, orr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * corr);
+                    q2_tmem_st_32x32(o_addr, orr);
+                }
+            }
+            const float nmsc = -m_ref * c;
+            const float2 nm2 = make_float2(nmsc, nmsc);
+            uint32_t pk[32];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float2 x0 = q2_fma2(make_float2(__uint_as_float(sr[ch][i]), __uint_as_float(sr[ch][i + 1])), c2, nm2);
+                    const float2 x1 = q2_fma2(make_float2(__uint_as_float(sr[ch][i + 2]), __uint_as_float(sr[ch][i + 3])), c2, nm2);
+                    const int g = i >> 2;
+                    const bool poly = ((g + 1) * kPolyOf8) / 8 != (g * kPolyOf8) / 8;
+                    const float2 e0 = poly ? q2_ex2_poly2(x0) : make_float2(q2_ex2(x0.x), q2_ex2(x0.y));
+                    const float2 e1 = poly ? q2_ex2_poly2(x1) : make_float2(q2_ex2(x1.x), q2_ex2(x1.y));
+                    l2a = q2_add2(l2a, e0);
+                    l2b = q2_add2(l2b, e1);
+                    pk[ch * 16 + (i >> 1)] = T16<T>::pack2(e0.x, e0.y);
+                    pk[ch * 16 + (i >> 1) + 1] = T16<T>::pack2(e1.x, e1.y);
+                }
+            }
+            if (j > 0) {   // the P buffer is free once P_t V_(j-1) has completed (long ago, normally)
+                q2_wait(&pv_done[t], (j - 1) & 1);
+                tc_fence_after();
+            }
+            q2_tmem_st_32x32(p_addr, pk);
+            q2_tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+        }
+        // ---- epilogue: row sum = both halves; this thread normalises and stores 32 of the 64 output columns
+        *x_mine = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float inv = 1.f / (*x_mine + *x_other);
+        q2_wait(&pv_done[t], (n - 1) & 1);
+        tc_fence_after();
+        const int q = q0 + t * kQ2BM + row;
+        uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kQ2D + hf * 32);
+        uint32_t orr[32];
+        tmem_ld_32x32(o_addr, orr);
+        tmem_ld_wait();
+        if (q < p.T) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 v;
+                v.x = T16<T>::pack2(__uint_as_float(orr[8 * i]) * inv, __uint_as_float(orr[8 * i + 1]) * inv);
+                v.y = T16<T>::pack2(__uint_as_float(orr[8 * i + 2]) * inv, __uint_as_float(orr[8 * i + 3]) * inv);
+                v.z = T16<T>::pack2(__uint_as_float(orr[8 * i + 4]) * inv, __uint_as_float(orr[8 * i + 5]) * inv);
+                v.w = T16<T>::pack2(__uint_as_float(orr[8 * i + 6]) * inv, __uint_as_float(orr[8 * i + 7]) * inv);
+                dst[i] = v;
+            }
+        }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ============================ softmax: one thread per query row ============================
@@ -463,28 +598,36 @@ wk_status encoder_attention_q2(const void* qkv, void* out, int B, int T, int n_h
     p.idesc_pv = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(kQ2D >> 3) << 17) |
                  ((uint32_t)(kQ2BM >> 4) << 24);
     dim3 grid((T + 2 * kQ2BM - 1) / (2 * kQ2BM), B * n_heads);
-    static const int poly = [] { const char* e = getenv("WKB200_ATTN_POLY"); return e ? atoi(e) : 0; }();      // bring-up switches
-    static const bool ordered = [] { const char* e = getenv("WKB200_ATTN_ORDER"); return !(e && e[0] == '0'); }();
+    const int poly = [] { const char* e = getenv("WKB200_ATTN_POLY"); return e ? atoi(e) : 0; }();      // bring-up switches (read per call)
+    const bool ordered = [] { const char* e = getenv("WKB200_ATTN_ORDER"); return !(e && e[0] == '0'); }();
     cudaError_t e = cudaSuccess;
-    auto launch = [&](auto kern, auto* o) {
+    const int split = [] { const char* e = getenv("WKB200_ATTN_SPLIT"); return e ? atoi(e) : 2; }();
+    auto launch = [&](auto kern, auto* o, int threads) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2Smem);
-        if (e == cudaSuccess) kern<<<grid, kQ2Threads, kQ2Smem, stream>>>(tm, o, p);
+        if (e == cudaSuccess) kern<<<grid, threads, kQ2Smem, stream>>>(tm, o, p);
     };
     auto pick = [&](auto* o) {
         using OT = std::remove_pointer_t<decltype(o)>;
-        if (ordered) {
+        if (split == 2) {
             switch (poly) {
-                case 2: launch(encoder_attention_q2_kernel<OT, 2, true>, o); break;
-                case 3: launch(encoder_attention_q2_kernel<OT, 3, true>, o); break;
-                case 4: launch(encoder_attention_q2_kernel<OT, 4, true>, o); break;
-                default: launch(encoder_attention_q2_kernel<OT, 0, true>, o); break;
+                case 2: launch(encoder_attention_q2_kernel<OT, 2, false, 2>, o, 640); break;
+                case 3: launch(encoder_attention_q2_kernel<OT, 3, false, 2>, o, 640); break;
+                case 4: launch(encoder_attention_q2_kernel<OT, 4, false, 2>, o, 640); break;
+                default: launch(encoder_attention_q2_kernel<OT, 0, false, 2>, o, 640); break;
+            }
+        } else if (ordered) {
+            switch (poly) {
+                case 2: launch(encoder_attention_q2_kernel<OT, 2, true, 1>, o, kQ2Threads); break;
+                case 3: launch(encoder_attention_q2_kernel<OT, 3, true, 1>, o, kQ2Threads); break;
+                case 4: launch(encoder_attention_q2_kernel<OT, 4, true, 1>, o, kQ2Threads); break;
+                default: launch(encoder_attention_q2_kernel<OT, 0, true, 1>, o, kQ2Threads); break;
             }
         } else {
             switch (poly) {
-                case 2: launch(encoder_attention_q2_kernel<OT, 2, false>, o); break;
-                case 3: launch(encoder_attention_q2_kernel<OT, 3, false>, o); break;
-                case 4: launch(encoder_attention_q2_kernel<OT, 4, false>, o); break;
-                default: launch(encoder_attention_q2_kernel<OT, 0, false>, o); break;
+                case 2: launch(encoder_attention_q2_kernel<OT, 2, false, 1>, o, kQ2Threads); break;
+                case 3: launch(encoder_attention_q2_kernel<OT, 3, false, 1>, o, kQ2Threads); break;
+                case 4: launch(encoder_attention_q2_kernel<OT, 4, false, 1>, o, kQ2Threads); break;
+                default: launch(encoder_attention_q2_kernel<OT, 0, false, 1>, o, kQ2Threads); break;
             }
         }
     };

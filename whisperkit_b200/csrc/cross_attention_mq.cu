@@ -2,9 +2,9 @@
 //
 // One CTA = one (window, head): K then V of that head (Tlen x 64, 16-bit) stream once through a TMA ring (128-key tiles, 128B swizzle,
 // rows past Tlen zero-filled by TMA) and serve all NQ queries.  The single-query kernel does its dot products on the FMA pipe, which is
-// free there (one query: 2 flops per byte); with NQ = 5 queries per byte stream the same layout is instruction-bound (130 us per layer at
-// 32 windows x 5 beams where the stream itself needs ~37 us), so here both products run on the tensor cores with the queries as the
-// 16-row A operand (rows >= NQ are zero):
+// free there (one query: 2 flops per byte); with NQ = 5 queries per byte stream the same layout is instruction-bound (the first version of
+// this kernel did it that way: 130 us per layer at 32 windows x 5 beams where the stream itself needs ~37 us; this one: 71 us, beam-5
+// pass 515 -> 660 audio-s/s), so here both products run on the tensor cores with the queries as the 16-row A operand (rows >= NQ are zero):
 //   scores = Q K^T      mma.sync m16n8k16, A = Q (hi + lo 16-bit split of the f32 query: two MMAs, ~16 mantissa bits),
 //                       B = K tile rows straight from the swizzled ring with ldmatrix
 //   out    = P V        A = P (f32 probabilities from smem, hi + lo split on the fly), B = V tile with ldmatrix.trans
@@ -55,7 +55,7 @@ template <typename T> __device__ __forceinline__ void mq_split2(float x, float y
 
 template <typename T, int NQ, int STAGES>
 __global__ void __launch_bounds__(kMqThreads)
-decoder_cross_attention_mqt_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+decoder_cross_attention_mq_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                                   const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq, T* __restrict__ out, int H,
                                   int Tlen, int chunks, const int32_t* __restrict__ done) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -220,11 +220,11 @@ static wk_status launch_mq(const CUtensorMap& tmk, const CUtensorMap& tmv, const
     if (smem > 227 * 1024) { set_error("decoder_cross_attention (beam): %d encoder positions do not fit shared memory", Tlen); return WK_ERR_INVALID_ARGUMENT; }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decoder_cross_attention_mqt_kernel<T, NQ, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(decoder_cross_attention_mq_kernel<T, NQ, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(cross mq): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
         attr_set = true;
     }
-    launch_k(decoder_cross_attention_mqt_kernel<T, NQ, ST>, dim3((B / NQ) * H), dim3(kMqThreads), smem, stream, 4, tmk, tmv, partial, splits, Bp, bq, (T*)out, H,
+    launch_k(decoder_cross_attention_mq_kernel<T, NQ, ST>, dim3((B / NQ) * H), dim3(kMqThreads), smem, stream, 4, tmk, tmv, partial, splits, Bp, bq, (T*)out, H,
              Tlen, chunks, done);
     return WK_OK;
 }

@@ -584,189 +584,7 @@ static size_t cross_smem_bytes(int T) {
     return (size_t)kCrossStages * kCrossStageBytes + (size_t)((T + 3) & ~3) * 4 + 64 * 4 + (4 * 64 + 32) * 4 + 2 * kCrossStages * 8 + 64;
 }
 
-// Cross attention for NQ queries that share one K/V block: the beams of a window (beam search).  Same streaming structure as above -
-// one CTA per (window, head), the K block then the V block through a ring of 16 000-byte bulk copies - but every staged row is used by
-// all NQ beams: K/V are read from HBM once per window instead of once per beam (the single-query kernel with kv_div would re-stream
-// them through L2 NQ times: measured ~200 us per layer at 32 windows x 5 beams against ~35 us of HBM time).
-template <typename T, int NQ>
-__global__ void __launch_bounds__(kCrossThreads)
-decoder_cross_attention_mq_kernel(const float* __restrict__ partial, int splits, int Bp, const float* __restrict__ bq,
-                                  const T* __restrict__ kcross, const T* __restrict__ vcross, T* __restrict__ out, int H, int Tlen,
-                                  const int32_t* __restrict__ done) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int Tpad = (Tlen + 3) & ~3;
-    uint8_t* ring = smem;                                                              // kCrossStages * 16000
-    float* scores = reinterpret_cast<float*>(smem + kCrossStages * kCrossStageBytes);  // [NQ][Tpad]
-    float* sq = scores + NQ * Tpad;                                                    // [NQ][64]
-    float* red = sq + NQ * 64;                                                         // [4][NQ][64] (+ statistics)
-    float* stat = red + 4 * NQ * 64;                                                   // [8] block reductions, [NQ] 1 / sum
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stat + 8 + NQ + 3);
-    full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~uintptr_t(7));
-    uint64_t* empty_bar = full_bar + kCrossStages;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int win = blockIdx.x / H, h = blockIdx.x % H;
-    const int r0 = win * NQ;                 // first decode row of the window
-    const int dm = H * 64;
-    const int chunks = Tlen / kCrossRows;
-    pdl_launch_dependents();
-    const int ended = done != nullptr ? done[r0] : 0;   // the beams of a window end together
-    if (tid == 0) {
-        for (int i = 0; i < kCrossStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    if (ended) { pdl_wait(); return; }
-    if (warp == 4) {
-        if (lane == 0) {
-            const uint8_t* kb = reinterpret_cast<const uint8_t*>(kcross + (long long)blockIdx.x * Tlen * 64);
-            const uint8_t* vb = reinterpret_cast<const uint8_t*>(vcross + (long long)blockIdx.x * Tlen * 64);
-            for (int c = 0; c < 2 * chunks; ++c) {
-                const int stage = c % kCrossStages;
-                const uint32_t ph = (c / kCrossStages) & 1;
-                mbar_wait(&empty_bar[stage], ph ^ 1);
-                mbar_expect_tx(&full_bar[stage], kCrossStageBytes);
-                const uint8_t* src = c < chunks ? kb + (long long)c * kCrossStageBytes : vb + (long long)(c - chunks) * kCrossStageBytes;
-                bulk_load_1d(ring + stage * kCrossStageBytes, src, kCrossStageBytes, &full_bar[stage]);
-            }
-        }
-        return;
-    }
-    pdl_wait();                      // the q partials come from the upstream GEMM
-    for (int i = tid; i < NQ * 64; i += 128) {
-        const int j = i >> 6, e = i & 63;
-        float q = bq[h * 64 + e];
-        for (int s = 0; s < splits; ++s) q += partial[((long long)s * Bp + r0 + j) * dm + h * 64 + e];
-        sq[i] = q * 0.125f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int sub = lane & 7, rsel = lane >> 3;
-    float qv[NQ][8];
-#pragma unroll
-    for (int j = 0; j < NQ; ++j)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qv[j][e] = sq[j * 64 + sub * 8 + e];
-    // K phase: scores[j][t] = q_j . K[t]
-    for (int c = 0; c < chunks; ++c) {
-        const int stage = c % kCrossStages;
-        mbar_wait(&full_bar[stage], (c / kCrossStages) & 1);
-        const uint8_t* tile = ring + stage * kCrossStageBytes;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp * 4 + rsel + 16 * i;
-            float acc[NQ];
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) acc[j] = 0.f;
-            if (r < kCrossRows) {
-                const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + sub * 16);
-                const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
-#pragma unroll
-                for (int j = 0; j < NQ; ++j)
-                    acc[j] = qv[j][0] * a0.x + qv[j][1] * a0.y + qv[j][2] * a1.x + qv[j][3] * a1.y + qv[j][4] * a2.x + qv[j][5] * a2.y + qv[j][6] * a3.x + qv[j][7] * a3.y;
-            }
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) {
-                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
-                acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
-            }
-            if (sub == 0 && r < kCrossRows) {
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) scores[j * Tpad + c * kCrossRows + r] = acc[j];
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // exact two-pass softmax per beam (consumers only)
-    for (int j = 0; j < NQ; ++j) {
-        float* sc = scores + j * Tpad;
-        float mx = -INFINITY;
-        for (int t = tid; t < Tlen; t += 128) mx = fmaxf(mx, sc[t]);
-        mx = warp_max(mx);
-        if (lane == 0) stat[warp] = mx;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mx = fmaxf(fmaxf(stat[0], stat[1]), fmaxf(stat[2], stat[3]));
-        float sm = 0.f;
-        for (int t = tid; t < Tlen; t += 128) {
-            const float pr = __expf(sc[t] - mx);
-            sc[t] = pr;
-            sm += pr;
-        }
-        sm = warp_sum(sm);
-        if (lane == 0) stat[4 + warp] = sm;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) stat[8 + j] = 1.f / (stat[4] + stat[5] + stat[6] + stat[7]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    // V phase: out_j[d] = sum_t p_j[t] V[t][d]
-    float acc[NQ][8];
-#pragma unroll
-    for (int j = 0; j < NQ; ++j)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-    for (int c = chunks; c < 2 * chunks; ++c) {
-        const int stage = c % kCrossStages;
-        mbar_wait(&full_bar[stage], (c / kCrossStages) & 1);
-        const uint8_t* tile = ring + stage * kCrossStageBytes;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp * 4 + rsel + 16 * i;
-            if (r < kCrossRows) {
-                const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + sub * 16);
-                const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) {
-                    const float pr = scores[j * Tpad + (c - chunks) * kCrossRows + r];
-                    acc[j][0] += pr * a0.x; acc[j][1] += pr * a0.y; acc[j][2] += pr * a1.x; acc[j][3] += pr * a1.y;
-                    acc[j][4] += pr * a2.x; acc[j][5] += pr * a2.y; acc[j][6] += pr * a3.x; acc[j][7] += pr * a3.y;
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-    }
-#pragma unroll
-    for (int j = 0; j < NQ; ++j)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 8);
-            acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 16);
-        }
-    if (rsel == 0) {
-#pragma unroll
-        for (int j = 0; j < NQ; ++j)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) red[(warp * NQ + j) * 64 + sub * 8 + e] = acc[j][e];
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int i = tid; i < NQ * 64; i += 128) {
-        const int j = i >> 6, e = i & 63;
-        const float o = (red[(0 * NQ + j) * 64 + e] + red[(1 * NQ + j) * 64 + e] + red[(2 * NQ + j) * 64 + e] + red[(3 * NQ + j) * 64 + e]) * stat[8 + j];
-        out[(long long)(r0 + j) * dm + h * 64 + e] = T16<T>::from_f(o);
-    }
-}
-
-template <int NQ> static size_t cross_mq_smem_bytes(int T) {
-    return (size_t)kCrossStages * kCrossStageBytes + (size_t)NQ * ((T + 3) & ~3) * 4 + (size_t)NQ * 64 * 4 + (size_t)4 * NQ * 64 * 4 + (8 + NQ + 4) * 4 + 8 +
-           2 * kCrossStages * 8 + 64;
-}
-
-template <typename T, int NQ>
-static wk_status launch_cross_mq(const float* partial, int splits, int Bp, const float* bq, const void* kcross, const void* vcross, void* out, int B, int H,
-                                 int Tlen, const int32_t* done, cudaStream_t stream) {
-    const size_t smem = cross_mq_smem_bytes<NQ>(Tlen);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decoder_cross_attention_mq_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(cross mq): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-        attr_set = true;
-    }
-    launch_k(decoder_cross_attention_mq_kernel<T, NQ>, dim3((B / NQ) * H), dim3(kCrossThreads), smem, stream, 4, partial, splits, Bp, bq, (const T*)kcross,
-             (const T*)vcross, (T*)out, H, Tlen, done);
-    return WK_OK;
-}
+// The beam-search form (NQ rows share one K/V block) lives in cross_attention_mq.cu: both products on the tensor cores.
 
 __global__ void decoder_align_mean_kernel(const float* __restrict__ scratch, int n_slots, const int32_t* __restrict__ steps,
                                           const int32_t* __restrict__ done, __half* __restrict__ out, int B, int Tlen, int max_rows) {
@@ -795,22 +613,8 @@ wk_status decoder_cross_attention(const float* partial, int splits, int Bp, cons
                                   const int32_t* done, float* align_scratch, uint32_t align_mask, int kv_div) {
     if (kv_div < 1 || B % kv_div != 0) { set_error("decoder_cross_attention: %d rows do not split into groups of %d", B, kv_div); return WK_ERR_INVALID_ARGUMENT; }
     if (T % kCrossRows != 0) { set_error("decoder_cross_attention: n_audio_ctx %d not a multiple of %d", T, kCrossRows); return WK_ERR_INVALID_ARGUMENT; }
-    static const bool mq_tc = [] { const char* e = getenv("WKB200_MQ_TC"); return e && e[0] == '1'; }();   // bring-up switch
-    if (mq_tc && kv_div > 1 && kv_div <= 8 && align_scratch == nullptr)
+    if (kv_div > 1 && kv_div <= 8 && align_scratch == nullptr)   // beam search: one CTA per (window, head) serves all beams from one K/V pass
         return decoder_cross_attention_mq(partial, splits, Bp, bq, kcross, vcross, out, B, H, T, dtype, stream, done, kv_div);
-    if (kv_div > 1 && kv_div <= 8 && align_scratch == nullptr) {
-        // beam search: one CTA per (window, head) serves all beams from one pass over the K/V block
-        wk_status r = WK_ERR_INVALID_ARGUMENT;
-#define WK_MQ(N) case N: r = dtype == WK_DTYPE_F16 ? launch_cross_mq<__half, N>(partial, splits, Bp, bq, kcross, vcross, out, B, H, T, done, stream) \
-                                                   : launch_cross_mq<__nv_bfloat16, N>(partial, splits, Bp, bq, kcross, vcross, out, B, H, T, done, stream); break;
-        switch (kv_div) { WK_MQ(2) WK_MQ(3) WK_MQ(4) WK_MQ(5) WK_MQ(6) WK_MQ(7) WK_MQ(8) default: break; }
-#undef WK_MQ
-        if (r != WK_OK) return r;
-        count_launch();
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { set_error("decoder_cross_attention (beams) launch: %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
-        return WK_OK;
-    }
     const size_t smem = cross_smem_bytes(T);
     static bool attr_set[2] = {false, false};
     const int ti = dtype == WK_DTYPE_F16 ? 1 : 0;
