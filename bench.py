@@ -59,7 +59,6 @@ def parse_args():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-windows", type=int, default=1)
     ap.add_argument("--profile-pass", action="store_true", help="one untimed pass of the hot path and exit (for ncu)")
-    ap.add_argument("--attn-variants", action="store_true", help="A/B of the encoder attention variants (bring-up switches) on the live QKV of one pass, then exit")
     ap.add_argument("--windows", type=int, default=0, help="30 s windows per GPU per step (default: --batch, i.e. one window per decode slot)")
     ap.add_argument("--eot-profile", action="store_true",
                     help="windows end at their own length: per-window sampleLength drawn (seeded) from a speech-like distribution instead of "
@@ -407,24 +406,6 @@ def run_own_arm(args):
     t_first = time.perf_counter()
     step_device()
     log(f"first pass took {time.perf_counter() - t_first:.2f} s, stage ms {model.last_timings()}")
-    if args.attn_variants:
-        # every variant timed by wk_bench_kernel (100 back-to-back launches on the QKV the pass above left in the workspace), three
-        # interleaved rounds so that clock / power drift hits all variants alike
-        variants = [("v1", None, None)] + [("q2", o, p_) for o in (0, 1) for p_ in (0, 3)] + [("q2 split", 2, p_) for p_ in (0, 2, 3, 4)]
-        got = {v: [] for v in variants}
-        for _ in range(3):
-            for v in variants:
-                os.environ["WKB200_ATTN_Q2"] = "0" if v[0] == "v1" else "1"
-                os.environ["WKB200_ATTN_SPLIT"] = "2" if v[0] == "q2 split" else "1"
-                if v[1] is not None:
-                    os.environ["WKB200_ATTN_ORDER"], os.environ["WKB200_ATTN_POLY"] = str(v[1]), str(v[2])
-                f, w_ = C.c_float(), C.c_double()
-                check(lib.wk_bench_kernel(model.handle, dec.handle, 3, min(B, enc_batch), 100, C.byref(f), C.byref(w_)))
-                got[v].append(f.value)
-        for v in variants:
-            med = sorted(got[v])[1]
-            print(f"attention {v}: " + " ".join(f"{x:.4f}" for x in got[v]) + f"  median {med:.4f} ms = {w_.value / (med * 1e-3) / 1e12:.0f} TFLOP/s", flush=True)
-        return
     if args.profile_pass:
         step_device()
         log(f"profile pass done, launches {int(lib.wk_kernel_launch_count(0))}")

@@ -1,17 +1,36 @@
-// K4: encoder self-attention (non-causal, head dim 64, S = 1500) on tcgen05 tensor cores.
+// K4: encoder self-attention (non-causal, head dim 64, S = 1500) on tcgen05 tensor cores with the probabilities kept in tensor memory.
 //
-// One CTA = one (window, head, 128-query tile).  192 threads, warp-specialised:
-//   warp 0      TMA producer: Q tile once, then K / V tiles of 128 keys through 3-deep smem rings (128B swizzle)
-//   warp 1      MMA issuer:   S_j = Q K_j^T   (tcgen05.mma 128x128x16 x4, accumulator S in TMEM, double buffered)
-//                             PV_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P_j from smem, B = V_j MN-major from smem)
-//   warps 2..   softmax:      P (2, or 4) threads per query row (warps w, w+4, ... share a TMEM lane quarter); for P = 2 each takes 64
-//                             of the tile's 128 keys and 32 of the 64 output columns.  tcgen05.ld S_j -> max / exp2 /
-//                             row sum in registers (only the row max is exchanged, through smem, once per tile),
-//                             P_j (16-bit) -> swizzled smem for the second MMA; PV_j is read back from TMEM and
-//                             accumulated into a register-resident O with the online-softmax rescale (no TMEM
-//                             read-modify-write).  Two softmax warps per scheduler hide each other's latencies.
-// Q/K/V are read in place from the packed qkv activation [B*T, 3*d_model] through one 3-D tensor map (per-window
-// out-of-bounds rows are zero-filled by TMA; keys >= T are masked to -inf before the softmax).
+// One CTA = one (window, head, 256-query block) = two 128-query tiles A and B that share every K / V tile.  384 threads:
+//   warp 0        TMA producer: Q_A, Q_B once, then K / V tiles of 128 keys through 4-deep smem rings (128B swizzle)
+//   warp 1        MMA issuer, per key tile j and query tile t:
+//                     S_t  = Q_t K_j^T          tcgen05.mma 128x128x16 x4, A and B from smem, accumulator S_t in TMEM
+//                     O_t += P_t V_j            tcgen05.mma 128x64x16  x8, A = P_t FROM TMEM (16-bit, written by the softmax warps
+//                                               into its own 64 columns), B = V_j MN-major from smem, accumulator O_t in TMEM
+//                 S_t(j+1) is issued as soon as the softmax warps have READ S_t(j) into registers (s_free), i.e. it runs under the
+//                 exponentials of tile j: the only serial chain left per query tile is load-S / max / exp / store-P
+//   warps 4..7    softmax of tile A, ONE thread per query row (warp w owns TMEM lane quarter w & 3)
+//   warps 8..11   softmax of tile B
+// (warps 2, 3 only fill warpgroup 0: setmaxnreg moves registers per warpgroup - 72 for warpgroup 0, 216 for the softmax warpgroups, whose
+// threads hold a whole 128-score row)
+// Compared with the round-1 kernel (one query tile per CTA, two threads per row, P through shared memory, O accumulated in registers) this
+// removes the per-tile row-max exchange through shared memory and its named barrier, the 32 KiB generic-proxy P store + proxy fence per
+// tile, the per-tile O read-back, and half of the K / V traffic from L2: 1.71 -> 1.11 ms per layer at 64 windows (432 -> 662 TFLOP/s).
+// A clock64 timeline of one CTA (profiles/r02_attention_trace.txt) shows the softmax warps never waiting any more (S ready in ~170
+// clocks, P buffer free in ~90): a key tile costs a softmax warp ~2700 clocks = load S 200 + max 450 + 128 exponentials / pack / sum 1600,
+// two such warps per scheduler, i.e. the kernel is bound by the per-element instruction work of the softmax (MUFU 16/clk/SM, FMA and ALU
+// pipes, issue slots), not by the tensor pipe (30 %).  Measured and NOT kept (profiles/r02_attention_variants.txt): a turn barrier that
+// hands the MUFU pipe from the A warp to the B warp of a scheduler (1.13 ms against 1.11 - the non-MUFU work serialises too); two
+// threads per row with 16 softmax warps and one OR-reducing named barrier per tile (1.15 - 1.28 ms: same total instruction work).
+//
+// exp2 on two pipes: 3 of every 8 groups of four scores take a Cody-Waite + degree-3 polynomial on the FMA / ALU pipes (relative error
+// 7.5e-5, far below the 16-bit rounding P gets next) instead of MUFU.EX2 (1.20 -> 1.11 ms).
+//
+// Online softmax with a lazy rescale: O_t and the row sum are relative to a reference maximum m_ref that only moves when some row
+// of the warp finds a score more than 2^8 above it (then the owning warp rescales its 32 rows of O_t in TMEM itself, after pv_done says
+// that P_t V_(j-1) has completed; P_t V_j cannot start before this warp publishes P_t(j), so O_t is quiescent meanwhile).  Probabilities
+// are therefore <= 2^8, exact in f32 sums and inside bf16 / f16 range.
+// Q/K/V are read in place from the packed qkv activation [B*T, 3*d_model] through one 3-D tensor map (per-window out-of-bounds rows are
+// zero-filled by TMA; keys >= T are masked to -inf before the softmax).
 // Reference counterpart: inside AudioEncoder.mlmodelc (Sources/WhisperKit/Core/AudioEncoder.swift:59-62).
 #include <stdio.h>
 #include <stdlib.h>
@@ -21,31 +40,47 @@
 
 namespace wk {
 
-static constexpr int kFaThreadsFor(int parts) { return 64 + 128 * parts; }   // TMA warp + MMA warp + 4 * parts softmax warps
-static constexpr int kFaBM = 128;          // queries per CTA
+static constexpr int kFaThreads = 384;     // warpgroup 0: TMA warp, MMA warp, two idle warps; warpgroups 1 and 2: softmax of tile A / B
+static constexpr int kFaPolyOf8 = 3;       // of every 8 groups of four scores, how many take the polynomial exp2 (measured: 0 -> 1.20 ms, 3 -> 1.11 ms)
+static constexpr int kFaBM = 128;          // queries per tile (two tiles per CTA)
 static constexpr int kFaBN = 128;          // keys per tile
 static constexpr int kFaD = 64;
 static constexpr int kFaTile = kFaBN * kFaD * 2;   // 16 KiB: one K or V or Q tile, 128-byte rows
-static constexpr int kFaStages = 3;
-static constexpr int kFaPBytes = kFaBM * kFaBN * 2;  // 32 KiB: P tile = two 64-key chunks of 16 KiB
-static constexpr int kFaSmem = kFaTile /*Q*/ + 2 * kFaStages * kFaTile /*K,V rings*/ + 2 * kFaPBytes + 1024 /*align*/ + 512 /*barriers*/ + 8192 /*row-max / row-sum exchange*/;
-static constexpr int kFaTmemCols = 512;    // S0 @0, S1 @128, O0 @256, O1 @320
+static constexpr int kFaStages = 4;
+static constexpr int kFaSmem = 2 * kFaTile /*Q_A, Q_B*/ + 2 * kFaStages * kFaTile /*K, V rings*/ + 1024 /*align*/ + 512 /*barriers*/;
+static constexpr int kFaTmemCols = 512;    // S_A @0, S_B @128, P_A @256, P_B @320 (16-bit: 64 columns each), O_A @384, O_B @448
+static constexpr float kFaRescaleLog2 = 8.f;
 
 struct FaParams {
     int T, H, dm, n_kv_tiles;
     float scale_log2e;
     uint32_t idesc_qk, idesc_pv;
-    // V (MN-major) descriptor knobs, overridable for bring-up experiments
-    uint32_t v_lbo, v_sbo, v_kstep;
 };
 
-__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2: 2^x, ex2(-inf) = +0
+__device__ __forceinline__ float fa_ex2(float x) {   // MUFU.EX2: 2^x, ex2(-inf) = +0
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA / ALU pipes for a pair of scores (x <= 8): round-to-nearest split x = n + f with the 1.5 * 2^23 trick (the low mantissa
+// bits of t hold n), degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (relative error 7.5e-5, far below the 16-bit rounding P gets
+// next), then n goes into the exponent field with one integer shift-add.  The MUFU pipe (16 results per clock and SM) bounds this
+// kernel, so a fixed share of every row goes this way (kPolyOf8 of every 8 groups of four scores).
+__device__ __forceinline__ float2 fa_ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 t = add2(x, make_float2(12582912.f, 12582912.f));
+    const float2 nf = add2(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = fma2(nf, make_float2(-1.f, -1.f), x);
+    float2 r = fma2(f, make_float2(0.05517146f, 0.05517146f), make_float2(0.24261086f, 0.24261086f));
+    r = fma2(r, f, make_float2(0.69326097f, 0.69326097f));
+    r = fma2(r, f, make_float2(0.9999281f, 0.9999281f));
+    r.x = __int_as_float(__float_as_int(r.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(r.y) + (__float_as_int(t.y) << 23));
+    return r;
+}
 
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
+__device__ __forceinline__ uint64_t fa_sw128_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)(lbo16 & 0x3FFF) << 16;
@@ -54,47 +89,65 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;
     return d;
 }
-
-// 32 lanes x 16 columns of 32-bit
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+// (the tcgen05 instructions of the MMA warp are predicated on the elect.sync lane inside the asm: see tc_mma_f16_elect in common.cuh)
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is read from tensor memory (lane = row, two consecutive 16-bit K elements per 32-bit column)
+__device__ __forceinline__ void fa_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// 32 lanes x 32 columns of 32-bit: thread i of the warp writes lane (base+i), columns [c, c+32)
+__device__ __forceinline__ void fa_tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+// bounded mbarrier wait without the printf of mbar_wait_bounded (register-light: it sits in the softmax loop): a protocol bug ends as a
+// trapped launch, not as a hung GPU
+__device__ __forceinline__ void fa_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0xffffu) == 0 && globaltimer_ns() - t0 > kSpinLimitNs) __trap();
+    }
+}
+__device__ __forceinline__ void fa_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// P = softmax threads per query row: each takes 128 / P of the tile's keys and 64 / P of the output columns
-template <typename T, int P>
-__global__ void __launch_bounds__(kFaThreadsFor(P), 1)
+template <typename T, int kPolyOf8>
+__global__ void __launch_bounds__(kFaThreads, 1)
 encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* __restrict__ out, const FaParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + kFaTile;
+    uint8_t* sQ = smem;                                // 2 tiles
+    uint8_t* sK = sQ + 2 * kFaTile;
     uint8_t* sV = sK + kFaStages * kFaTile;
-    uint8_t* sP = sV + kFaStages * kFaTile;           // 2 buffers x 32 KiB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kFaPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kFaStages * kFaTile);
     uint64_t* q_full = bars;                      // 1
-    uint64_t* k_full = bars + 1;                  // 3
-    uint64_t* k_empty = k_full + kFaStages;       // 3
-    uint64_t* v_full = k_empty + kFaStages;       // 3
-    uint64_t* v_empty = v_full + kFaStages;       // 3
-    uint64_t* s_full = v_empty + kFaStages;       // 2
-    uint64_t* s_empty = s_full + 2;               // 2
-    uint64_t* p_full = s_empty + 2;               // 2
-    uint64_t* p_empty = p_full + 2;               // 2
-    uint64_t* o_full = p_empty + 2;               // 2
-    uint64_t* o_empty = o_full + 2;               // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
-    float* xch = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parity][P parts][128 rows] row-max exchange, then [P][128] final sums
+    uint64_t* k_full = bars + 1;                  // kFaStages
+    uint64_t* k_empty = k_full + kFaStages;
+    uint64_t* v_full = k_empty + kFaStages;
+    uint64_t* v_empty = v_full + kFaStages;
+    uint64_t* s_full = v_empty + kFaStages;       // 2 (per query tile): S_t(j) complete
+    uint64_t* s_free = s_full + 2;                // 2: the softmax warps hold S_t(j) in registers, S_t may be overwritten
+    uint64_t* p_full = s_free + 2;                // 2: P_t(j) is in TMEM (and O_t rescaled if it had to be)
+    uint64_t* pv_done = p_full + 2;               // 2: P_t V_j complete: P_t may be overwritten, O_t may be rescaled / read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q_tile = blockIdx.x, bh = blockIdx.y;
+    const int bh = blockIdx.y;
     const int b = bh / p.H, h = bh % p.H;
-    const int q0 = q_tile * kFaBM;
+    const int q0 = blockIdx.x * (2 * kFaBM);
     const int n = p.n_kv_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -105,9 +158,7 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4 * P);
-            mbar_init(&p_full[i], 4 * P); mbar_init(&p_empty[i], 1);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4 * P);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
         }
         fence_barrier_init();
     }
@@ -120,201 +171,201 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
-            mbar_expect_tx(q_full, kFaTile);
+            mbar_expect_tx(q_full, 2 * kFaTile);
             tma_load_3d(sQ, &tm_qkv, q_full, h * kFaD, q0, b);
+            tma_load_3d(sQ + kFaTile, &tm_qkv, q_full, h * kFaD, q0 + kFaBM, b);
             for (int j = 0; j < n; ++j) {
                 const int st = j % kFaStages;
                 const uint32_t ph = (j / kFaStages) & 1;
-                mbar_wait(&k_empty[st], ph ^ 1);
+                fa_wait(&k_empty[st], ph ^ 1);
                 mbar_expect_tx(&k_full[st], kFaTile);
                 tma_load_3d(sK + st * kFaTile, &tm_qkv, &k_full[st], p.dm + h * kFaD, j * kFaBN, b);
-                mbar_wait(&v_empty[st], ph ^ 1);
+                fa_wait(&v_empty[st], ph ^ 1);
                 mbar_expect_tx(&v_full[st], kFaTile);
                 tma_load_3d(sV + st * kFaTile, &tm_qkv, &v_full[st], 2 * p.dm + h * kFaD, j * kFaBN, b);
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        auto mma1 = [&](int j) {   // S[j&1] = Q K_j^T
-            const int st = j % kFaStages;
-            const int sb = j & 1;
-            mbar_wait(&k_full[st], (j / kFaStages) & 1);
-            mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint64_t adesc = make_sw128_desc(smem_u32(sQ), 1, 64);
-                const uint64_t bdesc = make_sw128_desc(smem_u32(sK + st * kFaTile), 1, 64);
+        // every lane runs this code converged; only the tcgen05 instructions are predicated, on the lane elect.sync picks (see tc_mma_f16_elect)
+        const uint64_t dbase = ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);   // see fa_sw128_desc(.., 1, 64)
+        const uint64_t qd0 = dbase | (uint64_t)((smem_u32(sQ) >> 4) & 0x3FFF);
+        const uint64_t kd0 = dbase | (uint64_t)((smem_u32(sK) >> 4) & 0x3FFF);
+        const uint64_t vd0 = dbase | (uint64_t)((smem_u32(sV) >> 4) & 0x3FFF);
+        constexpr uint64_t kTileStep = kFaTile >> 4;   // descriptor start-address units (16 B) per 16 KiB tile; all tiles sit below 256 KiB
+        const uint32_t idesc_qk = p.idesc_qk, idesc_pv = p.idesc_pv;
+        auto mma_s = [&](int t, int st) {   // S_t = Q_t K^T
+            const uint64_t ad = qd0 + (uint64_t)t * kTileStep, bd = kd0 + (uint64_t)st * kTileStep;
+            const uint32_t d_addr = tmem + t * 128;
 #pragma unroll
-                for (int k = 0; k < kFaD / 16; ++k)
-                    tc_mma_f16(tmem + sb * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc_qk, k > 0 ? 1u : 0u);
-                tc_commit(&k_empty[st]);
-                tc_commit(&s_full[sb]);
-            }
-            __syncwarp();
+            for (int k = 0; k < kFaD / 16; ++k) tc_mma_f16_elect(d_addr, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_qk, k > 0 ? 1u : 0u);
+            tc_commit_elect(&s_full[t]);
+            if (t == 1) tc_commit_elect(&k_empty[st]);
         };
-        auto mma2 = [&](int j) {   // O[j&1] = P_j V_j
-            const int st = j % kFaStages;
-            const int sb = j & 1;
-            mbar_wait(&v_full[st], (j / kFaStages) & 1);
-            mbar_wait(&p_full[sb], (j >> 1) & 1);
-            mbar_wait(&o_empty[sb], ((j >> 1) & 1) ^ 1);
+        auto mma_pv = [&](int t, int st, uint32_t par, bool first) {   // O_t (+)= P_t V
+            fa_wait(&p_full[t], par);
+            __syncwarp();
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t pbase = smem_u32(sP + sb * kFaPBytes);
-                const uint32_t vbase = smem_u32(sV + st * kFaTile);
+            const uint64_t bd = vd0 + (uint64_t)st * kTileStep;
+            const uint32_t d_addr = tmem + 384 + t * 64, a_addr = tmem + 256 + t * 64;
+            // A = P_t: 16 keys = 8 TMEM columns per step.  B = V: MN-major (d contiguous, 128-byte rows), 16 keys = 16 rows = 2 KiB
+            fa_mma_ts(d_addr, a_addr, bd, idesc_pv, first ? 0u : 1u);
 #pragma unroll
-                for (int k = 0; k < kFaBN / 16; ++k) {
-                    // A = P: K-major, 64-key chunks of 16 KiB, 32 B per 16 keys inside a chunk
-                    const uint64_t adesc = make_sw128_desc(pbase + (k >> 2) * (kFaPBytes / 2) + (k & 3) * 32, 1, 64);
-                    // B = V: MN-major (d contiguous, 128-byte rows), 16 keys = 16 rows per step
-                    const uint64_t bdesc = make_sw128_desc(vbase + k * p.v_kstep, p.v_lbo, p.v_sbo);
-                    tc_mma_f16(tmem + 256 + sb * 64, adesc, bdesc, p.idesc_pv, k > 0 ? 1u : 0u);
-                }
-                tc_commit(&v_empty[st]);
-                tc_commit(&p_empty[sb]);
-                tc_commit(&o_full[sb]);
-            }
-            __syncwarp();
+            for (int k = 1; k < kFaBN / 16; ++k) fa_mma_ts(d_addr, a_addr + k * 8, bd + (uint64_t)(k * (2048 >> 4)), idesc_pv, 1u);
+            tc_commit_elect(&pv_done[t]);
+            if (t == 1) tc_commit_elect(&v_empty[st]);
         };
-        mbar_wait(q_full, 0);
-        mma1(0);
-        if (n > 1) mma1(1);
+        fa_wait(q_full, 0);
+        fa_wait(&k_full[0], 0);
+        __syncwarp();
+        tc_fence_after();
+        mma_s(0, 0);
+        mma_s(1, 0);
+        int st = 0, st_next = 1;
+        uint32_t ring_par = 0, ring_par_next = 0;   // parity of the ring slot st (st_next) for this (the next) key tile
         for (int j = 0; j < n; ++j) {
-            mma2(j);
-            if (j + 2 < n) mma1(j + 2);
+            if (j + 1 < n) {   // S(j+1) of both tiles as soon as their S(j) has been read: runs under the exponentials of tile j
+                fa_wait(&k_full[st_next], ring_par_next);
+                fa_wait(&s_free[0], j & 1);
+                __syncwarp();
+                tc_fence_after();
+                mma_s(0, st_next);
+                fa_wait(&s_free[1], j & 1);
+                __syncwarp();
+                tc_fence_after();
+                mma_s(1, st_next);
+            }
+            fa_wait(&v_full[st], ring_par);
+            mma_pv(0, st, j & 1, j == 0);
+            mma_pv(1, st, j & 1, j == 0);
+            st = st_next; ring_par = ring_par_next;
+            if (++st_next == kFaStages) { st_next = 0; ring_par_next ^= 1; }
         }
+    }
     } else {
-        // ============================ softmax / accumulate / epilogue ============================
-        constexpr int KT = kFaBN / P;                 // keys of the tile per thread (64 or 32)
-        constexpr int OC = kFaD / P;                  // output columns per thread (32 or 16)
-        constexpr int NCH = KT / 32;                  // 32-column TMEM loads per tile
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ============================ softmax: one thread per query row ============================
+        const int t = (warp - 4) >> 2;                // query tile
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int part = (warp - 2) >> 2;             // which slice of the keys / output columns
         const int row = quarter * 32 + lane;          // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t pair_bar = 1 + quarter;        // named barrier shared by the P warps of this lane quarter
-        float o[OC];
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] = 0.f;
-        float m_run = -INFINITY;      // running max of raw scores (identical in all threads of a row)
-        float m_acc = -INFINITY;      // max the register accumulator o[] is currently scaled to
-        float l_run = 0.f;            // this thread's share of the row sum
-        float m_tile_prev = -INFINITY;
+        const uint32_t s_addr = tmem + lane_addr + t * 128;
+        const uint32_t p_addr = tmem + lane_addr + 256 + t * 64;
+        const uint32_t o_addr = tmem + lane_addr + 384 + t * 64;
         const float c = p.scale_log2e;
-        const int sw = row & 7;
-
-        auto accumulate = [&](int i, float m_i) {   // o += PV_i[:, part*OC .. +OC], PV_i is relative to max m_i
-            const int sb = i & 1;
-            mbar_wait(&o_full[sb], (i >> 1) & 1);
-            tc_fence_after();
-            const float corr = ex2_approx((m_acc - m_i) * c);   // m_acc = -inf on first use -> 0
-            m_acc = m_i;
-            uint32_t r[OC];
-            if constexpr (OC == 32) tmem_ld_32x32(tmem + lane_addr + 256 + sb * 64 + part * OC, r);
-            else tmem_ld_32x16(tmem + lane_addr + 256 + sb * 64 + part * OC, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int t = 0; t < OC; ++t) o[t] = fmaf(o[t], corr, __uint_as_float(r[t]));
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[sb]);
-        };
+        const float2 c2 = make_float2(c, c);
+        float m_ref = -INFINITY;      // the maximum O_t and l are relative to
+        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
 
         for (int j = 0; j < n; ++j) {
-            const int sb = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            mbar_wait(&s_full[sb], ph);
+            fa_wait(&s_full[t], j & 1);
             tc_fence_after();
-            // this thread's KT scores into registers (all TMEM loads in flight), then release the S buffer
-            uint32_t sr[NCH][32];
+            uint32_t sr[4][32];
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32(tmem + lane_addr + sb * 128 + part * KT + ch * 32, sr[ch]);
+            for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(s_addr + ch * 32, sr[ch]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[sb]);
-            const int valid = p.T - j * kFaBN - part * KT;   // keys of this thread's slice that exist (>= KT except at the end)
-            if (valid < KT) {
+            if (lane == 0) mbar_arrive(&s_free[t]);   // S_t(j) is in registers: the MMA warp may start S_t(j+1)
+            const int valid = p.T - j * kFaBN;   // keys of this tile that exist (>= 128 except at the end)
+            if (valid < kFaBN) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch)
+                for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        if (ch * 32 + t >= valid) sr[ch][t] = 0xff800000u;   // -inf: key does not exist
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i >= valid) sr[ch][i] = 0xff800000u;   // -inf: key does not exist
             }
-            float mx0 = -INFINITY, mx1 = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch)
+            for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    mx0 = fmaxf(mx0, __uint_as_float(sr[ch][t]));
-                    mx1 = fmaxf(mx1, __uint_as_float(sr[ch][t + 1]));
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[ch][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[ch][i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(sr[ch][i + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(sr[ch][i + 3]));
                 }
-            // exchange the slice max with the partner threads (same row, other keys)
-            float* slot = xch + (j & 1) * (P * 128);
-            slot[part * 128 + row] = fmaxf(mx0, mx1);
-            asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * P) : "memory");
-            float mx = m_run;
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            if (j == 0) {
+                m_ref = mx;       // tile 0 always holds real keys, so mx is finite
+            } else if (__any_sync(0xffffffffu, (mx - m_ref) * c > kFaRescaleLog2)) {
+                // some row of this warp outgrew its reference: move every row of the warp to its current maximum and rescale O_t, l
+                const float m_new = fmaxf(m_ref, mx);
+                const float corr = fa_ex2((m_ref - m_new) * c);
+                m_ref = m_new;
+                l2a.x *= corr; l2a.y *= corr; l2b.x *= corr; l2b.y *= corr;
+                fa_wait(&pv_done[t], (j - 1) & 1);   // P_t V_(j-1) has landed in O_t
+                tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < P; ++q) mx = fmaxf(mx, slot[q * 128 + row]);
-            const float l_corr = ex2_approx((m_run - mx) * c);
-            const float msc = mx * c;
-            m_run = mx;
-            // P buffer free?  (PV of tile j-2 has consumed it)
-            mbar_wait(&p_empty[sb], ph ^ 1);
-            float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-            // P tile in smem = two 64-key chunk blocks of 16 KiB (128-byte rows, 128B swizzle); this thread's keys part*KT .. +KT
-            uint8_t* prow = sP + sb * kFaPBytes + ((part * KT) >> 6) * (kFaPBytes / 2) + row * 128;
-            const int chunk0 = ((part * KT) & 63) >> 3;   // first 16-byte chunk of the slice inside the 128-byte row
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t orr[32];
+                    tmem_ld_32x32(o_addr + half * 32, orr);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int t = 0; t < 32; t += 4) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sr[ch][t]), c, -msc));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sr[ch][t + 1]), c, -msc));
-                    const float p2 = ex2_approx(fmaf(__uint_as_float(sr[ch][t + 2]), c, -msc));
-                    const float p3 = ex2_approx(fmaf(__uint_as_float(sr[ch][t + 3]), c, -msc));
-                    ls0 += p0; ls1 += p1; ls2 += p2; ls3 += p3;
-                    pk[t >> 1] = T16<T>::pack2(p0, p1);
-                    pk[(t >> 1) + 1] = T16<T>::pack2(p2, p3);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = chunk0 + ch * 4 + q;   // 16-byte chunk inside the 128-byte row
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * corr);
+                    fa_tmem_st_32x32(o_addr + half * 32, orr);
                 }
             }
-            l_run = l_run * l_corr + ((ls0 + ls1) + (ls2 + ls3));
-            fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            const float nmsc = -m_ref * c;
+            const float2 nm2 = make_float2(nmsc, nmsc);
+            // P_t(j): 128 probabilities per row -> 64 packed 16-bit columns
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int ch = half * 2 + cc;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float2 x0 = fma2(make_float2(__uint_as_float(sr[ch][i]), __uint_as_float(sr[ch][i + 1])), c2, nm2);
+                        const float2 x1 = fma2(make_float2(__uint_as_float(sr[ch][i + 2]), __uint_as_float(sr[ch][i + 3])), c2, nm2);
+                        const int g = i >> 2;   // group of four scores inside the 32-score chunk
+                        const bool poly = ((g + 1) * kPolyOf8) / 8 != (g * kPolyOf8) / 8;
+                        const float2 e0 = poly ? fa_ex2_poly2(x0) : make_float2(fa_ex2(x0.x), fa_ex2(x0.y));
+                        const float2 e1 = poly ? fa_ex2_poly2(x1) : make_float2(fa_ex2(x1.x), fa_ex2(x1.y));
+                        l2a = add2(l2a, e0);
+                        l2b = add2(l2b, e1);
+                        pk[cc * 16 + (i >> 1)] = T16<T>::pack2(e0.x, e0.y);
+                        pk[cc * 16 + (i >> 1) + 1] = T16<T>::pack2(e1.x, e1.y);
+                    }
+                }
+                if (half == 0 && j > 0) {   // the P buffer is free once P_t V_(j-1) has completed (long ago, normally)
+                    fa_wait(&pv_done[t], (j - 1) & 1);
+                    tc_fence_after();
+                }
+                fa_tmem_st_32x32(p_addr + half * 32, pk);
+            }
+            fa_tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[sb]);
-            // fold in the previous tile's PV while this tile's second MMA runs
-            if (j > 0) accumulate(j - 1, m_tile_prev);
-            m_tile_prev = mx;
+            if (lane == 0) mbar_arrive(&p_full[t]);
         }
-        accumulate(n - 1, m_tile_prev);
-        // ---- epilogue: total row sum = all slices; normalise and store this thread's OC columns
-        float* fin = xch + 2 * P * 128;   // [P][128]
-        fin[part * 128 + row] = l_run;
-        asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * P) : "memory");
-        const int q = q0 + row;
-        if (q < p.T) {
-            float tot = 0.f;
+        // ---- epilogue: O_t / l, 64 columns = one 128-byte row segment per thread
+        fa_wait(&pv_done[t], (n - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.f / ((l2a.x + l2a.y) + (l2b.x + l2b.y));
+        const int q = q0 + t * kFaBM + row;
+        uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kFaD);
 #pragma unroll
-            for (int i = 0; i < P; ++i) tot += fin[i * 128 + row];
-            const float inv = 1.f / tot;
-            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.T + q) * p.dm + h * kFaD + part * OC);
+        for (int half = 0; half < 2; ++half) {
+            uint32_t orr[32];
+            tmem_ld_32x32(o_addr + half * 32, orr);
+            tmem_ld_wait();
+            if (q < p.T) {
 #pragma unroll
-            for (int i = 0; i < OC / 8; ++i) {
-                uint4 v;
-                v.x = T16<T>::pack2(o[8 * i] * inv, o[8 * i + 1] * inv);
-                v.y = T16<T>::pack2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-                v.z = T16<T>::pack2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-                v.w = T16<T>::pack2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-                dst[i] = v;
+                for (int i = 0; i < 4; ++i) {
+                    uint4 v;
+                    v.x = T16<T>::pack2(__uint_as_float(orr[8 * i]) * inv, __uint_as_float(orr[8 * i + 1]) * inv);
+                    v.y = T16<T>::pack2(__uint_as_float(orr[8 * i + 2]) * inv, __uint_as_float(orr[8 * i + 3]) * inv);
+                    v.z = T16<T>::pack2(__uint_as_float(orr[8 * i + 4]) * inv, __uint_as_float(orr[8 * i + 5]) * inv);
+                    v.w = T16<T>::pack2(__uint_as_float(orr[8 * i + 6]) * inv, __uint_as_float(orr[8 * i + 7]) * inv);
+                    dst[half * 4 + i] = v;
+                }
             }
         }
     }
@@ -328,8 +379,8 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, T* 
 
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream) {
     static PFN_encodeTiled enc = nullptr;
@@ -360,20 +411,16 @@ wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, in
     p.idesc_qk = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kFaBN >> 3) << 17) | ((uint32_t)(kFaBM >> 4) << 24);
     p.idesc_pv = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(kFaD >> 3) << 17) |
                  ((uint32_t)(kFaBM >> 4) << 24);
-    p.v_lbo = 1; p.v_sbo = 64; p.v_kstep = 2048;
-    dim3 grid((T + kFaBM - 1) / kFaBM, B * n_heads);
-    // P = 2 softmax threads per query row.  P = 4 (16 softmax warps, 32 keys and 16 output columns per thread) was built and measured on
-    // B200: correct, but slower (2.24 vs 2.05 ms per layer at 64 windows) - twice the row-max exchanges and named-barrier waits cost more
-    // than the extra warps hide - so only P = 2 is instantiated.
+    dim3 grid((T + 2 * kFaBM - 1) / (2 * kFaBM), B * n_heads);
     cudaError_t e = cudaSuccess;
     if (dtype == WK_DTYPE_F16) {
         static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
-        if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__half*)out, p);
+        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__half, kFaPolyOf8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+        if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__half, kFaPolyOf8><<<grid, kFaThreads, kFaSmem, stream>>>(tm, (__half*)out, p);
     } else {
         static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
-        if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, 2><<<grid, kFaThreadsFor(2), kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p);
+        if (!set) { e = cudaFuncSetAttribute(encoder_attention_tcgen05_kernel<__nv_bfloat16, kFaPolyOf8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem); set = e == cudaSuccess; }
+        if (e == cudaSuccess) encoder_attention_tcgen05_kernel<__nv_bfloat16, kFaPolyOf8><<<grid, kFaThreads, kFaSmem, stream>>>(tm, (__nv_bfloat16*)out, p);
     }
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fa): %s", cudaGetErrorString(e)); return WK_ERR_CUDA; }
     count_launch();

@@ -63,6 +63,16 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return d;
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
     float2 d;
     asm("{\n\t.reg .b64 ra, rb, rd;\n\t"

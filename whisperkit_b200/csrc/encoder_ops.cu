@@ -87,8 +87,6 @@ wk_status layernorm_f32_to_f32(const float* x, const float* gamma, const float* 
 
 // Encoder attention lives in attention_tcgen05.cu (TMA + tcgen05 + TMEM); this is only its entry point.
 wk_status encoder_attention(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream) {
-    const bool q2 = [] { const char* e = getenv("WKB200_ATTN_Q2"); return e && e[0] == '1'; }();   // bring-up switch (read per call)
-    if (q2) return encoder_attention_q2(qkv, out, B, T, n_heads, dtype, stream);
     return encoder_attention_tcgen05(qkv, out, B, T, n_heads, dtype, stream);
 }
 

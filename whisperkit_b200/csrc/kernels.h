@@ -85,8 +85,6 @@ wk_status layernorm_f32_to_f32(const float* x, const float* gamma, const float* 
 wk_status encoder_attention(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream);
 // tcgen05/TMA implementation (attention_tcgen05.cu) behind encoder_attention()
 wk_status encoder_attention_tcgen05(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream);
-// second generation (attention_q2.cu): two query tiles per CTA, one thread per row, P in tensor memory
-wk_status encoder_attention_q2(const void* qkv, void* out, int B, int T, int n_heads, int dtype, cudaStream_t stream);
 wk_status transpose_to_host_layout(const void* src, float* dst, int64_t B, int64_t rows, int64_t cols, int64_t src_rows_alloc,
                                    int64_t src_row_off, int64_t src_ld, int dtype, cudaStream_t stream);
 wk_status fill_random_16(void* dst, int64_t n, uint64_t seed, float std, float mean, int dtype, cudaStream_t stream);
