@@ -1,8 +1,11 @@
 """Beam search on the GPU against oracle/beam_ref.py - SELF-ORACLE parity: the reference's BeamSearchTokenSampler is an
 unimplemented stub (TokenSampler.swift:254-290), so the specification is openai/whisper's BeamSearchDecoder inside WhisperKit's decodeText
 loop, as restated in the oracle.  The oracle loop consumes the GPU decoder's own logits (predictLogits on explicit token prefixes), so token
-IDs must match bit for bit; log-probs and the ranking score agree to 5e-4 (the oracle's logits come from single-row decodes, whose cross-attention
-keeps q and P in f32; the beam kernel carries them through the tensor cores as hi + lo 16-bit pairs, ~2^-17 relative)."""
+IDs must match bit for bit; log-probs and the ranking score agree to 5e-4 under the f16 policy and 2e-3 under bf16.  Why not tighter: the
+oracle's logits come from single-row decodes, whose cross-attention keeps q and P in f32, while the beam kernel carries them through the
+tensor cores as hi + lo 16-bit pairs (~2^-17 relative).  That difference alone is invisible, but every attention output is then rounded
+to the policy's 16-bit storage type, and a value that lands on the other side of a rounding boundary moves by one storage ulp (2^-8
+relative for bf16, 2^-11 for f16) - about 1 % of the elements do - so two correct GPU paths agree only to the policy's own precision."""
 import numpy as np
 import pytest
 
@@ -53,8 +56,9 @@ def test_beam_search_matches_the_oracle_on_gpu_logits(variant, policy, beam, pat
         ref = BR.decode_text_beam(predict, prompt, o_ref, st_o, True, beam, patience)
         dec.close()
         assert res[b].tokens == ref.tokens, (b, res[b].tokens, ref.tokens)
-        np.testing.assert_allclose(res[b].tokenLogProbs, ref.tokenLogProbs, atol=5e-4)
-        assert abs(res[b].avgLogProb - ref.avgLogProb) < 5e-4 and res[b].steps == ref.steps
+        atol = 2e-3 if policy == "bf16" else 5e-4
+        np.testing.assert_allclose(res[b].tokenLogProbs, ref.tokenLogProbs, atol=atol)
+        assert abs(res[b].avgLogProb - ref.avgLogProb) < atol and res[b].steps == ref.steps
         differs += res[b].tokens != greedy[b].tokens
     print(f"[{variant}/{policy} beam {beam} patience {patience}] windows whose beam result differs from greedy: {differs} of {n_win}")
 

@@ -13,13 +13,12 @@ cap() {  # name, kernel regex, skip, count
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o $out/$1 $PASS > $out/$1.log 2>&1
   echo "$1 rc $?" >> $out/summary.txt
 }
-cap cross_attention decoder_cross_attention 40 1
-cap decoder_chain decoder_chain_kernel 8 2
-cap encoder_gemm gemm_tcgen05_kernel 2 4          # layer 0: QKV, out-proj, FC1+GELU, FC2 (after the two conv-stem GEMMs)
+cap cross_attention decoder_cross_attention_kernel 40 1
+cap encoder_gemm gemm_tcgen05_pair_kernel 0 4     # layer 0: QKV, out-proj, FC1+GELU, FC2 (the CTA-pair kernel runs the encoder-sized products)
 cap encoder_attention encoder_attention_tcgen05 0 1
 cap mel mel_pass 0 2
 cap self_attention decoder_self_attention 700 1   # a late step of the first pass (position ~20)
 cap sampler sampler_kernel 10 1
-cap decoder_gemm_logits gemm_tcgen05_kernel 235 1  # first decoder-side GEMM launches follow the 2 + 32*4 + 1 encoder-side ones
+cap decoder_gemm gemm_tcgen05_kernel 40 1          # a decoder swap-AB split-K GEMM (the single-CTA kernel also runs the two conv-stem GEMMs first)
 ls -la $out | tail -20
 cat $out/summary.txt

@@ -57,9 +57,19 @@ struct GemmKParams {
 };
 
 // fused epilogue of one 32-column chunk of the accumulator row held by this thread (shared by the single-CTA and the CTA-pair kernels)
+// residual prefetch for GEMM_OUT_F32_ADD (out += A W^T + b): the 32 f32 values this thread will add into do not depend on the accumulator, so
+// they are loaded BEFORE the wait for the MMAs (first chunk) / while the previous chunk is processed, instead of as a dependent round
+// trip to L2 per chunk after the accumulator is ready
+__device__ __forceinline__ void gemm_prefetch_residual(const GemmKParams& p, long long grow, bool row_ok, int col_base, int c, float4 (&pre)[8]) {
+    if (p.mode != GEMM_OUT_F32_ADD || !row_ok || c >= p.bn || col_base + c >= p.n) return;
+    const float4* o4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + grow * p.ld_out + col_base + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[j] = o4[j];
+}
+
 template <typename T>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32], int split, long long grow, int row_in_batch,
-                                                    bool row_ok, int col_base, int c) {
+                                                    bool row_ok, int col_base, int c, const float4 (&pre)[8]) {
     const int col0 = col_base + c;
     if (p.mode == GEMM_OUT_PARTIAL_T) {
         if (row_ok) {
@@ -121,7 +131,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKParams& p, const 
         if (p.mode == GEMM_OUT_F32_ADD) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float4 x = o4[j];
+                float4 x = pre[j];
                 x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
                 o4[j] = x;
             }
@@ -279,17 +289,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const bool row_ok = row_in_batch < p.m_rows_per_batch;
             const long long grow = (long long)batch * p.out_rows_per_batch + row_in_batch;
 
+            const int col_base = n_tile * p.bn;
+            float4 pre[8], pre_next[8];
+            gemm_prefetch_residual(p, grow, row_ok, col_base, csub * 32, pre);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
-            const int col_base = n_tile * p.bn;
 
             for (int c = csub * 32; c < p.bn; c += 64) {
                 uint32_t r[32];
                 __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent tails below
                 tmem_ld_32x32(taddr + c, r);
+                gemm_prefetch_residual(p, grow, row_ok, col_base, c + 64, pre_next);
                 tmem_ld_wait();
-                gemm_epilogue_chunk<T>(p, r, split, grow, row_in_batch, row_ok, col_base, c);
+                gemm_epilogue_chunk<T>(p, r, split, grow, row_in_batch, row_ok, col_base, c, pre);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pre[j] = pre_next[j];
             }
             // release the accumulator stage back to the MMA warp
             tc_fence_before();
@@ -448,16 +463,21 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int row_in_batch = m_tile * kBlockM + quarter * 32 + lane;
             const bool row_ok = row_in_batch < p.m_rows_per_batch;
             const long long grow = row_in_batch;
+            const int col_base = n_tile * p.bn;
+            float4 pre[8], pre_next[8];
+            gemm_prefetch_residual(p, grow, row_ok, col_base, csub * 32, pre);
             mbar_wait_bounded(&tfull_bar[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
-            const int col_base = n_tile * p.bn;
             for (int c = csub * 32; c < p.bn; c += 64) {
                 uint32_t r[32];
                 __syncwarp();
                 tmem_ld_32x32(taddr + c, r);
+                gemm_prefetch_residual(p, grow, row_ok, col_base, c + 64, pre_next);
                 tmem_ld_wait();
-                gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c);
+                gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c, pre);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pre[j] = pre_next[j];
             }
             tc_fence_before();
             __syncwarp();
