@@ -296,15 +296,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
 
-            for (int c = csub * 32; c < p.bn; c += 64) {
+            for (int c = csub * 32; c < p.bn; c += 128) {   // two chunks per trip: the residual buffers alternate, no register copies
                 uint32_t r[32];
                 __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent tails below
                 tmem_ld_32x32(taddr + c, r);
                 gemm_prefetch_residual(p, grow, row_ok, col_base, c + 64, pre_next);
                 tmem_ld_wait();
                 gemm_epilogue_chunk<T>(p, r, split, grow, row_in_batch, row_ok, col_base, c, pre);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pre[j] = pre_next[j];
+                if (c + 64 < p.bn) {
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + c + 64, r);
+                    gemm_prefetch_residual(p, grow, row_ok, col_base, c + 128, pre);
+                    tmem_ld_wait();
+                    gemm_epilogue_chunk<T>(p, r, split, grow, row_in_batch, row_ok, col_base, c + 64, pre_next);
+                }
             }
             // release the accumulator stage back to the MMA warp
             tc_fence_before();
@@ -455,30 +460,45 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;
         const int csub = (warp - 2) >> 2;
+        // tile w -> the output row of this thread and the first output column of the tile (plain 2-D product, one batch)
+        auto tile_row = [&](int w) { return (2 * (w / p.tiles_n) + (int)rank) * kBlockM + quarter * 32 + lane; };
+        auto tile_col = [&](int w) { return (w % p.tiles_n) * p.bn; };
+        // residual values of a tile's first chunk are fetched one tile ahead (the kernel is epilogue-bound exactly when it adds into a
+        // residual: the accumulator is then ready long before this warp gets to it, and a load issued at the top of the tile would be waited
+        // for in full)
+        float4 pre[8], pre_next[8];
+        if (pair < p.work) gemm_prefetch_residual(p, tile_row(pair), tile_row(pair) < p.m_rows_per_batch, tile_col(pair), csub * 32, pre);
         int it = 0;
         for (int w = pair; w < p.work; w += n_pairs, ++it) {
             const int acc = it & 1;
-            const int n_tile = w % p.tiles_n;
-            const int m_tile = 2 * (w / p.tiles_n) + (int)rank;
-            const int row_in_batch = m_tile * kBlockM + quarter * 32 + lane;
+            const int row_in_batch = tile_row(w);
             const bool row_ok = row_in_batch < p.m_rows_per_batch;
             const long long grow = row_in_batch;
-            const int col_base = n_tile * p.bn;
-            float4 pre[8], pre_next[8];
-            gemm_prefetch_residual(p, grow, row_ok, col_base, csub * 32, pre);
+            const int col_base = tile_col(w);
+            const int wn = w + n_pairs;
+            const bool has_next = wn < p.work;
+            const int row_n = has_next ? tile_row(wn) : 0, col_n = has_next ? tile_col(wn) : 0;
             mbar_wait_bounded(&tfull_bar[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
-            for (int c = csub * 32; c < p.bn; c += 64) {
+            bool next_sent = false;
+            for (int c = csub * 32; c < p.bn; c += 128) {   // two chunks per trip: the residual buffers alternate, no register copies
                 uint32_t r[32];
                 __syncwarp();
                 tmem_ld_32x32(taddr + c, r);
                 gemm_prefetch_residual(p, grow, row_ok, col_base, c + 64, pre_next);
                 tmem_ld_wait();
                 gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c, pre);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pre[j] = pre_next[j];
+                if (c + 64 < p.bn) {
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + c + 64, r);
+                    if (c + 128 < p.bn) gemm_prefetch_residual(p, grow, row_ok, col_base, c + 128, pre);
+                    else if (has_next) { gemm_prefetch_residual(p, row_n, row_n < p.m_rows_per_batch, col_n, csub * 32, pre); next_sent = true; }
+                    tmem_ld_wait();
+                    gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c + 64, pre_next);
+                }
             }
+            if (has_next && !next_sent) gemm_prefetch_residual(p, row_n, row_n < p.m_rows_per_batch, col_n, csub * 32, pre);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
