@@ -426,6 +426,8 @@ void* wk_model_stream(wk_model* m);
 /* C[M,N] = A[M,K] * W[N,K]^T (+bias) with the tcgen05 GEMM; out_dtype WK_DTYPE_BF16/F16/F32. */
 wk_status wk_test_gemm(wk_model* m, const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
                        int32_t in_dtype, int32_t out_dtype, int32_t gelu);
+/* out[M,N] (f32, in place) += A[M,K] * W[N,K]^T + bias: the residual-update epilogue of the encoder's out-proj / FC2. */
+wk_status wk_test_gemm_residual(wk_model* m, const void* a, const void* w, const float* bias, float* out, int32_t M, int32_t N, int32_t K, int32_t in_dtype);
 /* Same product through the decoder's swap-AB split-K path: out f32 [rows_x, N]. */
 wk_status wk_test_gemm_splitk(wk_model* m, const void* w, const void* x, float* out, int32_t N, int32_t rows_x, int32_t K, int32_t in_dtype, int32_t splits);
 /* Encoder attention on packed qkv [B*T, 3*d] -> out [B*T, d]. */

@@ -63,6 +63,28 @@ def test_gemm_tcgen05_vs_torch(toy, dt, M, N, K, gelu, out32):
     assert err <= tol, f"max err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K", [(3000, 1280, 1280), (4500, 1280, 1280), (4097, 1280, 5120), (6000, 384, 384), (9000, 1280, 256)])
+def test_gemm_residual_update_in_place(toy, dt, M, N, K):
+    """out += A W^T + bias in place (the f32 residual stream; encoder out-proj / FC2), below and above the row count at which the
+    CTA-pair kernel with the staged, transposed epilogue takes over (4096), with ragged last row tiles; every element must be touched
+    exactly once (the epilogue prefetches residual values one chunk / one tile ahead)."""
+    tdt, wdt = TD[dt]
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(tdt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(tdt)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    x0 = torch.randn(M, N, device="cuda", generator=g) * 3.0
+    out = x0.clone()
+    _sync()
+    wk._lib.check(toy.lib.wk_test_gemm_residual(toy.handle, p(a), p(w), p(bias), p(out), M, N, K, wdt))
+    torch.cuda.synchronize()
+    ref = x0 + a.float() @ w.float().t() + bias
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item() * max(1, K / 256), err
+
+
 @pytest.mark.parametrize("N,rows,Kd,splits", [(1280, 64, 1280, 0), (1280, 16, 1280, 20), (3840, 64, 1280, 5),
                                               (1280, 48, 5120, 16), (51866, 32, 256, 1), (384, 16, 384, 0)])
 def test_gemm_swap_ab_splitk(toy, N, rows, Kd, splits):

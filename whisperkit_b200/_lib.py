@@ -208,6 +208,7 @@ SYMBOLS = [
     ("wk_test_cross_attention", I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
     ("wk_test_cross_attention_shared", I32, [P, P, P, P, P, I32, I32, I32, I32, P, I32]),
     ("wk_test_self_attention", I32, [P, P, P, P, P, P, I32, I32, I32, P]),
+    ("wk_test_gemm_residual", I32, [P, P, P, P, P, I32, I32, I32, I32]),
     ("wk_test_gemm_splitk", I32, [P, P, P, P, I32, I32, I32, I32, I32]),
     ("wk_test_attention", I32, [P, P, P, I32, I32, I32, I32]),
     ("wk_debug_read", I32, [P, P, I32, I64, P, I64]),

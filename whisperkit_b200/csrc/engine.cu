@@ -968,6 +968,16 @@ wk_status wk_test_gemm(wk_model* m, const void* a, const void* w, const float* b
     return WK_OK;
 }
 
+// out[M, N] (f32, in place) += A W^T + bias: the residual-update epilogue of the encoder's out-proj / FC2 (GEMM_OUT_F32_ADD)
+wk_status wk_test_gemm_residual(wk_model* m, const void* a, const void* w, const float* bias, float* out, int32_t M, int32_t N, int32_t K, int32_t in_dtype) {
+    if (!m || !a || !w || !out) return WK_ERR_INVALID_ARGUMENT;
+    WK_CUDA_CHECK(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->api_mu);
+    WK_CHECK(gemm_tcgen05(plain_gemm(a, M, K, w, N, in_dtype, GEMM_OUT_F32_ADD, out, N, bias, 0), m->num_sms, m->stream));
+    WK_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return WK_OK;
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int Bp, int N, int rows, float* __restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * N) return;

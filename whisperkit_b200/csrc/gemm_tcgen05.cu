@@ -35,6 +35,8 @@ static constexpr int kGemmThreads = 320;   // TMA warp + MMA warp + 8 epilogue w
 static constexpr int kTmemCols = 512;
 static constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 static constexpr int kMaxStages = 10;
+static constexpr int kEpiStride = 20;      // floats per staged row: 16 values + 4 pad (conflict-free 16-byte column accesses)
+static constexpr int kEpiBytes = 8 * 32 * kEpiStride * 4;   // 20 KiB
 
 struct GemmKParams {
     int tiles_per_batch, n_batches, tiles_n, splits, work;
@@ -380,6 +382,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint8_t* smem_epi = smem_tail + 512;   // 8 epilogue warps x 32 rows x kEpiStride floats: the transpose buffers of the f32 read-modify-write epilogue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();          // 0 / 1: upper / lower tile of the pair, first / second half of B
@@ -460,48 +463,113 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;
         const int csub = (warp - 2) >> 2;
-        // tile w -> the output row of this thread and the first output column of the tile (plain 2-D product, one batch)
-        auto tile_row = [&](int w) { return (2 * (w / p.tiles_n) + (int)rank) * kBlockM + quarter * 32 + lane; };
+        // tile w -> the first output row of this warp's lane quarter and the first output column of the tile (plain 2-D product, one batch)
+        auto tile_row0 = [&](int w) { return (2 * (w / p.tiles_n) + (int)rank) * kBlockM + quarter * 32; };
         auto tile_col = [&](int w) { return (w % p.tiles_n) * p.bn; };
-        // residual values of a tile's first chunk are fetched one tile ahead (the kernel is epilogue-bound exactly when it adds into a
-        // residual: the accumulator is then ready long before this warp gets to it, and a load issued at the top of the tile would be waited
-        // for in full)
-        float4 pre[8], pre_next[8];
-        if (pair < p.work) gemm_prefetch_residual(p, tile_row(pair), tile_row(pair) < p.m_rows_per_batch, tile_col(pair), csub * 32, pre);
-        int it = 0;
-        for (int w = pair; w < p.work; w += n_pairs, ++it) {
-            const int acc = it & 1;
-            const int row_in_batch = tile_row(w);
-            const bool row_ok = row_in_batch < p.m_rows_per_batch;
-            const long long grow = row_in_batch;
-            const int col_base = tile_col(w);
-            const int wn = w + n_pairs;
-            const bool has_next = wn < p.work;
-            const int row_n = has_next ? tile_row(wn) : 0, col_n = has_next ? tile_col(wn) : 0;
-            mbar_wait_bounded(&tfull_bar[acc], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
-            bool next_sent = false;
-            for (int c = csub * 32; c < p.bn; c += 128) {   // two chunks per trip: the residual buffers alternate, no register copies
-                uint32_t r[32];
-                __syncwarp();
-                tmem_ld_32x32(taddr + c, r);
-                gemm_prefetch_residual(p, grow, row_ok, col_base, c + 64, pre_next);
-                tmem_ld_wait();
-                gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c, pre);
-                if (c + 64 < p.bn) {
-                    __syncwarp();
-                    tmem_ld_32x32(taddr + c + 64, r);
-                    if (c + 128 < p.bn) gemm_prefetch_residual(p, grow, row_ok, col_base, c + 128, pre);
-                    else if (has_next) { gemm_prefetch_residual(p, row_n, row_n < p.m_rows_per_batch, col_n, csub * 32, pre); next_sent = true; }
-                    tmem_ld_wait();
-                    gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c + 64, pre_next);
+        if (p.mode == GEMM_OUT_F32_ADD) {
+            // out += A W^T + b in place (out-proj, FC2: the f32 residual stream).  A thread owns a TMEM lane = an output ROW, so storing from
+            // the accumulator registers directly means 16-byte pieces at a 5 KB stride: 32 L1 transactions per warp instruction, and the
+            // read-modify-write doubles them - measured, the epilogue of a 128x256 tile then takes longer than its 20 k-blocks of MMAs
+            // (out-proj: tensor pipe 36 %).  Here each warp transposes its 32x16 sub-chunks through a padded shared-memory buffer and
+            // touches global memory with 4 lanes per row (64 contiguous bytes): 8 transactions per instruction.  The residual values are
+            // fetched one sub-chunk pair (and, across tiles, one tile) ahead, because this kernel is epilogue-bound exactly in this mode.
+            float* stg = reinterpret_cast<float*>(smem_epi) + (warp - 2) * (32 * kEpiStride);
+            const int trow = lane >> 2, tcol = (lane & 3) * 4;       // transposed view: 8 rows x 4 float4 per pass, 4 passes per sub-chunk
+            float* out32 = reinterpret_cast<float*>(p.out);
+            auto fetch = [&](int row0, int col, float4 (&x)[8]) {   // residual of one 32-column chunk = two 16-column halves x 4 passes
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int r = row0 + (q & 3) * 8 + trow, c = col + (q >> 2) * 16 + tcol;
+                    if (r < p.m_rows_per_batch && c < p.n) x[q] = *reinterpret_cast<const float4*>(out32 + (long long)r * p.ld_out + c);
                 }
+            };
+            float4 pre[8], pre_next[8];
+            if (pair < p.work) fetch(tile_row0(pair), tile_col(pair) + csub * 32, pre);
+            int it = 0;
+            for (int w = pair; w < p.work; w += n_pairs, ++it) {
+                const int acc = it & 1;
+                const int row0 = tile_row0(w), col_base = tile_col(w);
+                const int wn = w + n_pairs;
+                const bool has_next = wn < p.work;
+                mbar_wait_bounded(&tfull_bar[acc], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
+                auto chunk = [&](int c, const float4 (&x)[8]) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + c, r);
+                    const int col0 = col_base + c;
+                    float4 bb[8];   // the chunk's 32 bias values (one broadcast address per load), in flight under the TMEM load
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        bb[j] = (p.bias && col0 + 4 * j < p.n) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        // my row's 16 values (+ bias) -> smem, then 4 passes of 8 rows x 64 bytes: add the prefetched residual, store
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b4 = bb[half * 4 + j];
+                            const float4 v = make_float4(__uint_as_float(r[half * 16 + 4 * j]) + b4.x, __uint_as_float(r[half * 16 + 4 * j + 1]) + b4.y,
+                                                         __uint_as_float(r[half * 16 + 4 * j + 2]) + b4.z, __uint_as_float(r[half * 16 + 4 * j + 3]) + b4.w);
+                            *reinterpret_cast<float4*>(stg + lane * kEpiStride + 4 * j) = v;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int rr = q * 8 + trow;
+                            const int gr = row0 + rr, gc = col0 + half * 16 + tcol;
+                            const float4 v = *reinterpret_cast<const float4*>(stg + rr * kEpiStride + tcol);
+                            if (gr < p.m_rows_per_batch && gc < p.n) {
+                                float4 o = x[half * 4 + q];
+                                o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+                                *reinterpret_cast<float4*>(out32 + (long long)gr * p.ld_out + gc) = o;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                };
+                for (int c = csub * 32; c < p.bn; c += 128) {   // two chunks per trip: the residual buffers alternate, no register copies
+                    if (c + 64 < p.bn) fetch(row0, col_base + c + 64, pre_next);
+                    else if (has_next) fetch(tile_row0(wn), tile_col(wn) + csub * 32, pre_next);
+                    chunk(c, pre);
+                    if (c + 64 < p.bn) {
+                        if (c + 128 < p.bn) fetch(row0, col_base + c + 128, pre);
+                        else if (has_next) fetch(tile_row0(wn), tile_col(wn) + csub * 32, pre);
+                        chunk(c + 64, pre_next);
+                    } else if (has_next) {
+                        // odd number of chunks: the next tile's first chunk sits in pre_next, the next trip starts from pre
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) pre[q] = pre_next[q];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
-            if (has_next && !next_sent) gemm_prefetch_residual(p, row_n, row_n < p.m_rows_per_batch, col_n, csub * 32, pre);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        } else {
+            float4 pre[8];   // (unused outside GEMM_OUT_F32_ADD)
+            int it = 0;
+            for (int w = pair; w < p.work; w += n_pairs, ++it) {
+                const int acc = it & 1;
+                const int row_in_batch = tile_row0(w) + lane;
+                const bool row_ok = row_in_batch < p.m_rows_per_batch;
+                const long long grow = row_in_batch;
+                const int col_base = tile_col(w);
+                mbar_wait_bounded(&tfull_bar[acc], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * kAccStride + ((uint32_t)(quarter * 32) << 16);
+                for (int c = csub * 32; c < p.bn; c += 64) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + c, r);
+                    tmem_ld_wait();
+                    gemm_epilogue_chunk<T>(p, r, 0, grow, row_in_batch, row_ok, col_base, c, pre);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
         }
     }
 
@@ -608,7 +676,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
     // B stage must keep 1024-byte alignment of the following A stage
     if (p.stage_b_bytes % 1024 != 0) p.stage_b_bytes = (p.stage_b_bytes + 1023) / 1024 * 1024;
     const int stage_bytes = kStageA + p.stage_b_bytes;
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - kEpiBytes /*epilogue transpose buffers*/;
     int stages = smem_budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > total_kb / p.splits + 2) stages = total_kb / p.splits + 2;
@@ -651,7 +719,7 @@ wk_status gemm_tcgen05(const GemmDesc& d, int num_sms, cudaStream_t stream) {
         st = make_tmap(&tmB, d.b, d.in_dtype, 2, dims, str, box);
         if (st != WK_OK) return st;
     }
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + kEpiBytes;
     // CTA-pair path (two 128-row tiles of one column block per cluster, weight tile multicast): plain encoder-sized GEMMs only
     if (d.pair && !d.a_3d && d.taps == 1 && p.splits == 1 && d.mode != GEMM_OUT_PARTIAL_T && d.bn % 16 == 0 && d.bn >= 32 && num_sms >= 2 &&
         p.tiles_per_batch >= 2) {
