@@ -225,7 +225,6 @@ static bool resolve_name(wk_model* m, const std::string& name, Dest* out) {
 
 // ---------------------------------------------------------------------------------------------- mel + encoder schedule
 bool gemm_pair_enabled();
-bool gemm_pair_skip_gelu();
 GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int dtype, int mode, void* out, int64_t ld_out,
                     const float* bias, int gelu) {
     GemmDesc g;
@@ -235,7 +234,7 @@ GemmDesc plain_gemm(const void* a, int64_t M, int K, const void* w, int N, int d
     g.m_rows_per_batch = (int)M; g.n = N; g.k = K; g.taps = 1;
     g.bn = N >= 256 ? 256 : round_up(N, 16);
     g.splits = 1; g.mode = mode; g.gelu = gelu; g.out = out; g.ld_out = ld_out; g.out_rows_per_batch = M; g.bias = bias;
-    g.pair = gemm_pair_enabled() && M >= 4096 && !(gelu && gemm_pair_skip_gelu());   // encoder-sized products: CTA pairs with the weight tile multicast
+    g.pair = gemm_pair_enabled() && M >= 4096;   // encoder-sized products: CTA pairs with the weight tile multicast
     return g;
 }
 
@@ -244,11 +243,6 @@ bool gemm_pair_enabled() {
     // 18.0 -> 16.3 ms, encoder pass 176.0 -> 173.8 ms at 64 windows on B200).  WKB200_GEMM_PAIR=0 (read once per process) keeps the
     // single-CTA kernel reachable for A/B timing.
     static const bool on = !(getenv("WKB200_GEMM_PAIR") && atoi(getenv("WKB200_GEMM_PAIR")) == 0);
-    return on;
-}
-
-bool gemm_pair_skip_gelu() {   // A/B switch: WKB200_GEMM_PAIR=2 keeps the epilogue-heavy FC1+GELU product on the single-CTA kernel
-    static const bool on = getenv("WKB200_GEMM_PAIR") && atoi(getenv("WKB200_GEMM_PAIR")) == 2;
     return on;
 }
 
